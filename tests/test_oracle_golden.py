@@ -1,0 +1,58 @@
+"""Pins the CPU oracle (oracle/*.c) against fixtures recorded from the live reference."""
+import numpy as np
+import pytest
+
+import oracle
+from replay_util import ALL_GAMES, check_slot, have_fixture, load_fixture, slot_records, slot_tape
+
+GAMES = [g for g in ALL_GAMES if have_fixture(g)]
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_oracle_replays_reference_tape(game):
+    fx = load_fixture(game)
+    total = 0
+    for slot in range(len(fx['slot_seed'])):
+        env = oracle.OracleEnv(game)
+        tape = slot_tape(fx, slot)
+        env.set_tape(tape)
+        total += check_slot(fx, slot, env, game)
+        assert env.tape_err() == 0
+        assert env.tape_pos() == len(tape)
+    assert total == len(fx['rec_slot'])
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_oracle_mt19937_reproduces_reference_from_seed(game):
+    """seed -> sha512 -> MT19937 -> numpy-legacy shuffle/randint/choice: the draws the oracle makes
+    from the seed alone equal the draws the reference's RandomState made."""
+    fx = load_fixture(game)
+    for slot in range(len(fx['slot_seed'])):
+        env = oracle.OracleEnv(game)
+        env.seed(int(fx['slot_seed'][slot]))
+        env.record()
+        check_slot(fx, slot, env, game + ' (mt)')
+        np.testing.assert_array_equal(env.recorded(), slot_tape(fx, slot))
+
+
+def test_philox_known_answers():
+    L = oracle.lib()
+    out = np.zeros(4, np.uint32)
+    ctr = np.zeros(4, np.uint32)
+    L.orc_philox4x32_10(ctr.ctypes.data, 0, 0, out.ctypes.data)
+    assert [hex(v) for v in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    ctr[:] = 0xffffffff
+    L.orc_philox4x32_10(ctr.ctypes.data, 0xffffffff, 0xffffffff, out.ctypes.data)
+    assert [hex(v) for v in out] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    ctr[:] = [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]
+    L.orc_philox4x32_10(ctr.ctypes.data, 0xa4093822, 0x299f31d0, out.ctypes.data)
+    assert [hex(v) for v in out] == ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+
+
+def test_seed_words():
+    """rlcard/utils/seeding.py:91-113 word split: 1-2 little-endian uint32 words of sha512(str(seed))[:8]."""
+    import hashlib, struct
+    for seed in (0, 1, 42, 12941, 2 ** 40 + 7):
+        w = oracle.seed_words(seed)
+        lo, hi = struct.unpack('2I', hashlib.sha512(str(seed).encode()).digest()[:8])
+        assert w == ([lo, hi] if hi else [lo])
