@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched simulator (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--game leduc-holdem] [--envs E] [--rollout-len T]
+  python bench.py --impl reference ...      # the CPU arm: the oracle port on the host cores
+
+One bench "step" = one pass of the hot path over the whole batch: ONE rlc_rollout_random launch that
+advances each of the E envs of this GPU by T env-steps (uniform-random legal actions, auto reset) and
+writes the full trajectory (obs + legal mask + action + player + done + payoffs) to HBM.  The
+trajectory of one step (E*T*B bytes, hundreds of MB) is larger than the 126 MB L2, so every timed
+iteration streams to DRAM.  N>1: one process per GPU (torchrun), envs sharded by global env id, no
+collective on the step path; the only reduction is the end-of-run episode statistics.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_ENVS = {'blackjack': 65536, 'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384,
+                'doudizhu': 8192, 'scout': 8192}
+METRIC = 'env steps/sec (random policy, obs+mask)'
+UNIT = 'env-steps/s'
+
+
+def algorithmic_bytes_per_env_step(info, obs_elem, T):
+    """B = O + M + 4 (action) + 4 (player) + 1 (done) + 4P (payoffs) per env-step, plus the
+    packed state read+written once per launch (amortised over the T steps of the launch)."""
+    O = info.obs_stride * obs_elem
+    M = info.mask_words * 4 if info.mask_bitpacked else info.num_actions
+    per_step = O + M + 4 + 4 + 1 + 4 * info.num_players
+    state = 2 * 4 * info.state_words
+    return per_step + state / float(T), per_step, state
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksEventReasonSwPowerCap: 'sw_power_cap'} if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown') else {
+                 nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap'}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+def cpu_port_run(game, envs, T, seed, threads, budget_s=12.0):
+    """The oracle (C port of the reference algorithm) on the host cores: bounded sample of the same
+    workload (same Philox chance/policy, trajectories written to host memory)."""
+    import numpy as np
+    import oracle
+    n = min(envs, 8192)
+    v = oracle.OracleVec(game, n, seed)
+    L = v.L
+    P, A = v.num_players, v.num_actions
+    obs = np.zeros((T, n, v.obs_stride), np.float32)
+    mask = np.zeros((T, n, A), np.uint8)
+    act = np.zeros((T, n), np.int32); pl = np.zeros((T, n), np.int32)
+    done = np.zeros((T, n), np.uint8); pay = np.zeros((T, n, P), np.float32)
+    args = (v.h, T, obs.ctypes.data, v.obs_stride, mask.ctypes.data, act.ctypes.data, pl.ctypes.data,
+            done.ctypes.data, pay.ctypes.data, threads)
+    L.orc_envs_rollout(*args)                      # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        steps += L.orc_envs_rollout(*args)
+        dt = time.perf_counter() - t0
+        if dt > budget_s or steps >= 400_000_000:
+            break
+    return steps / dt, dt, steps, n
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores (the C oracle port of
+    the reference algorithm; the Python reference itself cannot travel to the GPU box)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    T = args.rollout_len
+    per = []
+    t_all = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt, steps, n = cpu_port_run(args.game, args.envs, T, args.seed, threads, budget_s=6.0)
+        per.append(v)
+    value = sum(per) / len(per)
+    sample = '%d envs x %d-step launches, uniform-random legal policy, obs f32 + mask written to host RAM, %d threads' % (
+        min(args.envs, 8192), T, threads)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * args.envs * T / value, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+            'config': {'workload': '%s, %d envs per GPU, %d env-steps per launch' % (args.game, args.envs, T)},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'wall_s': time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--game', default='leduc-holdem')
+    ap.add_argument('--envs', type=int, default=None, help='envs per GPU')
+    ap.add_argument('--rollout-len', type=int, default=128, help='env-steps per env per launch (T)')
+    ap.add_argument('--obs-dtype', default=None, choices=['uint8', 'float32'])
+    ap.add_argument('--seed', type=int, default=20261018)
+    ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.envs is None:
+        args.envs = DEFAULT_ENVS[args.game]
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import rlcard_b200
+    from rlcard_b200 import _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    info = rlcard_b200.game_info(args.game)
+    if args.obs_dtype is None:
+        args.obs_dtype = 'float32' if info.obs_native_dtype == _lib.DTYPE_F32 else 'uint8'
+    odt = torch.float32 if args.obs_dtype == 'float32' else torch.uint8
+    E, T, K, W = args.envs, args.rollout_len, args.steps, args.warmup
+
+    env = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed, env_id_base=rank * E, obs_dtype=odt)
+    env.reset()
+    traj = env.alloc_trajectory(T)
+    L = rlcard_b200.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        env.rollout_random(T, out=traj)
+    barrier()
+    cvd = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+    ids = [x for x in cvd.split(',') if x.strip().isdigit()]
+    sampler = ClockSampler(int(ids[local]) if len(ids) > local else local)
+    sampler.start()
+    launches0 = L.rlc_launch_count()
+    stream = torch.cuda.current_stream(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(K):
+        env.rollout_random(T, out=traj)
+        ev[k + 1].record(stream)
+    barrier()
+    launches = L.rlc_launch_count() - launches0
+    elapsed_ms = ev[0].elapsed_time(ev[K])
+    kernel_ms = sum(ev[k].elapsed_time(ev[k + 1]) for k in range(K)) / K
+    # keep the GPU under the same load a little longer so the clock record has enough samples
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        env.rollout_random(T, out=traj)
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    env.check_errors()
+
+    # episode statistics: the only cross-GPU reduction of the whole path
+    done = traj['done'].bool()
+    stats = torch.cat([(traj['payoffs'] * done.unsqueeze(-1)).sum((0, 1)).double(),
+                       done.sum().double().reshape(1), torch.tensor([float(E * T)], device=dev, dtype=torch.float64)])
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    value = world * E * T * K / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: a host-resident agent picks a uniform legal
+    # action from the mask it received (numpy), actions go H2D from pinned memory, Env.step runs, and obs /
+    # mask / player / done / payoffs come back D2H into pinned memory, every step.
+    e2e = None
+    if info.num_actions == 4:
+        Ke = args.e2e_steps
+        env2 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 1, env_id_base=rank * E, obs_dtype=odt)
+        h_act = torch.zeros(E, dtype=torch.int32).pin_memory()
+        h_obs = torch.zeros((E, info.obs_stride), dtype=odt).pin_memory()
+        h_mask = torch.zeros((E, 4), dtype=torch.uint8).pin_memory()
+        h_cur = torch.zeros(E, dtype=torch.int32).pin_memory()
+        h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
+        h_pay = torch.zeros((E, info.num_players), dtype=torch.float32).pin_memory()
+        d_act = torch.zeros(E, dtype=torch.int32, device=dev)
+        # k-th legal action LUT: code = 4 mask bits, r uniform in [0,12) (12 = lcm(1..4)) -> exact uniform
+        lut = np.zeros((16, 12), np.int32)
+        for code in range(1, 16):
+            ids = [a for a in range(4) if (code >> a) & 1]
+            for r in range(12):
+                lut[code, r] = ids[r % len(ids)]
+        rng = np.random.default_rng(args.seed)
+        rnd = rng.integers(0, 12, size=(Ke + W, E), dtype=np.int64)
+        m32 = h_mask.numpy().view(np.uint32).reshape(E)
+
+        def host_step(i):
+            code = ((m32.astype(np.uint64) * np.uint64(0x01020408)) >> np.uint64(24)) & np.uint64(15)
+            np.take(lut.reshape(-1), code.astype(np.int64) * 12 + rnd[i], out=h_act.numpy())
+            d_act.copy_(h_act, non_blocking=True)
+            env2.step(d_act)
+            h_obs.copy_(env2.obs, non_blocking=True); h_mask.copy_(env2.mask, non_blocking=True)
+            h_cur.copy_(env2.cur_player, non_blocking=True); h_done.copy_(env2.done, non_blocking=True)
+            h_pay.copy_(env2.payoffs, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        env2.reset()
+        h_mask.copy_(env2.mask); torch.cuda.synchronize(dev)
+        for i in range(W):
+            host_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            host_step(W + i)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        d2h = sum(x.numel() * x.element_size() for x in (h_obs, h_mask, h_cur, h_done, h_pay))
+        e2e = {'value': world * E * Ke / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h_act.numel() * 4,
+               'd2h_bytes_per_step': d2h, 'steps': Ke,
+               'what': 'VecEnv.step per env-step: numpy uniform-legal policy on host -> H2D actions (pinned) -> '
+                       'rlc_step -> D2H obs+mask+player+done+payoffs (pinned), synchronous round trip'}
+        env2.check_errors()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'MEASURED_PEAKS.json hbm_gbs (measured)'
+    else:
+        peak, peak_src = 6650.0, 'B200_PROFILING.md fallback'
+    b_step, per_step, state_b = algorithmic_bytes_per_env_step(info, 4 if odt == torch.float32 else 1, T)
+    achieved = E * T * b_step / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('%s:%s:%d:%d' % (args.game, args.obs_dtype, E, T))
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': '%s, %d envs per GPU, obs %s[%d] + legal mask u8[%d] + action/player/done/payoffs per '
+                               'env-step' % (args.game, E, args.obs_dtype, info.obs_stride, info.num_actions),
+                   'envs_per_gpu': E, 'env_steps_per_launch_per_env': T, 'policy': 'uniform-random legal (Philox, on device)',
+                   'chance': 'Philox4x32-10 keyed (seed, global env id, episode)', 'auto_reset': True,
+                   'l2': 'trajectory written per launch = %.0f MB > 126 MB L2' % (E * T * per_step / 1e6)},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': traffic, 'kernel': 'k_rollout<%s>' % args.game, 'kernel_ms': kernel_ms,
+                     'bytes_per_env_step': b_step, 'peak_source': peak_src},
+        'episodes_last_launch': float(stats[info.num_players].item()),
+        'mean_payoff_per_seat': [float(x) / max(1.0, float(stats[info.num_players].item())) for x in stats[:info.num_players]],
+    }
+    if e2e:
+        line['e2e'] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, dt, steps, n = cpu_port_run(args.game, E, T, args.seed, threads)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': '%d env-steps in %.1f s: %d envs x %d-step launches of the C oracle, same Philox '
+                                          'chance + policy, obs f32 + mask to host RAM' % (steps, dt, n, T)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,142 @@
+/*
+ * rlcard_b200.h -- C ABI of the B200-native batched card-game simulator.
+ *
+ * This is the drop-in boundary for the reference's Env hot path
+ * (rlcard/envs/env.py:52-231 reset/step/get_state/get_payoffs/run and the
+ * per-game envs + engines under rlcard/envs/<game>.py, rlcard/games/<game>/).
+ * Plain pointers and sizes only; all per-env memory is owned by the caller
+ * (torch tensors on the Python side) and lives in HBM.  Every entry point
+ * returns 0 or a negative rlc_status; rlc_last_error() describes the failure.
+ * All launches are asynchronous on the caller's stream (a cudaStream_t passed
+ * as void*; NULL = legacy default stream).
+ *
+ * Layouts (n = number of envs of this call, P players, A actions):
+ *   state     uint32 [state_words][n]   struct-of-arrays, opaque (rlc_game_info.state_words)
+ *   obs       obs_t  [n][obs_stride]    row = the reference's exact obs layout of the seat's
+ *                                       _extract_state, zero padded to obs_stride (max seat dim)
+ *   mask      uint8  [n][A]             1 = legal (games with A <= 256)
+ *             uint32 [n][mask_words]    bit a%32 of word a/32 (DouDizhu, A = 27472)
+ *   cur_player int32 [n], done uint8 [n], payoffs float [n][P], err int32 [n]
+ *   rollout trajectories carry a leading [T] dimension over the same rows.
+ */
+#ifndef RLCARD_B200_H
+#define RLCARD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLC_ABI_VERSION 1
+#define RLC_MAX_PLAYERS 4
+
+/* env ids of rlcard/envs/__init__.py:6-54 covered by this library */
+enum rlc_game {
+    RLC_BLACKJACK = 0,   /* 'blackjack'     */
+    RLC_LEDUC = 1,       /* 'leduc-holdem'  */
+    RLC_LIMIT = 2,       /* 'limit-holdem'  */
+    RLC_UNO = 3,         /* 'uno'           */
+    RLC_DOUDIZHU = 4,    /* 'doudizhu'      */
+    RLC_SCOUT = 5,       /* 'scout'         */
+    RLC_NUM_GAMES = 6
+};
+
+enum rlc_status {
+    RLC_OK = 0, RLC_EINVAL = -1, RLC_ENOTIMPL = -2, RLC_ECUDA = -3, RLC_ENOTABLE = -4
+};
+
+/* where the engines' bounded random draws come from (replaces game.np_random, env.py:228-231) */
+enum rlc_chance {
+    RLC_CHANCE_PHILOX = 0,   /* throughput: Philox4x32-10 keyed (seed, global env id, episode) */
+    RLC_CHANCE_TAPE = 1,     /* replay: recorded np.random draws, uint8 tape per env          */
+    RLC_CHANCE_MT19937 = 2   /* replay from a seed: np.random.RandomState on device           */
+};
+
+enum rlc_dtype { RLC_U8 = 0, RLC_F32 = 1 };
+
+enum rlc_step_flags {
+    RLC_AUTO_RESET = 1,      /* deal the next episode inside the step that ends one          */
+    RLC_TERMINAL_OBS = 2     /* also write every seat's terminal get_state (env.py:161-164)  */
+};
+
+typedef struct rlc_info {
+    int32_t game_id, num_players, num_actions;
+    int32_t obs_dim[RLC_MAX_PLAYERS];   /* state_shape per seat (e.g. doudizhu 790/901/901) */
+    int32_t obs_stride;                 /* elements per obs row                              */
+    int32_t obs_native_dtype;           /* rlc_dtype the reference values fit losslessly      */
+    int32_t mask_bitpacked;             /* 0: uint8 [n][A]; 1: uint32 [n][mask_words]         */
+    int32_t mask_words;
+    int32_t state_words;                /* uint32 words per env                               */
+    int32_t max_tape_draws_reset;       /* draws a reset can consume (tape sizing aid)        */
+    int32_t threads_per_env;            /* 1 (thread per env) or 32 (warp per env)            */
+    int32_t reserved[4];
+} rlc_info;
+
+typedef struct rlc_buffers {
+    uint32_t *state;          /* [state_words][n]                                             */
+    /* chance source */
+    int32_t chance;           /* rlc_chance                                                   */
+    uint64_t seed;            /* PHILOX key                                                   */
+    uint32_t env_id_base;     /* PHILOX: global id of env 0 of this buffer (multi-GPU shards) */
+    const uint8_t *tape;      /* TAPE: [n][tape_stride] draw outcomes                         */
+    int32_t tape_stride;
+    int32_t *tape_pos;        /* TAPE: [n] cursor (in/out)                                    */
+    uint32_t *mt;             /* MT19937: [625][n] (624 state words + index), in/out          */
+    /* outputs */
+    void *obs;                /* [n][obs_stride] of obs_dtype                                 */
+    int32_t obs_dtype;        /* rlc_dtype                                                    */
+    void *mask;               /* see header comment                                           */
+    int32_t *cur_player;      /* [n]                                                          */
+    uint8_t *done;            /* [n]                                                          */
+    float *payoffs;           /* [n][P]                                                       */
+    void *terminal_obs;       /* [n][P][obs_stride], written for done envs when RLC_TERMINAL_OBS */
+    int32_t *err;             /* [n] sticky bit flags: 1 tape exhausted, 2 tape value out of range,
+                                 4 illegal action replaced by the reference's fallback         */
+} rlc_buffers;
+
+/* trajectory buffers of rlc_rollout_random: [T][n][...], any pointer may be NULL */
+typedef struct rlc_trajectory {
+    void *obs;                /* [T][n][obs_stride] obs the acting player saw (obs_dtype of rlc_buffers) */
+    void *mask;               /* [T][n][A] or [T][n][mask_words]                              */
+    int32_t *action;          /* [T][n] action id taken                                       */
+    int32_t *player;          /* [T][n] acting player                                         */
+    uint8_t *done;            /* [T][n] episode ended with this action                        */
+    float *payoffs;           /* [T][n][P] payoffs when done else 0                           */
+} rlc_trajectory;
+
+int rlc_abi_version(void);
+const char *rlc_last_error(void);
+
+/* rlcard.make() metadata: Env.num_players/num_actions/state_shape (env.py:41-43) */
+int rlc_game_info(int game_id, rlc_info *out);
+
+/* constant rule tables (DouDizhu action table = games/doudizhu/jsondata.zip, utils.py:14-38),
+ * uploaded once per device; blob format in DESIGN.md */
+int rlc_upload_tables(int game_id, int device, const void *blob, size_t nbytes);
+
+/* Env.reset (env.py:52-63) for envs with reset_mask[i] != 0 (NULL = all): deal, first state,
+ * writes obs/mask/cur_player/done=0.  state must be zero-initialised before the first reset. */
+int rlc_reset(int game_id, const rlc_buffers *b, int n, const uint8_t *reset_mask, void *stream);
+
+/* Env.step (env.py:65-86) for every env: actions[i] < 0 = leave env i untouched.  Writes the next
+ * state's obs/mask/cur_player, done and payoffs (Env.get_payoffs, env.py:199-207). */
+int rlc_step(int game_id, const rlc_buffers *b, const int32_t *actions, int n, int flags, void *stream);
+
+/* Env.get_state(player_id) (env.py:188-197): obs/mask as seen by seat[i] (NULL = current player);
+ * also refreshes cur_player/done/payoffs. */
+int rlc_observe(int game_id, const rlc_buffers *b, const int32_t *seat, int n, void *stream);
+
+/* The Env.run loop with RandomAgents (env.py:120-169, agents/random_agent.py:17-27) fused on
+ * device: k_steps env-steps per env, uniform-random legal actions from the Philox policy stream,
+ * auto reset.  Trajectory rows as documented above. */
+int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *traj, int n, int k_steps,
+                       void *stream);
+
+/* number of kernels this library has launched in this process (bench bookkeeping) */
+int64_t rlc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,81 @@
+"""ctypes binding of the C-ABI CUDA library (include/rlcard_b200.h).
+
+There is no CPU fallback: if ``librlcard_b200.so`` is missing or fails to load, importing
+any compute entry point raises.  Build it with ``python -c 'import __graft_entry__ as g; g.build()'``
+or ``make -C rlcard_b200/csrc -j``.
+"""
+import ctypes as C
+import os
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_DIR, 'librlcard_b200.so')
+
+RLC_MAX_PLAYERS = 4
+GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5}
+CHANCE_PHILOX, CHANCE_TAPE, CHANCE_MT19937 = 0, 1, 2
+DTYPE_U8, DTYPE_F32 = 0, 1
+AUTO_RESET, TERMINAL_OBS = 1, 2
+
+
+class RlcInfo(C.Structure):
+    _fields_ = [('game_id', C.c_int32), ('num_players', C.c_int32), ('num_actions', C.c_int32),
+                ('obs_dim', C.c_int32 * RLC_MAX_PLAYERS), ('obs_stride', C.c_int32),
+                ('obs_native_dtype', C.c_int32), ('mask_bitpacked', C.c_int32), ('mask_words', C.c_int32),
+                ('state_words', C.c_int32), ('max_tape_draws_reset', C.c_int32), ('threads_per_env', C.c_int32),
+                ('reserved', C.c_int32 * 4)]
+
+
+class RlcBuffers(C.Structure):
+    _fields_ = [('state', C.c_void_p), ('chance', C.c_int32), ('seed', C.c_uint64), ('env_id_base', C.c_uint32),
+                ('tape', C.c_void_p), ('tape_stride', C.c_int32), ('tape_pos', C.c_void_p), ('mt', C.c_void_p),
+                ('obs', C.c_void_p), ('obs_dtype', C.c_int32), ('mask', C.c_void_p), ('cur_player', C.c_void_p),
+                ('done', C.c_void_p), ('payoffs', C.c_void_p), ('terminal_obs', C.c_void_p), ('err', C.c_void_p)]
+
+
+class RlcTrajectory(C.Structure):
+    _fields_ = [('obs', C.c_void_p), ('mask', C.c_void_p), ('action', C.c_void_p), ('player', C.c_void_p),
+                ('done', C.c_void_p), ('payoffs', C.c_void_p)]
+
+
+EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
+           'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count']
+
+_LIB = None
+
+
+class RlcError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA extension; raises (no fallback) when it is not built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RlcError('CUDA extension %s is not built (run __graft_entry__.build()); there is no CPU fallback'
+                           % SO_PATH)
+        L = C.CDLL(SO_PATH)
+        vp, i32 = C.c_void_p, C.c_int
+        L.rlc_abi_version.restype = i32
+        L.rlc_last_error.restype = C.c_char_p
+        L.rlc_launch_count.restype = C.c_int64
+        L.rlc_game_info.argtypes = [i32, C.POINTER(RlcInfo)]
+        L.rlc_upload_tables.argtypes = [i32, i32, vp, C.c_size_t]
+        L.rlc_reset.argtypes = [i32, C.POINTER(RlcBuffers), i32, vp, vp]
+        L.rlc_step.argtypes = [i32, C.POINTER(RlcBuffers), vp, i32, i32, vp]
+        L.rlc_observe.argtypes = [i32, C.POINTER(RlcBuffers), vp, i32, vp]
+        L.rlc_rollout_random.argtypes = [i32, C.POINTER(RlcBuffers), C.POINTER(RlcTrajectory), i32, i32, vp]
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise RlcError('rlcard_b200 C-ABI call failed (%d): %s' % (rc, lib().rlc_last_error().decode()))
+
+
+def game_info(game):
+    gid = GAME_IDS[game] if isinstance(game, str) else int(game)
+    info = RlcInfo()
+    check(lib().rlc_game_info(gid, C.byref(info)))
+    return info

@@ -1,0 +1,268 @@
+// game_poker.cuh -- Leduc Hold'em and Limit Texas Hold'em (2 players) as register-resident
+// state machines, one env per thread.  Reference: rlcard/games/leducholdem/*, rlcard/games/
+// limitholdem/* (round.py is shared), rlcard/envs/{leducholdem,limitholdem}.py.
+#pragma once
+#include "common.cuh"
+
+namespace rlc {
+
+enum { kCall = 0, kRaise = 1, kFold = 2, kCheck = 3 };   // envs/leducholdem.py:26
+
+// games/limitholdem/round.py as plain registers (2 players)
+struct BetRound {
+    int pointer, have_raised, not_raise_num, raised0, raised1;
+    __device__ __forceinline__ void start(int p, int r0, int r1) {          // round.py:35-51
+        pointer = p; have_raised = 0; not_raise_num = 0; raised0 = r0; raised1 = r1;
+    }
+    __device__ __forceinline__ uint32_t legal(int allowed) const {          // round.py:95-116
+        const int mx = max(raised0, raised1), mine = pointer ? raised1 : raised0;
+        uint32_t m = 0xFu;
+        if (have_raised >= allowed) m &= ~(1u << kRaise);
+        if (mine < mx) m &= ~(1u << kCheck);
+        if (mine == mx) m &= ~(1u << kCall);
+        return m;
+    }
+    // round.py:53-93; returns chips the actor adds, sets folded flag of the actor
+    __device__ __forceinline__ int proceed(int action, int raise_amount, bool &fold) {
+        const int mx = max(raised0, raised1), mine = pointer ? raised1 : raised0;
+        int diff = 0; fold = false;
+        if (action == kCall) { diff = mx - mine; not_raise_num++; }
+        else if (action == kRaise) { diff = mx - mine + raise_amount; have_raised++; not_raise_num = 1; }
+        else if (action == kFold) fold = true;
+        else not_raise_num++;
+        if (pointer) raised1 += diff; else raised0 += diff;
+        pointer ^= 1;     // 2 players: the other seat is never the folded one
+        return diff;
+    }
+};
+
+// ========================================================================================
+// Leduc: 32-bit packed state.
+//  [0:2) hand0 rank  [2:4) hand1 rank  [4:6) public rank (pre-drawn third pop)  [6] public dealt
+//  [7:11) chips0 [11:15) chips1 [15:19) raised0 [19:23) raised1 [23:25) have_raised
+//  [25:27) not_raise_num [27] pointer [28:30) round_counter [30] folded0 [31] folded1
+// ========================================================================================
+struct Leduc {
+    static constexpr int kGameId = 1, P = 2, A = 4, OBS = 36, GAME_WORDS = 1, MASK_WORDS = 1;
+    static constexpr int kMaxResetDraws = 6;
+    int hand0, hand1, pub, pub_dealt, chips0, chips1, rc, fold0, fold1;
+    BetRound r;
+
+    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) {
+        const uint32_t w = st[i];
+        hand0 = bf_get(w, 0, 2); hand1 = bf_get(w, 2, 2); pub = bf_get(w, 4, 2); pub_dealt = bf_get(w, 6, 1);
+        chips0 = bf_get(w, 7, 4); chips1 = bf_get(w, 11, 4); r.raised0 = bf_get(w, 15, 4); r.raised1 = bf_get(w, 19, 4);
+        r.have_raised = bf_get(w, 23, 2); r.not_raise_num = bf_get(w, 25, 2); r.pointer = bf_get(w, 27, 1);
+        rc = bf_get(w, 28, 2); fold0 = bf_get(w, 30, 1); fold1 = bf_get(w, 31, 1);
+        (void)n;
+    }
+    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const {
+        st[i] = hand0 | (hand1 << 2) | (pub << 4) | (pub_dealt << 6) | (chips0 << 7) | (chips1 << 11) |
+                (r.raised0 << 15) | (r.raised1 << 19) | (r.have_raised << 23) | (r.not_raise_num << 25) |
+                (r.pointer << 27) | (rc << 28) | (fold0 << 30) | ((uint32_t)fold1 << 31);
+        (void)n;
+    }
+    // games/leducholdem/game.py:46-95; deck [SJ,HJ,SQ,HQ,SK,HK] (dealer.py:10) kept as nibbles
+    template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
+        uint32_t deck = 0x543210u;
+#pragma unroll
+        for (int i = 5; i >= 3; i--) {                       // pops take positions 5,4,3 only
+            const int j = (int)ch.below((uint32_t)i + 1u);
+            const uint32_t a = (deck >> (4 * i)) & 15u, b = (deck >> (4 * j)) & 15u, x = a ^ b;
+            deck ^= (x << (4 * i)) | (x << (4 * j));
+        }
+        ch.skip_fy(2, 1);
+        hand0 = (deck >> 21) & 3; hand1 = (deck >> 17) & 3; pub = (deck >> 13) & 3; pub_dealt = 0;   // rank = card>>1
+        const int sb = (int)ch.below(2u);
+        chips0 = sb == 0 ? 1 : 2; chips1 = sb == 0 ? 2 : 1;
+        fold0 = fold1 = 0; rc = 0;
+        r.start(sb, chips0, chips1);
+    }
+    __device__ __forceinline__ int raise_amount() const { return rc == 0 ? 2 : 4; }   // game.py:36,129
+    __device__ __forceinline__ void legal(uint32_t (&m)[1]) const { m[0] = r.legal(2); }
+    __device__ __forceinline__ int player() const { return r.pointer; }
+    __device__ __forceinline__ bool over() const { return (fold0 + fold1 == 1) || rc >= 2; }   // game.py:154-168
+    // env.py:65-86, envs/leducholdem.py:81-96, game.py:97-136
+    template <class Ch> __device__ __forceinline__ void step(int id, Ch &, int &err) {
+        const uint32_t m = r.legal(2);
+        int action = id;
+        if (id < 0 || id > 3 || !((m >> id) & 1u)) { action = ((m >> kCheck) & 1u) ? kCheck : kFold; err |= 4; }
+        const int actor = r.pointer;
+        bool fold;
+        const int diff = r.proceed(action, raise_amount(), fold);
+        if (actor) { chips1 += diff; fold1 |= fold; } else { chips0 += diff; fold0 |= fold; }
+        if (r.not_raise_num >= 2) {
+            if (rc == 0) pub_dealt = 1;
+            rc++;
+            r.start(r.pointer, 0, 0);
+        }
+    }
+    // games/leducholdem/judger.py:12-64, game.py:170-178 (chips / big blind)
+    __device__ __forceinline__ void payoffs(float *out) const {
+        int w0, w1;
+        if (fold0 + fold1 == 1) { w0 = fold1; w1 = fold0; }
+        else if (pub_dealt && hand0 == pub) { w0 = 1; w1 = 0; }
+        else if (pub_dealt && hand1 == pub) { w0 = 0; w1 = 1; }
+        else { w0 = hand0 >= hand1; w1 = hand1 >= hand0; }
+        const float each = (float)(chips0 + chips1) / (float)(w0 + w1);
+        out[0] = (w0 ? each - (float)chips0 : -(float)chips0) * 0.5f;
+        out[1] = (w1 ? each - (float)chips1 : -(float)chips1) * 0.5f;
+    }
+    // envs/leducholdem.py:41-71 (row is pre-zeroed)
+    template <class T> __device__ __forceinline__ void encode_obs(int seat, bool, T *row) const {
+        const int mine = seat ? chips1 : chips0, other = seat ? chips0 : chips1;
+        row[seat ? hand1 : hand0] = (T)1;
+        if (pub_dealt) row[3 + pub] = (T)1;
+        row[6 + mine] = (T)1;
+        row[21 + other] = (T)1;
+    }
+};
+
+// ========================================================================================
+// 7-card evaluator on rank/suit bit masks (orders hands like games/limitholdem/utils.py
+// compare_hands).  card id = 13*suit + rank (A=0, 2..K = 1..12).
+// ========================================================================================
+__device__ __forceinline__ uint32_t top_bits(uint32_t m, int keep) {   // keep the `keep` highest set bits
+    while (__popc(m) > keep) m &= m - 1;
+    return m;
+}
+__device__ __forceinline__ int straight_top(uint32_t m) {   // m bit r = rank (2->0 .. A->12); 0 = none, else top+1
+    const uint32_t x = (m << 1) | ((m >> 12) & 1u);          // bit0 = ace playing low
+    const uint32_t run = x & (x >> 1) & (x >> 2) & (x >> 3) & (x >> 4);
+    return run ? (32 - __clz(run)) + 3 : 0;                  // top bit index in x (1-based rank), 5-high wheel -> 4
+}
+__device__ __forceinline__ uint32_t holdem_strength7(const int (&c)[7]) {
+    uint32_t s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        const int suit = c[i] / 13, rk = c[i] - 13 * suit;
+        const uint32_t bit = 1u << ((rk + 12) % 13);
+        s[0] |= suit == 0 ? bit : 0u; s[1] |= suit == 1 ? bit : 0u;
+        s[2] |= suit == 2 ? bit : 0u; s[3] |= suit == 3 ? bit : 0u;
+    }
+    const uint32_t any = s[0] | s[1] | s[2] | s[3];
+    uint32_t fl = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (__popc(s[k]) >= 5) fl = s[k];
+    if (fl) { const int t = straight_top(fl); if (t) return (9u << 26) | (uint32_t)t; }
+    const uint32_t x4 = s[0] & s[1] & s[2] & s[3];
+    const uint32_t x3 = ((s[0] & s[1] & s[2]) | (s[0] & s[1] & s[3]) | (s[0] & s[2] & s[3]) | (s[1] & s[2] & s[3])) & ~x4;
+    const uint32_t x2 = ((s[0] & s[1]) | (s[0] & s[2]) | (s[0] & s[3]) | (s[1] & s[2]) | (s[1] & s[3]) | (s[2] & s[3])) & ~x3 & ~x4;
+    if (x4) {
+        const uint32_t q = 31 - __clz(x4), k = 31 - __clz(any & ~(1u << q));
+        return (8u << 26) | (q << 4) | k;
+    }
+    if (x3 && ((x3 & (x3 - 1)) || x2)) {
+        const uint32_t t = 31 - __clz(x3), rest = (x3 & ~(1u << t)) | x2, p = 31 - __clz(rest);
+        return (7u << 26) | (t << 4) | p;
+    }
+    if (fl) return (6u << 26) | top_bits(fl, 5);
+    { const int t = straight_top(any); if (t) return (5u << 26) | (uint32_t)t; }
+    if (x3) { const uint32_t t = 31 - __clz(x3); return (4u << 26) | (t << 13) | top_bits(any & ~(1u << t), 2); }
+    if (x2 & (x2 - 1)) {
+        const uint32_t hi = 31 - __clz(x2), lo = 31 - __clz(x2 & ~(1u << hi));
+        return (3u << 26) | (hi << 17) | (lo << 13) | top_bits(any & ~(1u << hi) & ~(1u << lo), 1);
+    }
+    if (x2) { const uint32_t p = 31 - __clz(x2); return (2u << 26) | (p << 13) | top_bits(any & ~(1u << p), 3); }
+    return (1u << 26) | top_bits(any, 5);
+}
+
+// ========================================================================================
+// Limit Hold'em: 4 game words.
+//  w0: cards 0..4 (6 bits each): hole p0a, p1a, p0b, p1b (deal order game.py:68-69), flop0
+//  w1: flop1, flop2, turn, river (6 bits each) | have_raised [24:27) | not_raise_num [27:29) |
+//      pointer [29] | folded0 [30] | folded1 [31]
+//  w2: chips0 [0:6) chips1 [6:12) raised0 [12:17) raised1 [17:22) round_counter [22:25)
+//  w3: raise_nums 4x3 bits [0:12) | raise_nums shown by the reset() state (Q-LH1) [12:24)
+// ========================================================================================
+struct Limit {
+    static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
+    static constexpr int kMaxResetDraws = 52;
+    int card[9];           // 0,2 = p0 hole; 1,3 = p1 hole; 4..8 board in deal order
+    int chips0, chips1, rc, fold0, fold1;
+    uint32_t rn, rn_shown;  // 4 x 3-bit raise counters
+    BetRound r;
+
+    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) {
+        const uint32_t w0 = st[i], w1 = st[n + i], w2 = st[2 * n + i], w3 = st[3 * n + i];
+#pragma unroll
+        for (int k = 0; k < 5; k++) card[k] = bf_get(w0, 6 * k, 6);
+#pragma unroll
+        for (int k = 0; k < 4; k++) card[5 + k] = bf_get(w1, 6 * k, 6);
+        r.have_raised = bf_get(w1, 24, 3); r.not_raise_num = bf_get(w1, 27, 2); r.pointer = bf_get(w1, 29, 1);
+        fold0 = bf_get(w1, 30, 1); fold1 = bf_get(w1, 31, 1);
+        chips0 = bf_get(w2, 0, 6); chips1 = bf_get(w2, 6, 6); r.raised0 = bf_get(w2, 12, 5); r.raised1 = bf_get(w2, 17, 5);
+        rc = bf_get(w2, 22, 3);
+        rn = w3 & 0xfffu; rn_shown = (w3 >> 12) & 0xfffu;
+    }
+    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const {
+        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) w0 |= (uint32_t)card[k] << (6 * k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) w1 |= (uint32_t)card[5 + k] << (6 * k);
+        w1 |= (r.have_raised << 24) | (r.not_raise_num << 27) | (r.pointer << 29) | (fold0 << 30) | ((uint32_t)fold1 << 31);
+        st[i] = w0; st[n + i] = w1;
+        st[2 * n + i] = chips0 | (chips1 << 6) | (r.raised0 << 12) | (r.raised1 << 17) | (rc << 22);
+        st[3 * n + i] = rn | (rn_shown << 12);
+    }
+    // games/limitholdem/game.py:46-103: only the last 9 deck positions are ever popped
+    template <class Ch> __device__ void reset(Ch &ch) {
+        uint8_t deck[52];
+#pragma unroll
+        for (int i = 0; i < 52; i++) deck[i] = (uint8_t)i;     // utils.py:34-43 order == card2index.json
+        shuffle_tail_u8(ch, deck, 52, 9);
+#pragma unroll
+        for (int k = 0; k < 9; k++) card[k] = deck[51 - k];
+        const int sb = (int)ch.below(2u);
+        chips0 = sb == 0 ? 1 : 2; chips1 = sb == 0 ? 2 : 1;
+        fold0 = fold1 = 0; rc = 0;
+        r.start(sb, chips0, chips1);                          // (bb+1)%2 == sb for two players (game.py:81)
+        rn_shown = rn;                                        // Q-LH1: reset() state shows the old list (game.py:98 vs :101)
+        rn = 0;
+    }
+    __device__ __forceinline__ int n_public() const { return rc == 0 ? 0 : (rc == 1 ? 3 : (rc == 2 ? 4 : 5)); }
+    __device__ __forceinline__ void legal(uint32_t (&m)[1]) const { m[0] = r.legal(4); }
+    __device__ __forceinline__ int player() const { return r.pointer; }
+    __device__ __forceinline__ bool over() const { return (fold0 + fold1 == 1) || rc >= 4; }   // game.py:216-231
+    // game.py:105-156
+    template <class Ch> __device__ __forceinline__ void step(int id, Ch &, int &err) {
+        const uint32_t m = r.legal(4);
+        int action = id;
+        if (id < 0 || id > 3 || !((m >> id) & 1u)) { action = ((m >> kCheck) & 1u) ? kCheck : kFold; err |= 4; }
+        const int actor = r.pointer;
+        bool fold;
+        const int diff = r.proceed(action, rc >= 2 ? 4 : 2, fold);   // doubled from round 2 on (game.py:148-149)
+        if (actor) { chips1 += diff; fold1 |= fold; } else { chips0 += diff; fold0 |= fold; }
+        rn = (rn & ~(7u << (3 * rc))) | ((uint32_t)r.have_raised << (3 * rc));   // game.py:133
+        if (r.not_raise_num >= 2) { rc++; r.start(r.pointer, 0, 0); }
+    }
+    // game.py:233-243, judger.py:11-108 for two players: winner takes min(chips) from the loser
+    __device__ __forceinline__ void payoffs(float *out) const {
+        int w0, w1;
+        if (fold0 + fold1 == 1) { w0 = fold1; w1 = fold0; }
+        else {
+            const int h0[7] = { card[0], card[2], card[4], card[5], card[6], card[7], card[8] };
+            const int h1[7] = { card[1], card[3], card[4], card[5], card[6], card[7], card[8] };
+            const uint32_t s0 = holdem_strength7(h0), s1 = holdem_strength7(h1);
+            w0 = s0 >= s1; w1 = s1 >= s0;
+        }
+        const int pot = min(chips0, chips1);
+        float p0 = 0.f;
+        if (w0 != w1) p0 = w0 ? (float)pot : -(float)pot;
+        out[0] = p0 * 0.5f; out[1] = -p0 * 0.5f;
+    }
+    // envs/limitholdem.py:40-71
+    template <class T> __device__ __forceinline__ void encode_obs(int seat, bool reset_view, T *row) const {
+        row[card[seat]] = (T)1; row[card[2 + seat]] = (T)1;
+        const int np_ = n_public();
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (k < np_) row[card[4 + k]] = (T)1;
+        // the state object returned by reset() still references last episode's list (Q-LH1)
+        const uint32_t shown = reset_view ? rn_shown : rn;
+#pragma unroll
+        for (int k = 0; k < 4; k++) row[52 + 5 * k + ((shown >> (3 * k)) & 7u)] = (T)1;
+    }
+};
+
+}  // namespace rlc

@@ -1,0 +1,254 @@
+// kernels.cuh -- one-env-per-thread kernels, templated on <Game, Chance source, obs dtype>.
+//   k_env<RESET|STEP|OBSERVE>  Env.reset / Env.step / Env.get_state over n envs (env.py:52-86,188-197)
+//   k_rollout                  the Env.run loop with RandomAgents fused on device (env.py:120-169)
+// State is SoA uint32 [words][n] (coalesced word loads); obs rows are staged per warp in shared
+// memory and streamed out with 128-bit stores (common.cuh warp_tile_flush).
+#pragma once
+#include "common.cuh"
+#include "../../include/rlcard_b200.h"
+
+namespace rlc {
+
+struct KParams {
+    uint32_t *state; size_t n;
+    uint64_t seed; uint32_t env_id_base;
+    const uint8_t *tape; int tape_stride; int32_t *tape_pos; uint32_t *mt;
+    void *obs; void *mask; int32_t *cur_player; uint8_t *done; float *payoffs; void *terminal_obs; int32_t *err;
+    const int32_t *actions; const uint8_t *reset_mask; const int32_t *seat; int flags;
+    void *t_obs; void *t_mask; int32_t *t_action; int32_t *t_player; uint8_t *t_done; float *t_payoffs; int T;
+};
+
+enum { kModeReset = 0, kModeStep = 1, kModeObserve = 2 };
+
+// ---- chance source plumbing -------------------------------------------------------------
+template <class Ch> struct ChanceIO;
+template <> struct ChanceIO<ChancePhilox> {
+    static __device__ __forceinline__ void open(ChancePhilox &c, const KParams &p, size_t i, const EnvHeader &h) {
+        c.s.init(p.seed, p.env_id_base + (uint32_t)i, h.episode - 1u, 0u); c.draw = h.draw; c.err = 0;
+    }
+    static __device__ __forceinline__ void close(ChancePhilox &c, const KParams &, size_t, EnvHeader &h) { h.draw = c.draw; }
+};
+template <> struct ChanceIO<ChanceTape> {
+    static __device__ __forceinline__ void open(ChanceTape &c, const KParams &p, size_t i, const EnvHeader &) {
+        c.tape = p.tape + i * (size_t)p.tape_stride; c.len = p.tape_stride; c.pos = p.tape_pos[i]; c.err = 0;
+    }
+    static __device__ __forceinline__ void close(ChanceTape &c, const KParams &p, size_t i, EnvHeader &) { p.tape_pos[i] = c.pos; }
+};
+template <> struct ChanceIO<ChanceMt> {
+    static __device__ __forceinline__ void open(ChanceMt &c, const KParams &p, size_t i, const EnvHeader &) {
+        c.mt = p.mt + i; c.n = p.n; c.mti = (int)p.mt[(size_t)624 * p.n + i]; c.err = 0;
+    }
+    static __device__ __forceinline__ void close(ChanceMt &c, const KParams &p, size_t i, EnvHeader &) {
+        p.mt[(size_t)624 * p.n + i] = (uint32_t)c.mti;
+    }
+};
+
+template <class G, class Ch>
+__device__ __forceinline__ void new_episode(G &g, Ch &ch, EnvHeader &h) {
+    h.episode++; h.t = 0;
+    ch.new_episode(h.episode - 1u);
+    g.reset(ch);
+}
+
+// dense uint8 mask row [A] of one env; rows of a warp are contiguous
+template <class G>
+__device__ __forceinline__ void write_mask_row(uint8_t *gmask, size_t env, const uint32_t (&m)[G::MASK_WORDS]) {
+    if constexpr (G::A == 4) {
+        const uint32_t w = (m[0] & 1u) | ((m[0] & 2u) << 7) | ((m[0] & 4u) << 14) | ((m[0] & 8u) << 21);
+        reinterpret_cast<uint32_t *>(gmask)[env] = w;
+    } else if constexpr (G::A == 2) {
+        reinterpret_cast<uint16_t *>(gmask)[env] = (uint16_t)((m[0] & 1u) | ((m[0] & 2u) << 7));
+    } else {
+        uint8_t *rowp = gmask + env * (size_t)G::A;
+        for (int a = 0; a < G::A; a++) rowp[a] = (m[a >> 5] >> (a & 31)) & 1u;
+    }
+}
+
+template <class G, class Ch, class ObsT, int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
+    if (warp_env0 >= p.n) return;
+    const size_t i = warp_env0 + lane;
+    const bool valid = i < p.n;
+    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * G::OBS;
+    ObsT *row = tile + lane * G::OBS;
+    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    __syncwarp();
+
+    G g; EnvHeader h; Ch ch; int err = 0;
+    if (valid) {
+        h.load(p.state, p.n, i);
+        g.load(p.state + kHeaderWords * p.n, p.n, i);
+        ChanceIO<Ch>::open(ch, p, i, h);
+        bool done = false;
+        float pay[G::P];
+#pragma unroll
+        for (int k = 0; k < G::P; k++) pay[k] = 0.f;
+        if constexpr (MODE == kModeReset) {
+            if (!p.reset_mask || p.reset_mask[i]) new_episode(g, ch, h);
+        } else if constexpr (MODE == kModeStep) {
+            const int a = p.actions[i];
+            if (a >= 0 && h.episode != 0 && !g.over()) {
+                g.step(a, ch, err);
+                h.t++;
+                if (g.over()) {
+                    done = true;
+                    g.payoffs(pay);
+                    if ((p.flags & RLC_TERMINAL_OBS) && p.terminal_obs) {
+                        ObsT *dst = reinterpret_cast<ObsT *>(p.terminal_obs) + i * (size_t)(G::P * G::OBS);
+                        for (int s = 0; s < G::P; s++) {
+                            g.encode_obs(s, false, row);
+                            for (int k = 0; k < G::OBS; k++) { dst[s * G::OBS + k] = row[k]; row[k] = (ObsT)0; }
+                        }
+                    }
+                    if (p.flags & RLC_AUTO_RESET) new_episode(g, ch, h);
+                }
+            } else if (g.over()) { done = true; g.payoffs(pay); }
+        } else {
+            if (h.episode != 0 && g.over()) { done = true; g.payoffs(pay); }
+        }
+        const int seat = (MODE == kModeObserve && p.seat) ? p.seat[i] : g.player();
+        if (p.obs) g.encode_obs(seat, MODE != kModeObserve && h.t == 0, row);
+        uint32_t m[G::MASK_WORDS];
+        g.legal(m);
+        if (p.mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.mask), i, m);
+        if (p.cur_player) p.cur_player[i] = g.player();
+        if (p.done) p.done[i] = done ? 1 : 0;
+        if (p.payoffs) {
+#pragma unroll
+            for (int k = 0; k < G::P; k++) p.payoffs[i * G::P + k] = pay[k];
+        }
+        if constexpr (MODE != kModeObserve) {
+            ChanceIO<Ch>::close(ch, p, i, h);
+            h.store(p.state, p.n, i);
+            g.store(p.state + kHeaderWords * p.n, p.n, i);
+        }
+        err |= ch.err;
+        if (err && p.err) p.err[i] |= err;
+    }
+    __syncwarp();
+    if (p.obs)
+        warp_tile_flush(reinterpret_cast<uint8_t *>(p.obs) + warp_env0 * (size_t)kRowBytes,
+                        reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+}
+
+// Fused random rollout: T env-steps per env, state in registers for the whole launch; per step the
+// warp emits one coalesced obs tile plus mask/action/player/done/payoff rows of the trajectory.
+template <class G, class Ch, class ObsT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
+    if (warp_env0 >= p.n) return;
+    const size_t i = warp_env0 + lane;
+    const bool valid = i < p.n;
+    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * G::OBS;
+    ObsT *row = tile + lane * G::OBS;
+    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    __syncwarp();
+
+    G g; EnvHeader h; Ch ch; int err = 0;
+    PhiloxStream pol;
+    if (valid) {
+        h.load(p.state, p.n, i);
+        g.load(p.state + kHeaderWords * p.n, p.n, i);
+        ChanceIO<Ch>::open(ch, p, i, h);
+        if (h.episode == 0) new_episode(g, ch, h);
+        pol.init(p.seed, p.env_id_base + (uint32_t)i, h.episode - 1u, 1u);
+    }
+    for (int t = 0; t < p.T; t++) {
+        const size_t rowi = (size_t)t * p.n + i;
+        uint32_t m[G::MASK_WORDS];
+        if (valid) {
+            if (p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
+            g.legal(m);
+        }
+        __syncwarp();
+        if (p.t_obs)
+            warp_tile_flush(reinterpret_cast<uint8_t *>(p.t_obs) + ((size_t)t * p.n + warp_env0) * (size_t)kRowBytes,
+                            reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        __syncwarp();
+        if (valid) {
+            if (p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
+            if (p.t_player) __stcs(p.t_player + rowi, g.player());
+            const int cnt = popc_words<G::MASK_WORDS>(m);
+            const int k = (int)__umulhi(pol.word(h.t), (uint32_t)cnt);
+            const int a = kth_set_bit<G::MASK_WORDS>(m, k);
+            if (p.t_action) __stcs(p.t_action + rowi, a);
+            g.step(a, ch, err);
+            h.t++;
+            const bool over = g.over();
+            float pay[G::P];
+#pragma unroll
+            for (int q = 0; q < G::P; q++) pay[q] = 0.f;
+            if (over) {
+                g.payoffs(pay);
+                new_episode(g, ch, h);
+                pol.new_episode(h.episode - 1u);
+            }
+            if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
+            if (p.t_payoffs) {
+                if constexpr (G::P == 2) __stcs(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
+                else if constexpr (G::P == 4) __stcs(reinterpret_cast<float4 *>(p.t_payoffs) + rowi, make_float4(pay[0], pay[1], pay[2], pay[3]));
+                else {
+#pragma unroll
+                    for (int q = 0; q < G::P; q++) p.t_payoffs[rowi * G::P + q] = pay[q];
+                }
+            }
+        }
+    }
+    if (valid) {
+        ChanceIO<Ch>::close(ch, p, i, h);
+        h.store(p.state, p.n, i);
+        g.store(p.state + kHeaderWords * p.n, p.n, i);
+        err |= ch.err;
+        if (err && p.err) p.err[i] |= err;
+    }
+}
+
+// ---- host-side launcher shared by the per-game translation units ----------------------------
+enum { kOpReset = 0, kOpStep = 1, kOpObserve = 2, kOpRollout = 3 };
+
+template <class G, class Ch, class ObsT>
+cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
+    constexpr int BLOCK = 64;
+    const unsigned grid = (unsigned)((p.n + BLOCK - 1) / BLOCK);
+    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT);
+    cudaError_t e = cudaSuccess;
+#define RLC_LAUNCH(KERNEL)                                                                           \
+    do {                                                                                             \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) { KERNEL<<<grid, BLOCK, smem, stream>>>(p); e = cudaGetLastError(); }  \
+    } while (0)
+    switch (op) {
+    case kOpReset: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeReset, BLOCK>)); break;
+    case kOpStep: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeStep, BLOCK>)); break;
+    case kOpObserve: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
+    case kOpRollout: RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK>)); break;
+    default: e = cudaErrorInvalidValue;
+    }
+#undef RLC_LAUNCH
+    return e;
+}
+
+template <class G>
+cudaError_t dispatch_game(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t stream) {
+    if (obs_dtype == RLC_U8) {
+        if (chance == RLC_CHANCE_PHILOX) return launch_op<G, ChancePhilox, uint8_t>(op, p, stream);
+        if (chance == RLC_CHANCE_TAPE) return launch_op<G, ChanceTape, uint8_t>(op, p, stream);
+        if (chance == RLC_CHANCE_MT19937) return launch_op<G, ChanceMt, uint8_t>(op, p, stream);
+    } else if (obs_dtype == RLC_F32) {
+        if (chance == RLC_CHANCE_PHILOX) return launch_op<G, ChancePhilox, float>(op, p, stream);
+        if (chance == RLC_CHANCE_TAPE) return launch_op<G, ChanceTape, float>(op, p, stream);
+        if (chance == RLC_CHANCE_MT19937) return launch_op<G, ChanceMt, float>(op, p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rlc

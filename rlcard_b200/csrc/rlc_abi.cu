@@ -1,0 +1,143 @@
+// rlc_abi.cu -- the C ABI (include/rlcard_b200.h): argument checking, per-game dispatch,
+// error reporting.  No torch types, no allocation of per-env memory.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "kernels.cuh"
+
+namespace rlc {
+cudaError_t dispatch_blackjack(int, int, int, const KParams &, cudaStream_t);
+cudaError_t dispatch_leduc(int, int, int, const KParams &, cudaStream_t);
+cudaError_t dispatch_limit(int, int, int, const KParams &, cudaStream_t);
+#ifdef RLC_HAVE_UNO
+cudaError_t dispatch_uno(int, int, int, const KParams &, cudaStream_t);
+#endif
+#ifdef RLC_HAVE_SCOUT
+cudaError_t dispatch_scout(int, int, int, const KParams &, cudaStream_t);
+#endif
+#ifdef RLC_HAVE_DOUDIZHU
+cudaError_t dispatch_doudizhu(int, int, int, const KParams &, cudaStream_t);
+cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes);
+#endif
+}  // namespace rlc
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+
+static const rlc_info kInfo[RLC_NUM_GAMES] = {
+    /* game, P, A, obs_dim[4], stride, native dtype, bitpacked, mask_words, state_words, reset draws, threads/env */
+    { RLC_BLACKJACK, 1, 2, {2, 0, 0, 0}, 2, RLC_U8, 0, 1, rlc::kHeaderWords + 15, 55, 1, {0, 0, 0, 0} },
+    { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, {0, 0, 0, 0} },
+    { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, {0, 0, 0, 0} },
+    { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, 0, 0, 1, {0, 0, 0, 0} },
+    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 901, RLC_U8, 1, 859, 0, 0, 32, {0, 0, 0, 0} },
+    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, 0, 0, 1, {0, 0, 0, 0} },
+};
+
+static int dispatch(int game, int op, const rlc_buffers *b, rlc::KParams &p, void *stream) {
+    cudaError_t e;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (game) {
+    case RLC_BLACKJACK: e = rlc::dispatch_blackjack(op, b->chance, b->obs_dtype, p, s); break;
+    case RLC_LEDUC: e = rlc::dispatch_leduc(op, b->chance, b->obs_dtype, p, s); break;
+    case RLC_LIMIT: e = rlc::dispatch_limit(op, b->chance, b->obs_dtype, p, s); break;
+#ifdef RLC_HAVE_UNO
+    case RLC_UNO: e = rlc::dispatch_uno(op, b->chance, b->obs_dtype, p, s); break;
+#endif
+#ifdef RLC_HAVE_SCOUT
+    case RLC_SCOUT: e = rlc::dispatch_scout(op, b->chance, b->obs_dtype, p, s); break;
+#endif
+#ifdef RLC_HAVE_DOUDIZHU
+    case RLC_DOUDIZHU: e = rlc::dispatch_doudizhu(op, b->chance, b->obs_dtype, p, s); break;
+#endif
+    default: return fail(RLC_ENOTIMPL, "game %d has no kernels in this build", game);
+    }
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? RLC_EINVAL : RLC_ECUDA, "CUDA: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RLC_OK;
+}
+
+static int fill(int game, const rlc_buffers *b, int n, rlc::KParams &p) {
+    if (game < 0 || game >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game);
+    if (!b || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+    if (!b->state) return fail(RLC_EINVAL, "state buffer is required");
+    if (b->chance == RLC_CHANCE_TAPE && (!b->tape || !b->tape_pos || b->tape_stride <= 0))
+        return fail(RLC_EINVAL, "tape chance needs tape, tape_pos and tape_stride");
+    if (b->chance == RLC_CHANCE_MT19937 && !b->mt) return fail(RLC_EINVAL, "mt19937 chance needs the mt buffer");
+    if (b->chance < 0 || b->chance > 2) return fail(RLC_EINVAL, "bad chance kind %d", b->chance);
+    if (b->obs_dtype != RLC_U8 && b->obs_dtype != RLC_F32) return fail(RLC_EINVAL, "bad obs dtype %d", b->obs_dtype);
+    if (kInfo[game].obs_native_dtype == RLC_F32 && b->obs_dtype != RLC_F32)
+        return fail(RLC_EINVAL, "game %d has fractional obs values: obs_dtype must be RLC_F32", game);
+    memset(&p, 0, sizeof p);
+    p.state = b->state; p.n = (size_t)n; p.seed = b->seed; p.env_id_base = b->env_id_base;
+    p.tape = b->tape; p.tape_stride = b->tape_stride; p.tape_pos = b->tape_pos; p.mt = b->mt;
+    p.obs = b->obs; p.mask = b->mask; p.cur_player = b->cur_player; p.done = b->done; p.payoffs = b->payoffs;
+    p.terminal_obs = b->terminal_obs; p.err = b->err;
+    return RLC_OK;
+}
+
+extern "C" {
+
+int rlc_abi_version(void) { return RLC_ABI_VERSION; }
+const char *rlc_last_error(void) { return g_err; }
+int64_t rlc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int rlc_game_info(int game_id, rlc_info *out) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES || !out) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    *out = kInfo[game_id];
+    return RLC_OK;
+}
+
+int rlc_upload_tables(int game_id, int device, const void *blob, size_t nbytes) {
+#ifdef RLC_HAVE_DOUDIZHU
+    if (game_id == RLC_DOUDIZHU) {
+        cudaError_t e = rlc::doudizhu_upload(device, blob, nbytes);
+        return e == cudaSuccess ? RLC_OK : fail(RLC_ECUDA, "table upload: %s", cudaGetErrorString(e));
+    }
+#endif
+    (void)device; (void)blob; (void)nbytes;
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    return RLC_OK;   /* the other games have no uploaded tables */
+}
+
+int rlc_reset(int game_id, const rlc_buffers *b, int n, const uint8_t *reset_mask, void *stream) {
+    rlc::KParams p; int rc = fill(game_id, b, n, p);
+    if (rc) return rc;
+    p.reset_mask = reset_mask;
+    return dispatch(game_id, rlc::kOpReset, b, p, stream);
+}
+
+int rlc_step(int game_id, const rlc_buffers *b, const int32_t *actions, int n, int flags, void *stream) {
+    rlc::KParams p; int rc = fill(game_id, b, n, p);
+    if (rc) return rc;
+    if (!actions) return fail(RLC_EINVAL, "actions is required");
+    p.actions = actions; p.flags = flags;
+    return dispatch(game_id, rlc::kOpStep, b, p, stream);
+}
+
+int rlc_observe(int game_id, const rlc_buffers *b, const int32_t *seat, int n, void *stream) {
+    rlc::KParams p; int rc = fill(game_id, b, n, p);
+    if (rc) return rc;
+    p.seat = seat;
+    return dispatch(game_id, rlc::kOpObserve, b, p, stream);
+}
+
+int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *traj, int n, int k_steps, void *stream) {
+    rlc::KParams p; int rc = fill(game_id, b, n, p);
+    if (rc) return rc;
+    if (k_steps <= 0) return fail(RLC_EINVAL, "k_steps must be positive");
+    if (traj) {
+        p.t_obs = traj->obs; p.t_mask = traj->mask; p.t_action = traj->action; p.t_player = traj->player;
+        p.t_done = traj->done; p.t_payoffs = traj->payoffs;
+    }
+    p.T = k_steps;
+    return dispatch(game_id, rlc::kOpRollout, b, p, stream);
+}
+
+}  // extern "C"

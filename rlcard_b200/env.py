@@ -1,0 +1,188 @@
+"""Single-env facade with the reference's ``Env`` surface (rlcard/envs/env.py:9-231).
+
+``rlcard_b200.make(env_id, config)`` returns an object whose ``reset/step/get_state/is_over/
+get_player_id/get_payoffs/run/set_agents/seed/get_action_feature`` behave like the reference's, with the
+game itself running in the CUDA kernels (a ``VecEnv`` of one env in ``mt19937`` mode: the same
+``np.random.RandomState`` stream the reference would consume for this seed, so trajectories are
+identical to ``rlcard.make(env_id, {'seed': s})``).
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .vec_env import VecEnv
+
+DEFAULT_CONFIG = {'allow_step_back': False, 'seed': None}   # envs/registration.py:4-7
+
+# per env: raw action names by id, reference obs dtype, reference obs shape per seat
+_POKER_ACTIONS = ['call', 'raise', 'fold', 'check']
+
+
+def _uno_actions():
+    colors, traits = ['r', 'g', 'b', 'y'], [str(i) for i in range(10)] + ['skip', 'reverse', 'draw_2', 'wild', 'wild_draw_4']
+    return ['%s-%s' % (c, t) for c in colors for t in traits] + ['draw']   # games/uno/jsondata/action_space.json
+
+
+def _scout_actions():
+    acts = []
+    for s in range(16):
+        for e in range(s + 1, 17):
+            acts.append('play-%d-%d' % (s, e))                             # games/scout/utils/utils.py:186-200
+    for ins in range(17):
+        for tag in ('front-%d-normal', 'front-%d-flip', 'back-%d-normal', 'back-%d-flip'):
+            acts.append('scout-' + tag % ins)
+    return acts
+
+
+_SPECS = {
+    'blackjack': dict(actions=lambda: ['hit', 'stand'], dtype=np.int64, shape=lambda d: (d,)),
+    'leduc-holdem': dict(actions=lambda: _POKER_ACTIONS, dtype=np.float64, shape=lambda d: (d,)),
+    'limit-holdem': dict(actions=lambda: _POKER_ACTIONS, dtype=np.float64, shape=lambda d: (d,)),
+    'uno': dict(actions=_uno_actions, dtype=np.int64, shape=lambda d: (4, 4, 15)),
+    'doudizhu': dict(actions=lambda: None, dtype=np.int8, shape=lambda d: (d,)),
+    'scout': dict(actions=_scout_actions, dtype=np.float32, shape=lambda d: (d,)),
+}
+_STATE_SHAPE = {'uno': [4, 4, 15]}
+_INT_PAYOFF = {'blackjack', 'uno', 'doudizhu', 'scout'}
+
+
+class Env:
+    """The reference's Env API over one CUDA-resident env."""
+
+    def __init__(self, env_id, config=None, device='cuda:0'):
+        cfg = dict(DEFAULT_CONFIG)
+        cfg.update(config or {})
+        for k, v in cfg.items():
+            if k.startswith('game_'):
+                default = {'game_num_players': {'blackjack': 1}.get(env_id, 2), 'game_num_decks': 1}.get(k)
+                if default is not None and v != default:
+                    raise NotImplementedError('%s=%r: only the reference default (%r) is built' % (k, v, default))
+        self.name = env_id
+        self.allow_step_back = cfg['allow_step_back']
+        if self.allow_step_back:
+            raise NotImplementedError('allow_step_back=True is not supported by the batched simulator')
+        self.device = device
+        self._spec = _SPECS[env_id]
+        self._vec = VecEnv(env_id, 1, device=device, mode='mt19937', auto_reset=False)
+        self.num_players = self._vec.num_players
+        self.num_actions = self._vec.num_actions
+        self.state_shape = [list(_STATE_SHAPE.get(env_id, [d])) for d in self._vec.obs_dims]
+        self.action_shape = [[54] if env_id == 'doudizhu' else None for _ in range(self.num_players)]
+        self.actions = self._spec['actions']()
+        self.timestep = 0
+        self.action_recorder = []
+        self.agents = None
+        self.seed(cfg['seed'])
+
+    # -- seeding (env.py:228-231, utils/seeding.py:33-41)
+    def seed(self, seed=None):
+        if seed is None:
+            import os
+            seed = int.from_bytes(os.urandom(8), 'little')
+        if not (isinstance(seed, int) and seed >= 0):
+            raise ValueError('Seed must be a non-negative integer or omitted, not {}'.format(seed))
+        self._seed = seed
+        self._vec.seed_mt19937([seed])
+        return seed
+
+    # -- state dict assembly (the per-env _extract_state)
+    def _state_dict(self):
+        v = self._vec
+        pid = int(v.cur_player[0].item())
+        return self._dict_from(v.obs[0], v.mask[0], pid), pid
+
+    def _dict_from(self, obs_row, mask_row, seat_for_dim):
+        d = self._vec.obs_dims[seat_for_dim]
+        obs = obs_row[:d].cpu().numpy().astype(self._spec['dtype']).reshape(self._spec['shape'](d))
+        ids = np.nonzero(mask_row.cpu().numpy())[0].tolist()
+        state = {'obs': obs, 'legal_actions': OrderedDict((int(a), None) for a in ids)}
+        state['raw_legal_actions'] = [self.actions[a] for a in ids] if self.actions else list(ids)
+        state['raw_obs'] = {'obs': obs, 'legal_actions': state['raw_legal_actions']}
+        state['action_record'] = self.action_recorder
+        return state
+
+    def reset(self):
+        self._vec.reset()
+        self.action_recorder = []
+        return self._state_dict()
+
+    def step(self, action, raw_action=False):
+        if raw_action:
+            action = self.actions.index(action)
+        self.timestep += 1
+        self.action_recorder.append((self.get_player_id(), self.actions[action] if self.actions else action))
+        a = torch.tensor([int(action)], dtype=torch.int32, device=self._vec.device)
+        self._vec.step(a, auto_reset=False)
+        return self._state_dict()
+
+    def step_back(self):
+        raise Exception('Step back is off. To use step_back, please set allow_step_back=True in rlcard.make')
+
+    def set_agents(self, agents):
+        self.agents = agents
+
+    def is_over(self):
+        self._vec.get_state(None)
+        return bool(self._vec.done[0].item())
+
+    def get_player_id(self):
+        return int(self._vec.cur_player[0].item())
+
+    def get_state(self, player_id):
+        self._vec.get_state(int(player_id))
+        return self._dict_from(self._vec.obs[0], self._vec.mask[0], int(player_id))
+
+    def get_payoffs(self):
+        self._vec.get_state(None)
+        p = self._vec.payoffs[0].cpu().numpy().astype(np.float64)
+        return p.astype(np.int64) if self.name in _INT_PAYOFF else p
+
+    def get_action_feature(self, action):
+        feature = np.zeros(self.num_actions, dtype=np.int8)   # env.py:217-226 default one-hot
+        feature[action] = 1
+        return feature
+
+    def get_perfect_information(self):
+        raise NotImplementedError
+
+    # -- the rollout loop, env.py:120-169 verbatim in behaviour
+    def run(self, is_training=False):
+        trajectories = [[] for _ in range(self.num_players)]
+        state, player_id = self.reset()
+        trajectories[player_id].append(state)
+        while not self.is_over():
+            if not is_training:
+                action, _ = self.agents[player_id].eval_step(state)
+            else:
+                action = self.agents[player_id].step(state)
+            next_state, next_player_id = self.step(action, self.agents[player_id].use_raw)
+            trajectories[player_id].append(action)
+            state, player_id = next_state, next_player_id
+            if not self.is_over():
+                trajectories[player_id].append(state)
+        for pid in range(self.num_players):
+            trajectories[pid].append(self.get_state(pid))
+        return trajectories, self.get_payoffs()
+
+
+class RandomAgent:
+    """agents/random_agent.py:14-47: uniform over state['legal_actions'] with the global np.random."""
+    use_raw = False
+
+    def __init__(self, num_actions):
+        self.num_actions = num_actions
+
+    @staticmethod
+    def step(state):
+        return int(np.random.choice(list(state['legal_actions'].keys())))
+
+    def eval_step(self, state):
+        n = len(state['legal_actions'])
+        info = {'probs': {state['raw_legal_actions'][i]: 1.0 / n for i in range(n)}}
+        return self.step(state), info
+
+
+def make(env_id, config=None, device='cuda:0'):
+    """rlcard.make (envs/registration.py:77-89)."""
+    return Env(env_id, config, device=device)

@@ -1,0 +1,250 @@
+"""VecEnv: N independent card-game envs stepped by CUDA kernels through the C ABI.
+
+Drop-in for the reference's rollout loops (``Env.run`` in rlcard/envs/env.py:120-169, the body of
+examples/run_random.py:23-27, ``tournament`` in rlcard/utils/utils.py:200-225 and the DMC actor loop
+rlcard/agents/dmc_agent/utils.py:121-137): instead of one Python ``Env`` per process, one ``VecEnv``
+per GPU holds every env's packed state in HBM.  torch owns all memory; the library gets raw pointers.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (AUTO_RESET, CHANCE_MT19937, CHANCE_PHILOX, CHANCE_TAPE, DTYPE_F32, DTYPE_U8, GAME_IDS,
+                   TERMINAL_OBS, RlcBuffers, RlcTrajectory, check, game_info, lib)
+
+_MODES = {'throughput': CHANCE_PHILOX, 'philox': CHANCE_PHILOX, 'replay': CHANCE_TAPE, 'tape': CHANCE_TAPE,
+          'mt19937': CHANCE_MT19937}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def seed_words(seed):
+    """rlcard/utils/seeding.py:33-113: sha512(str(seed))[:8] -> uint32 words given to RandomState.seed."""
+    import hashlib
+    import struct
+    seed = int(seed) % 2 ** 64
+    lo, hi = struct.unpack('2I', hashlib.sha512(str(seed).encode('utf8')).digest()[:8])
+    return [lo, hi] if hi else [lo]
+
+
+class VecEnv:
+    """``num_envs`` environments of one game on one GPU.
+
+    mode 'throughput': Philox4x32-10 chance keyed by (seed, env_id_base + i, episode).
+    mode 'replay':     chance draws come from a uint8 tape per env (``set_tape``), i.e. the
+                       reference's recorded np.random outcomes.
+    mode 'mt19937':    np.random.RandomState on device, seeded per env like ``rlcard.make(seed=...)``.
+    """
+
+    def __init__(self, env_id, num_envs, device='cuda:0', seed=0, mode='throughput', obs_dtype=None,
+                 env_id_base=0, auto_reset=True, terminal_obs=False):
+        if env_id not in GAME_IDS:
+            raise ValueError('unknown env id %r (have %s)' % (env_id, sorted(GAME_IDS)))
+        self.L = lib()                     # raises if the CUDA extension is missing
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.RlcError('rlcard_b200 runs on CUDA devices only (no CPU fallback)')
+        self.name = env_id
+        self.gid = GAME_IDS[env_id]
+        info = game_info(self.gid)
+        if info.state_words == 0:
+            raise _lib.RlcError('game %r has no kernels in this build' % env_id)
+        self.num_envs = int(num_envs)
+        self.num_players = info.num_players
+        self.num_actions = info.num_actions
+        self.obs_dims = list(info.obs_dim)[:info.num_players]
+        self.obs_stride = info.obs_stride
+        self.mask_bitpacked = bool(info.mask_bitpacked)
+        self.mask_words = info.mask_words
+        self.state_words = info.state_words
+        self.chance = _MODES[mode]
+        self.seed_value = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.auto_reset = bool(auto_reset)
+        self.terminal_obs_enabled = bool(terminal_obs)
+        if obs_dtype is None:
+            obs_dtype = torch.float32 if info.obs_native_dtype == DTYPE_F32 else torch.uint8
+        if obs_dtype not in (torch.uint8, torch.float32):
+            raise ValueError('obs_dtype must be torch.uint8 or torch.float32')
+        self.obs_dtype = obs_dtype
+        N, dev = self.num_envs, self.device
+        with torch.cuda.device(dev):
+            self.state = torch.zeros((self.state_words, N), dtype=torch.int32, device=dev)
+            self.obs = torch.zeros((N, self.obs_stride), dtype=obs_dtype, device=dev)
+            if self.mask_bitpacked:
+                self.mask = torch.zeros((N, self.mask_words), dtype=torch.int32, device=dev)
+            else:
+                self.mask = torch.zeros((N, self.num_actions), dtype=torch.uint8, device=dev)
+            self.cur_player = torch.zeros(N, dtype=torch.int32, device=dev)
+            self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
+            self.payoffs = torch.zeros((N, self.num_players), dtype=torch.float32, device=dev)
+            self.err = torch.zeros(N, dtype=torch.int32, device=dev)
+            self.terminal_obs = (torch.zeros((N, self.num_players, self.obs_stride), dtype=obs_dtype, device=dev)
+                                 if terminal_obs else None)
+        self.tape = None
+        self.tape_pos = None
+        self.mt = None
+        self._buf = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ chance sources
+    def set_tape(self, tape):
+        """tape: uint8 [num_envs, L] draw outcomes in consumption order (replay mode)."""
+        tape = torch.as_tensor(np.ascontiguousarray(tape, dtype=np.uint8)).to(self.device)
+        assert tape.dim() == 2 and tape.shape[0] == self.num_envs
+        self.tape = tape.contiguous()
+        self.tape_pos = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self._buf = None
+
+    def seed_mt19937(self, seeds):
+        """Per-env ``rlcard.make(..., {'seed': s})`` seeding (utils/seeding.py:33-41)."""
+        assert len(seeds) == self.num_envs
+        st = np.zeros((625, self.num_envs), np.uint32)
+        for i, s in enumerate(seeds):
+            rs = np.random.RandomState()
+            rs.seed(seed_words(s))
+            key = rs.get_state()
+            st[:624, i] = key[1]
+            st[624, i] = key[2]
+        self.mt = torch.as_tensor(st.view(np.int32)).to(self.device).contiguous()
+        self._buf = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _buffers(self):
+        if self._buf is None:
+            b = RlcBuffers()
+            b.state = self.state.data_ptr()
+            b.chance = self.chance
+            b.seed = self.seed_value % 2 ** 64
+            b.env_id_base = self.env_id_base
+            if self.chance == CHANCE_TAPE:
+                if self.tape is None:
+                    raise _lib.RlcError("replay mode needs set_tape() before reset()")
+                b.tape = self.tape.data_ptr(); b.tape_stride = self.tape.shape[1]; b.tape_pos = self.tape_pos.data_ptr()
+            if self.chance == CHANCE_MT19937:
+                if self.mt is None:
+                    raise _lib.RlcError("mt19937 mode needs seed_mt19937() before reset()")
+                b.mt = self.mt.data_ptr()
+            b.obs = self.obs.data_ptr()
+            b.obs_dtype = DTYPE_F32 if self.obs_dtype == torch.float32 else DTYPE_U8
+            b.mask = self.mask.data_ptr()
+            b.cur_player = self.cur_player.data_ptr()
+            b.done = self.done.data_ptr()
+            b.payoffs = self.payoffs.data_ptr()
+            b.terminal_obs = self.terminal_obs.data_ptr() if self.terminal_obs is not None else None
+            b.err = self.err.data_ptr()
+            self._buf = b
+        return self._buf
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ Env surface, vector form
+    def reset(self, reset_mask=None):
+        """Env.reset for all envs (or those with reset_mask != 0) -> (obs, mask, cur_player)."""
+        with torch.cuda.device(self.device):
+            if reset_mask is not None:
+                reset_mask = reset_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            check(self.L.rlc_reset(self.gid, C.byref(self._buffers()), self.num_envs, _ptr(reset_mask), self._stream()))
+        self.launches += 1
+        return self.obs, self.mask, self.cur_player
+
+    def step(self, actions, auto_reset=None):
+        """Env.step for all envs; actions int32 [N] on the device (negative = leave env untouched).
+        -> (obs, mask, cur_player, done, payoffs)."""
+        auto = self.auto_reset if auto_reset is None else auto_reset
+        flags = (AUTO_RESET if auto else 0) | (TERMINAL_OBS if self.terminal_obs is not None else 0)
+        with torch.cuda.device(self.device):
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            check(self.L.rlc_step(self.gid, C.byref(self._buffers()), _ptr(actions), self.num_envs, flags, self._stream()))
+        self.launches += 1
+        return self.obs, self.mask, self.cur_player, self.done, self.payoffs
+
+    def get_state(self, seat=None):
+        """Env.get_state(player_id): obs/mask as seen by seat (int, int32 [N] tensor or None = current)."""
+        with torch.cuda.device(self.device):
+            if seat is not None and not torch.is_tensor(seat):
+                seat = torch.full((self.num_envs,), int(seat), dtype=torch.int32, device=self.device)
+            if seat is not None:
+                seat = seat.to(device=self.device, dtype=torch.int32).contiguous()
+            check(self.L.rlc_observe(self.gid, C.byref(self._buffers()), _ptr(seat), self.num_envs, self._stream()))
+        self.launches += 1
+        return self.obs, self.mask, self.cur_player, self.done, self.payoffs
+
+    def alloc_trajectory(self, T, obs=True, mask=True):
+        N, dev = self.num_envs, self.device
+        tr = {}
+        tr['obs'] = torch.empty((T, N, self.obs_stride), dtype=self.obs_dtype, device=dev) if obs else None
+        if mask:
+            shape = (T, N, self.mask_words) if self.mask_bitpacked else (T, N, self.num_actions)
+            tr['mask'] = torch.empty(shape, dtype=torch.int32 if self.mask_bitpacked else torch.uint8, device=dev)
+        else:
+            tr['mask'] = None
+        tr['action'] = torch.empty((T, N), dtype=torch.int32, device=dev)
+        tr['player'] = torch.empty((T, N), dtype=torch.int32, device=dev)
+        tr['done'] = torch.empty((T, N), dtype=torch.uint8, device=dev)
+        tr['payoffs'] = torch.empty((T, N, self.num_players), dtype=torch.float32, device=dev)
+        return tr
+
+    def rollout_random(self, T, out=None):
+        """T env-steps per env with on-device uniform-random agents (the Env.run loop with RandomAgents),
+        auto reset.  Returns trajectory tensors [T, N, ...]: obs/mask the acting player saw, action,
+        player, done, payoffs."""
+        if out is None:
+            out = self.alloc_trajectory(T)
+        tr = RlcTrajectory()
+        for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+            t = out.get(k)
+            if t is not None:
+                assert t.is_contiguous() and t.shape[0] >= T
+                setattr(tr, k, t.data_ptr())
+        with torch.cuda.device(self.device):
+            check(self.L.rlc_rollout_random(self.gid, C.byref(self._buffers()), C.byref(tr), self.num_envs, int(T),
+                                            self._stream()))
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ rollout helpers (callers of the path)
+    def run(self, policy, num_steps, auto_reset=True):
+        """Vector form of Env.run: policy(obs, mask, cur_player) -> int32 actions [N] on the device.
+        Returns (sum of payoffs per seat over finished episodes, episodes finished)."""
+        obs, mask, cur = self.reset()
+        total = torch.zeros(self.num_players, dtype=torch.float64, device=self.device)
+        episodes = torch.zeros((), dtype=torch.int64, device=self.device)
+        for _ in range(num_steps):
+            actions = policy(obs, mask, cur)
+            obs, mask, cur, done, pay = self.step(actions, auto_reset=auto_reset)
+            d = done.bool()
+            total += (pay * d.unsqueeze(1)).sum(0).double()
+            episodes += d.sum()
+        return total, episodes
+
+    def check_errors(self):
+        e = int(self.err.max().item()) if self.num_envs else 0
+        if e:
+            bad = int((self.err != 0).sum().item())
+            raise _lib.RlcError('device error flags set on %d envs (OR=%d: 1 tape exhausted, 2 tape value out of '
+                                'range, 4 illegal action replaced by fallback)' % (bad, e))
+
+
+def random_policy(generator=None):
+    """Uniform-random legal action from a dense mask with torch ops (a stand-in for learned policies;
+    the fused path is VecEnv.rollout_random)."""
+    def policy(obs, mask, cur_player):
+        w = mask.float()
+        return torch.multinomial(w, 1, generator=generator).squeeze(1).int()
+    return policy
+
+
+def vec_tournament(env, num_steps):
+    """rlcard.utils.tournament (utils/utils.py:200-225) over a VecEnv with on-device random agents:
+    mean payoff per seat over the episodes finished in num_steps rollout steps."""
+    tr = env.rollout_random(num_steps, out=env.alloc_trajectory(num_steps, obs=False, mask=False))
+    done = tr['done'].bool()
+    n = int(done.sum().item())
+    tot = (tr['payoffs'] * done.unsqueeze(-1)).sum((0, 1)).double()
+    return (tot / max(n, 1)).tolist(), n

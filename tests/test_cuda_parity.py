@@ -1,0 +1,190 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (rlcard_b200.VecEnv / make),
+against (1) fixtures recorded from the live reference and (2) the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import rlcard_b200
+from replay_util import ALL_GAMES, check_slot, have_fixture, load_fixture, slot_records, slot_tape
+
+pytestmark = pytest.mark.gpu
+
+
+def built(game):
+    return rlcard_b200.game_info(game).state_words > 0
+
+
+GAMES = [g for g in ALL_GAMES if built(g)]
+FIX_GAMES = [g for g in GAMES if have_fixture(g)]
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('obs_dtype', [torch.uint8, torch.float32])
+@pytest.mark.parametrize('game', FIX_GAMES)
+def test_replay_reference_tapes_vectorised(game, obs_dtype):
+    """Replay mode: all fixture slots side by side in one VecEnv, lock-step over the record streams;
+    every obs / legal set / player / done / payoff must equal the reference's."""
+    if rlcard_b200.game_info(game).obs_native_dtype == 1 and obs_dtype == torch.uint8:
+        pytest.skip('fractional obs')
+    fx = load_fixture(game)
+    S = len(fx['slot_seed'])
+    recs = [slot_records(fx, s) for s in range(S)]
+    L = max(len(slot_tape(fx, s)) for s in range(S))
+    tape = np.zeros((S, L + 8), np.uint8)
+    for s in range(S):
+        t = slot_tape(fx, s); tape[s, :len(t)] = t
+    env = rlcard_b200.VecEnv(game, S, mode='replay', obs_dtype=obs_dtype, auto_reset=False)
+    env.set_tape(tape)
+    checked = 0
+    for tick in range(max(len(r) for r in recs)):
+        live = [s for s in range(S) if tick < len(recs[s])]
+        kinds = {s: int(fx['rec_kind'][recs[s][tick]]) for s in live}
+        for kind in (0, 1, 2, 3):
+            group = [s for s in live if kinds[s] == kind]
+            if not group:
+                continue
+            if kind == 0:
+                m = torch.zeros(S, dtype=torch.uint8); m[group] = 1
+                env.reset(m.cuda())
+            elif kind == 1:
+                a = torch.full((S,), -1, dtype=torch.int32)
+                for s in group:
+                    a[s] = int(fx['rec_arg'][recs[s][tick]])
+                env.step(a.cuda())
+            elif kind == 2:
+                seat = torch.zeros(S, dtype=torch.int32)
+                for s in group:
+                    seat[s] = int(fx['rec_arg'][recs[s][tick]])
+                env.get_state(seat.cuda())
+            else:
+                env.get_state(None)
+            obs, mask, cur, done, pay = (to_np(x) for x in (env.obs, env.mask, env.cur_player, env.done, env.payoffs))
+            for s in group:
+                r = recs[s][tick]
+                tag = '%s slot %d rec %d kind %d' % (game, s, r, kind)
+                if kind == 3:
+                    np.testing.assert_array_equal(pay[s].astype(np.float64), fx['rec_payoffs'][r], err_msg=tag)
+                else:
+                    d = int(fx['rec_obs_dim'][r])
+                    np.testing.assert_array_equal(obs[s, :d].astype(np.float64), fx['rec_obs'][r, :d].astype(np.float64), err_msg=tag)
+                    assert not obs[s, d:].any(), tag
+                    np.testing.assert_array_equal(mask[s], fx['legal'][r], err_msg=tag)
+                assert cur[s] == fx['rec_player'][r], tag
+                assert bool(done[s]) == bool(fx['rec_done'][r]), tag
+                checked += 1
+    assert checked == len(fx['rec_slot'])
+    err = to_np(env.err)
+    assert not (err & 3).any()                      # tape never exhausted / out of range
+    pos = to_np(env.tape_pos)
+    for s in range(S):
+        assert pos[s] == len(slot_tape(fx, s))      # and consumed exactly
+
+
+class FacadeAdapter:
+    def __init__(self, env):
+        self.env = env; self.state = None
+    def reset(self):
+        self.state, _ = self.env.reset()
+    def step(self, a):
+        self.state, _ = self.env.step(a)
+    def obs(self, seat):
+        st = self.state if seat < 0 else self.env.get_state(seat)
+        self._last = st
+        return np.asarray(st['obs']).reshape(-1)
+    def legal_mask(self):
+        m = np.zeros(self.env.num_actions, np.uint8); m[list(self._last['legal_actions'].keys())] = 1
+        return m
+    def is_over(self):
+        return self.env.is_over()
+    def player(self):
+        return self.env.get_player_id()
+    def payoffs(self):
+        return self.env.get_payoffs()
+
+
+@pytest.mark.parametrize('game', FIX_GAMES)
+def test_make_facade_reproduces_reference_from_seed(game):
+    """rlcard_b200.make(env, {'seed': s}) == rlcard.make(env, {'seed': s}): np.random.RandomState runs on
+    the device (MT19937 + numpy legacy bounded draws), no tape."""
+    fx = load_fixture(game)
+    for slot in range(min(3, len(fx['slot_seed']))):
+        env = rlcard_b200.make(game, {'seed': int(fx['slot_seed'][slot])})
+        check_slot(fx, slot, FacadeAdapter(env), game + ' (facade)')
+
+
+@pytest.mark.parametrize('obs_dtype', [torch.uint8, torch.float32])
+@pytest.mark.parametrize('game', GAMES)
+def test_throughput_rollout_equals_oracle(game, obs_dtype):
+    """Throughput mode (Philox chance + fused random policy + auto reset) vs the CPU twin, bit-exact on the
+    whole trajectory, across two consecutive launches (state carried in HBM between them)."""
+    if rlcard_b200.game_info(game).obs_native_dtype == 1 and obs_dtype == torch.uint8:
+        pytest.skip('fractional obs')
+    n, T, seed, base = 1000, 40, 987654321, 77           # ragged: n not a multiple of 32
+    env = rlcard_b200.VecEnv(game, n, seed=seed, env_id_base=base, obs_dtype=obs_dtype)
+    orc = oracle.OracleVec(game, n, seed, env0=base)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=4)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            np.testing.assert_array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64),
+                                          err_msg='%s launch %d %s' % (game, launch, k))
+    env.check_errors()
+    assert int(ref['done'].sum()) > 0
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_step_api_equals_fused_rollout(game):
+    """Env.step kernel == fused rollout kernel: feeding the rollout's actions through step() (auto reset)
+    reproduces obs / mask / player / done / payoffs."""
+    n, T, seed = 512, 30, 4242
+    a = rlcard_b200.VecEnv(game, n, seed=seed, obs_dtype=torch.float32)
+    b = rlcard_b200.VecEnv(game, n, seed=seed, obs_dtype=torch.float32)
+    a.reset()
+    tr = a.rollout_random(T)
+    obs, mask, cur = b.reset()
+    for t in range(T):
+        assert torch.equal(obs, tr['obs'][t]) and torch.equal(mask, tr['mask'][t]) and torch.equal(cur, tr['player'][t]), (game, t)
+        obs, mask, cur, done, pay = b.step(tr['action'][t])
+        assert torch.equal(done, tr['done'][t]) and torch.equal(pay, tr['payoffs'][t]), (game, t)
+    assert torch.equal(a.state, b.state)
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_full_size_properties(game):
+    """BASELINE.json sizes: properties that do not need the oracle."""
+    n = {'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384, 'blackjack': 65536}.get(game, 8192)
+    T = 64
+    env = rlcard_b200.VecEnv(game, n, seed=7)
+    env.reset()
+    tr = env.rollout_random(T)
+    env.check_errors()
+    mask, act, done, pay = tr['mask'], tr['action'].long(), tr['done'].bool(), tr['payoffs']
+    assert bool((mask.gather(2, act.unsqueeze(-1)) == 1).all())          # every action taken was legal
+    assert bool((mask.sum(-1) >= 1).all())
+    assert bool((pay[~done] == 0).all())
+    if game in ('leduc-holdem', 'limit-holdem'):
+        assert bool((pay.sum(-1) == 0).all())                              # zero-sum
+        assert bool(((pay * 2) == (pay * 2).round()).all())                # multiples of 0.5
+    assert int(done.sum()) > n                                             # episodes finish and restart
+    # shard invariance: envs [n/2, n) of this run == a second VecEnv with env_id_base n/2
+    env2 = rlcard_b200.VecEnv(game, n // 2, seed=7, env_id_base=n // 2)
+    env2.reset()
+    tr2 = env2.rollout_random(T)
+    for k in ('obs', 'mask', 'action', 'done', 'payoffs'):
+        assert torch.equal(tr[k][:, n // 2:], tr2[k]), k
+
+
+def test_illegal_action_fallback_and_noop():
+    env = rlcard_b200.VecEnv('leduc-holdem', 64, seed=3, auto_reset=False)
+    obs, mask, cur = env.reset()
+    before = env.state.clone()
+    env.step(torch.full((64,), -1, dtype=torch.int32, device='cuda'))     # no-op
+    assert torch.equal(before, env.state)
+    env.step(torch.full((64,), 3, dtype=torch.int32, device='cuda'))      # 'check' is illegal for the small blind
+    assert bool((env.err & 4).all())                                       # -> fold fallback (envs/leducholdem.py:90-96)
+    assert bool(env.done.all())
