@@ -41,6 +41,7 @@ typedef struct orc_chance {
 
 uint32_t orc_below(orc_chance *ch, uint32_t n);          /* uniform in [0, n) */
 void orc_shuffle_u8(orc_chance *ch, uint8_t *x, int n);   /* numpy legacy list shuffle */
+void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail);
 void orc_mt_init_by_array(orc_chance *ch, const uint32_t *key, int len);
 uint32_t orc_mt_next(orc_chance *ch);
 void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t out[4]);

@@ -110,6 +110,17 @@ void orc_shuffle_u8(orc_chance *ch, uint8_t *x, int n) {
     }
 }
 
+/* Shuffle of a deck from which only the last `tail` positions are ever dealt (deck.pop()).
+ * Tape / MT19937 modes make every draw the reference made; throughput (Philox) mode, whose draw
+ * layout is this project's own spec, makes only the `tail` observable swaps. */
+void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail) {
+    int stop = (ch->kind == ORC_CHANCE_PHILOX && tail < n - 1) ? n - tail : 1;
+    for (int i = n - 1; i >= stop; i--) {
+        uint32_t j = orc_below(ch, (uint32_t)i + 1u);
+        uint8_t t = x[i]; x[i] = x[j]; x[j] = t;
+    }
+}
+
 /* ------------------------------------------------------------------ env handles */
 extern const orc_game_vt orc_vt_blackjack, orc_vt_leduc, orc_vt_limit, orc_vt_uno, orc_vt_doudizhu, orc_vt_scout;
 const orc_game_vt *orc_game(int g) {

@@ -67,7 +67,7 @@ static void leduc_create(void *s) { (void)s; }
 static int leduc_reset(void *s, orc_chance *ch) {
     leduc_t *g = (leduc_t *)s;
     for (int i = 0; i < 6; i++) g->deck[i] = (uint8_t)i;
-    orc_shuffle_u8(ch, g->deck, 6); g->deck_len = 6;
+    orc_shuffle_tail_u8(ch, g->deck, 6, 3); g->deck_len = 6;
     for (int i = 0; i < 2; i++) { g->hand[i] = g->deck[--g->deck_len]; g->in_chips[i] = 0; g->folded[i] = 0; }
     int sb = (int)orc_below(ch, 2), bb = (sb + 1) % 2;
     g->in_chips[bb] = 2; g->in_chips[sb] = 1;
@@ -192,7 +192,7 @@ static int limit_reset(void *s, orc_chance *ch) {
     limit_t *g = (limit_t *)s;
     memcpy(g->shown_raise_nums, g->raise_nums, sizeof g->raise_nums);   /* stale list seen by the reset() state */
     for (int i = 0; i < 52; i++) g->deck[i] = (uint8_t)i;               /* utils/utils.py:34-43 == card2index.json */
-    orc_shuffle_u8(ch, g->deck, 52); g->deck_len = 52;
+    orc_shuffle_tail_u8(ch, g->deck, 52, 9); g->deck_len = 52;
     for (int i = 0; i < 4; i++) g->hand[i % 2][i / 2] = g->deck[--g->deck_len];
     g->n_public = 0;
     int sb = (int)orc_below(ch, 2), bb = (sb + 1) % 2;

@@ -1,0 +1,205 @@
+// game_uno.cuh -- UNO, 2 players, 108 cards, 61 actions, one env per thread.
+// Reference: rlcard/games/uno/{game,round,dealer,card,utils}.py, rlcard/envs/uno.py.
+//
+// A card is its 6-bit code 15*colour + trait, which is the frozen UnoCard.str (card.py:22): for the
+// eight wild cards the colour in the code is the ORIGINAL deck colour, so the code also identifies
+// the physical wild card (Q-UNO1).  The mutable UnoCard.color only ever matters for the target, which
+// is kept by value as (code, current colour).  Non-wild hand cards are interchangeable, so a hand is
+// 52 two-bit counters plus two arrival-ordered lists of held wild / wild_draw_4 cards (Q-UNO2: the
+// first held card of that trait is the one played, round.py:71-75).  Draw pile and played pile are
+// ordered lists (replace_deck shuffles deck+played in list order, round.py:155-160).
+//
+// Game words (38): [0..26] 108 card bytes: draw pile at [0,dl), played pile stored downwards from 107
+//   [27..30] seat 0 counters per colour (13 x 2 bits)   [31] seat 0 wild lists
+//   [32..35] seat 1 counters                            [36] seat 1 wild lists
+//   [37] dl[0:7) pl[7:14) target code[14:20) target colour[20:22) direction[22] current[23] winner+1[24:26) err8[26]
+// wild list word: wild: count[0:3) entries[3:11) ; wild_draw_4: count[11:14) entries[14:22)
+#pragma once
+#include "common.cuh"
+
+namespace rlc {
+
+struct Uno {
+    static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = 38, MASK_WORDS = 2;
+    static constexpr int kMaxResetDraws = 256;
+    uint8_t cards[108];
+    uint32_t hc[2][4], hw[2];
+    int dl, pl, tcode, tcolor, dir, cur, winner;   // dir: 0 = +1, 1 = -1 ; winner: -1 none
+
+    __device__ void load(const uint32_t *st, size_t n, size_t i) {
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+            const uint32_t v = st[(size_t)k * n + i];
+            cards[4 * k] = v & 255u; cards[4 * k + 1] = (v >> 8) & 255u; cards[4 * k + 2] = (v >> 16) & 255u; cards[4 * k + 3] = v >> 24;
+        }
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) hc[p][c] = st[(size_t)(27 + 5 * p + c) * n + i];
+            hw[p] = st[(size_t)(31 + 5 * p) * n + i];
+        }
+        const uint32_t m = st[(size_t)37 * n + i];
+        dl = bf_get(m, 0, 7); pl = bf_get(m, 7, 7); tcode = bf_get(m, 14, 6); tcolor = bf_get(m, 20, 2);
+        dir = bf_get(m, 22, 1); cur = bf_get(m, 23, 1); winner = (int)bf_get(m, 24, 2) - 1;
+    }
+    __device__ void store(uint32_t *st, size_t n, size_t i) const {
+#pragma unroll
+        for (int k = 0; k < 27; k++)
+            st[(size_t)k * n + i] = cards[4 * k] | (cards[4 * k + 1] << 8) | (cards[4 * k + 2] << 16) | ((uint32_t)cards[4 * k + 3] << 24);
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) st[(size_t)(27 + 5 * p + c) * n + i] = hc[p][c];
+            st[(size_t)(31 + 5 * p) * n + i] = hw[p];
+        }
+        st[(size_t)37 * n + i] = dl | (pl << 7) | (tcode << 14) | (tcolor << 20) | (dir << 22) | (cur << 23) | ((winner + 1) << 24);
+    }
+
+    // ---- list primitives
+    __device__ __forceinline__ int pop_deck(int &err) { if (dl <= 0) { err |= 8; return -1; } return cards[--dl]; }   // Q-UNO4
+    __device__ __forceinline__ void push_played(int code) { cards[107 - pl] = (uint8_t)code; pl++; }
+    __device__ __forceinline__ void to_hand(int p, int code) {
+        const int c = code / 15, t = code - 15 * c;
+        if (t < 13) hc[p][c] += 1u << (2 * t);
+        else {
+            const int base = t == 13 ? 0 : 11;
+            const int cnt = (hw[p] >> base) & 7;
+            hw[p] = (hw[p] & ~(3u << (base + 3 + 2 * cnt))) | ((uint32_t)c << (base + 3 + 2 * cnt));
+            hw[p] += 1u << base;
+        }
+    }
+    __device__ __forceinline__ int wild_count(int p, int t) const { return (hw[p] >> (t == 13 ? 0 : 11)) & 7; }
+    __device__ __forceinline__ int take_first_wild(int p, int t) {        // original colour of the first held wild of trait t
+        const int base = t == 13 ? 0 : 11;
+        const uint32_t field = (hw[p] >> base) & 0x7ffu;
+        const int cnt = field & 7, first = (field >> 3) & 3;
+        const uint32_t rest = ((field >> 5) << 3) | (uint32_t)(cnt - 1);  // drop entry 0, count - 1
+        hw[p] = (hw[p] & ~(0x7ffu << base)) | ((rest & 0x7ffu) << base);
+        return first;
+    }
+    __device__ __forceinline__ bool hand_empty(int p) const { return (hc[p][0] | hc[p][1] | hc[p][2] | hc[p][3]) == 0 && (hw[p] & 0x3807u) == 0; }
+    template <class Ch> __device__ void shuffle_deck(Ch &ch) { shuffle_tail_u8(ch, cards, dl, dl); }   // dealer.py:14-17
+    template <class Ch> __device__ void replace_deck(Ch &ch) {            // round.py:155-160
+        uint8_t tmp[108];
+        for (int k = 0; k < pl; k++) tmp[k] = cards[107 - k];
+        for (int k = 0; k < pl; k++) cards[dl + k] = tmp[k];
+        dl += pl; pl = 0;
+        shuffle_deck(ch);
+    }
+    __device__ __forceinline__ void deal(int p, int num, int &err) {      // dealer.py:19-26
+        for (int k = 0; k < num; k++) { const int c = pop_deck(err); if (c >= 0) to_hand(p, c); }
+    }
+
+    // games/uno/game.py:22-56, round.py:24-52, dealer.py:28-39, utils.py:31-52 (deck order)
+    template <class Ch> __device__ void reset(Ch &ch) {
+        int n = 0, err = 0;
+        for (int c = 0; c < 4; c++) {
+            for (int t = 0; t < 10; t++) { cards[n++] = (uint8_t)(15 * c + t); if (t) cards[n++] = (uint8_t)(15 * c + t); }
+            for (int t = 10; t < 13; t++) { cards[n++] = (uint8_t)(15 * c + t); cards[n++] = (uint8_t)(15 * c + t); }
+            cards[n++] = (uint8_t)(15 * c + 13); cards[n++] = (uint8_t)(15 * c + 14);
+        }
+        dl = 108; pl = 0;
+#pragma unroll
+        for (int p = 0; p < 2; p++) { hc[p][0] = hc[p][1] = hc[p][2] = hc[p][3] = 0; hw[p] = 0; }
+        shuffle_deck(ch);
+        deal(0, 7, err); deal(1, 7, err);
+        dir = 0; cur = 0; winner = -1;
+        int top = cards[--dl];
+        while (top % 15 == 14) { cards[dl++] = (uint8_t)top; shuffle_deck(ch); top = cards[--dl]; }
+        tcode = top; tcolor = top / 15;
+        if (top % 15 == 13) tcolor = (int)ch.below(4u);
+        push_played(top);
+        const int t = top % 15;                                            // round.py:38-52
+        if (t == 10) cur = 1;
+        else if (t == 11) { dir = 1; cur = 1; }
+        else if (t == 12) deal(0, 2, err);
+    }
+    __device__ __forceinline__ int player() const { return cur; }
+    __device__ __forceinline__ bool over() const { return winner >= 0; }   // game.py:154-160
+    // round.py:96-135 as a 61-bit set
+    __device__ void legal(uint32_t (&m)[2]) const {
+        uint64_t bits = 0;
+        const bool twild = (tcode % 15) >= 13;
+        const int ttrait = tcode % 15;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t w = hc[cur][c];
+            uint32_t have = 0;
+#pragma unroll
+            for (int t = 0; t < 13; t++) have |= ((w >> (2 * t)) & 3u) ? (1u << t) : 0u;
+            uint32_t ok = (c == tcolor) ? have : 0u;
+            if (!twild) ok |= have & (1u << ttrait);
+            bits |= (uint64_t)ok << (15 * c);
+        }
+        if (wild_count(cur, 13)) bits |= (1ull << 13) | (1ull << 28) | (1ull << 43) | (1ull << 58);
+        if (!bits && wild_count(cur, 14)) bits = (1ull << 14) | (1ull << 29) | (1ull << 44) | (1ull << 59);
+        if (!bits) bits = 1ull << 60;
+        m[0] = (uint32_t)bits; m[1] = (uint32_t)(bits >> 32);
+    }
+    // round.py:194-227 (two players)
+    template <class Ch> __device__ void non_number(int code, int color, Ch &ch, int &err) {
+        const int t = code % 15;
+        int current = cur;
+        if (t == 11) dir ^= 1;
+        else if (t == 10) current ^= 1;
+        else if (t == 12 || t == 14) {
+            const int need = t == 12 ? 2 : 4;
+            if (dl < need) replace_deck(ch);
+            deal(current ^ 1, need, err);
+            current ^= 1;
+        }
+        cur = current ^ 1;
+        tcode = code; tcolor = color;
+    }
+    // env.py:65-86, envs/uno.py:39-45, game.py:58-81, round.py:54-94, 162-192
+    template <class Ch> __device__ void step(int id, Ch &ch, int &err) {
+        uint32_t m[2];
+        legal(m);
+        if (id < 0 || id > 60 || !((m[id >> 5] >> (id & 31)) & 1u)) {   // reference: random legal from the GLOBAL rng
+            err |= 4; id = m[0] ? __ffs(m[0]) - 1 : 32 + __ffs(m[1]) - 1;
+        }
+        if (id == 60) {                                                 // _perform_draw_action
+            if (dl == 0) replace_deck(ch);
+            const int card = pop_deck(err);
+            if (card < 0) { cur ^= 1; return; }
+            const int c = card / 15, t = card - 15 * c;
+            if (t >= 13) { tcolor = (int)ch.below(4u); tcode = card; push_played(card); cur ^= 1; }
+            else if (c == tcolor) {
+                push_played(card);
+                if (t < 10) { tcode = card; tcolor = c; cur ^= 1; }
+                else non_number(card, c, ch, err);
+            } else { to_hand(cur, card); cur ^= 1; }
+            return;
+        }
+        const int color = id / 15, trait = id - 15 * color;
+        int code = id;
+        if (trait >= 13) code = 15 * take_first_wild(cur, trait) + trait;
+        else hc[cur][color] -= 1u << (2 * trait);
+        if (hand_empty(cur)) winner = cur;
+        push_played(code);
+        if (trait < 10) { cur ^= 1; tcode = code; tcolor = color; }
+        else non_number(code, color, ch, err);
+    }
+    __device__ __forceinline__ void payoffs(float *out) const {          // game.py:108-118
+        out[0] = winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f);
+        out[1] = winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f);
+    }
+    // envs/uno.py:24-33, utils.py:69-127 (row pre-zeroed): planes 0..2 hand copies, plane 3 target
+    template <class T> __device__ void encode_obs(int seat, bool, T *row) const {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t w = hc[seat][c];
+#pragma unroll
+            for (int t = 0; t < 13; t++) {
+                const int k = (w >> (2 * t)) & 3;
+                row[60 * k + 15 * c + t] = (T)1;                       // k == 0 keeps plane 0 set
+            }
+            const int kw = wild_count(seat, 13) ? 60 : 0, k4 = wild_count(seat, 14) ? 60 : 0;
+            row[kw + 15 * c + 13] = (T)1;
+            row[k4 + 15 * c + 14] = (T)1;
+        }
+        row[180 + tcode] = (T)1;                                       // target.str: original colour (Q-UNO1)
+    }
+};
+
+}  // namespace rlc
