@@ -234,7 +234,7 @@ def main():
     # action from the mask it received (numpy), actions go H2D from pinned memory, Env.step runs, and obs /
     # mask / player / done / payoffs come back D2H into pinned memory, every step.
     e2e = None
-    if info.num_actions == 4:
+    if info.num_actions == 4 and args.e2e_steps > 0:
         Ke = args.e2e_steps
         env2 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 1, env_id_base=rank * E, obs_dtype=odt)
         h_act = torch.zeros(E, dtype=torch.int32).pin_memory()

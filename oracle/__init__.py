@@ -55,7 +55,7 @@ def lib():
         L.orc_envs_rollout.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32]
         L.orc_envs_episodes.restype = i64; L.orc_envs_episodes.argtypes = [vp]
         L.orc_holdem_strength7.restype = C.c_uint32; L.orc_holdem_strength7.argtypes = [vp]
-        L.orc_philox_draw.restype = C.c_uint32; L.orc_philox_draw.argtypes = [C.c_uint32] * 6
+        L.orc_philox_word.restype = C.c_uint32; L.orc_philox_word.argtypes = [C.c_uint32] * 7
         L.orc_philox4x32_10.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         _LIB = L
     return _LIB

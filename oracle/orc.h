@@ -32,7 +32,7 @@ typedef struct orc_chance {
     /* tape (replay of recorded reference draws) */
     const uint8_t *tape; int64_t tape_len, tape_pos; int tape_err;
     /* philox (throughput mode; spec shared with the CUDA kernels) */
-    uint32_t key0, key1, env_id, episode, draw;
+    uint32_t key0, key1, env_id, episode, t, draw;
     /* numpy-legacy MT19937 (np.random.RandomState) */
     uint32_t mt[624]; int mti;
     /* optional recording of the draws made (any kind) */
@@ -45,7 +45,7 @@ void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail);
 void orc_mt_init_by_array(orc_chance *ch, const uint32_t *key, int len);
 uint32_t orc_mt_next(orc_chance *ch);
 void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t out[4]);
-uint32_t orc_philox_draw(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t stream, uint32_t draw);
+uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t t, uint32_t block, uint32_t word);
 
 /* ---- per-game engines ---- */
 typedef struct orc_game_vt {

@@ -69,12 +69,13 @@ void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-/* throughput-mode draw layout (DESIGN.md "Philox streams"): counter = (draw/4, episode,
- * env_id, stream), key = seed; the draw is word draw%4 of the block. */
-uint32_t orc_philox_draw(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t stream, uint32_t draw) {
-    uint32_t ctr[4] = { draw >> 2, episode, env_id, stream }, out[4];
+/* throughput-mode draw layout (DESIGN.md "Philox streams"): block b of step (episode e, step t) of an
+ * env has counter = (t, e, env_id, b), key = seed.  Block 0 = [policy word, chance draw 0, 1, 2];
+ * block b >= 1 = chance draws 3+4(b-1) .. 6+4(b-1).  word 0..3 selects inside the block. */
+uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t t, uint32_t block, uint32_t word) {
+    uint32_t ctr[4] = { t, episode, env_id, block }, out[4];
     orc_philox4x32_10(ctr, k0, k1, out);
-    return out[draw & 3u];
+    return out[word & 3u];
 }
 
 /* ------------------------------------------------------------------ bounded draws */
@@ -90,8 +91,10 @@ uint32_t orc_below(orc_chance *ch, uint32_t n) {
         if (v >= n) { ch->tape_err |= 2; v = n - 1; }
         break;
     case ORC_CHANCE_PHILOX:
-        v = (uint32_t)(((uint64_t)orc_philox_draw(ch->key0, ch->key1, ch->env_id, ch->episode, 0u, ch->draw) * n) >> 32);
-        ch->draw++;
+        {
+            uint32_t d = ch->draw++, blk = d < 3 ? 0u : 1u + ((d - 3u) >> 2), word = d < 3 ? d + 1u : ((d - 3u) & 3u);
+            v = (uint32_t)(((uint64_t)orc_philox_word(ch->key0, ch->key1, ch->env_id, ch->episode, ch->t, blk, word) * n) >> 32);
+        }
         break;
     default: {
         uint32_t max = n - 1, mask = max;
@@ -134,7 +137,7 @@ const orc_game_vt *orc_game(int g) {
     }
     return NULL;
 }
-struct orc_env { const orc_game_vt *vt; void *st; orc_chance ch; uint32_t t; };
+struct orc_env { const orc_game_vt *vt; void *st; orc_chance ch; uint32_t t, episode; };
 
 static void env_init(orc_env *e, int game_id) {
     memset(e, 0, sizeof *e);
@@ -154,7 +157,7 @@ void orc_env_set_tape(orc_env *e, const uint8_t *tape, int64_t len) {
 }
 void orc_env_set_philox(orc_env *e, uint64_t seed, uint32_t env_id) {
     e->ch.kind = ORC_CHANCE_PHILOX; e->ch.key0 = (uint32_t)seed; e->ch.key1 = (uint32_t)(seed >> 32);
-    e->ch.env_id = env_id; e->ch.episode = 0; e->ch.draw = 0;
+    e->ch.env_id = env_id; e->ch.episode = 0; e->ch.t = 0xffffffffu; e->ch.draw = 0;
 }
 void orc_env_set_mt(orc_env *e, const uint32_t *key, int len) { orc_mt_init_by_array(&e->ch, key, len); }
 void orc_env_record(orc_env *e, uint8_t *buf, int64_t cap) { e->ch.rec = buf; e->ch.rec_cap = cap; e->ch.rec_len = 0; }
@@ -199,9 +202,11 @@ typedef struct {
     uint8_t *done; float *payoffs; int64_t episodes;
 } rollout_job;
 
+/* first deal: a reset outside any step (t = 0xffffffff of episode 0); later deals happen inside the step
+ * that ended the previous episode and continue that step's chance draws */
 static void env_new_episode(orc_env *e, int first) {
-    if (!first) e->ch.episode++;
-    e->ch.draw = 0;
+    if (first) { e->ch.episode = 0; e->ch.t = 0xffffffffu; e->ch.draw = 0; e->episode = 0; }
+    else e->episode++;
     e->t = 0;
     e->vt->reset(e->st, &e->ch);
 }
@@ -228,7 +233,8 @@ static void *rollout_worker(void *arg) {
             if (J->mask) memcpy(J->mask + row * A, m, (size_t)A);
             if (J->player) J->player[row] = pl;
             /* uniform-random legal action: k-th legal id in ascending order, k from the policy stream */
-            uint32_t r = orc_philox_draw(e->ch.key0, e->ch.key1, e->ch.env_id, e->ch.episode, 1u, e->t);
+            e->ch.episode = e->episode; e->ch.t = e->t; e->ch.draw = 0;      /* this step's Philox coordinates */
+            uint32_t r = orc_philox_word(e->ch.key0, e->ch.key1, e->ch.env_id, e->episode, e->t, 0u, 0u);
             int k = (int)(((uint64_t)r * (uint32_t)cnt) >> 32), a = 0;
             for (a = 0; a < A; a++) if (m[a] && k-- == 0) break;
             if (J->action) J->action[row] = a;

@@ -67,7 +67,12 @@ static void leduc_create(void *s) { (void)s; }
 static int leduc_reset(void *s, orc_chance *ch) {
     leduc_t *g = (leduc_t *)s;
     for (int i = 0; i < 6; i++) g->deck[i] = (uint8_t)i;
-    orc_shuffle_tail_u8(ch, g->deck, 6, 3); g->deck_len = 6;
+    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: one word deals the three cards */
+        uint32_t x = orc_below(ch, 120);
+        int j[3] = { (int)(x / 20), (int)((x / 4) % 5), (int)(x % 4) };
+        for (int s = 0; s < 3; s++) { uint8_t t = g->deck[5 - s]; g->deck[5 - s] = g->deck[j[s]]; g->deck[j[s]] = t; }
+    } else orc_shuffle_tail_u8(ch, g->deck, 6, 3);
+    g->deck_len = 6;
     for (int i = 0; i < 2; i++) { g->hand[i] = g->deck[--g->deck_len]; g->in_chips[i] = 0; g->folded[i] = 0; }
     int sb = (int)orc_below(ch, 2), bb = (sb + 1) % 2;
     g->in_chips[bb] = 2; g->in_chips[sb] = 1;
@@ -192,10 +197,20 @@ static int limit_reset(void *s, orc_chance *ch) {
     limit_t *g = (limit_t *)s;
     memcpy(g->shown_raise_nums, g->raise_nums, sizeof g->raise_nums);   /* stale list seen by the reset() state */
     for (int i = 0; i < 52; i++) g->deck[i] = (uint8_t)i;               /* utils/utils.py:34-43 == card2index.json */
-    orc_shuffle_tail_u8(ch, g->deck, 52, 9); g->deck_len = 52;
+    int sb;
+    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: three words deal nine cards + blind */
+        uint32_t x1 = orc_below(ch, 52u * 51u * 50u), x2 = orc_below(ch, 49u * 48u * 47u), x3 = orc_below(ch, 46u * 45u * 44u * 2u);
+        uint32_t z = x3 >> 1;
+        int j[9] = { (int)(x1 / 2550), (int)((x1 / 50) % 51), (int)(x1 % 50), (int)(x2 / 2256), (int)((x2 / 47) % 48),
+                     (int)(x2 % 47), (int)(z / 1980), (int)((z / 44) % 45), (int)(z % 44) };
+        for (int s = 0; s < 9; s++) { uint8_t t = g->deck[51 - s]; g->deck[51 - s] = g->deck[j[s]]; g->deck[j[s]] = t; }
+        sb = (int)(x3 & 1u);
+    } else { orc_shuffle_tail_u8(ch, g->deck, 52, 9); sb = -1; }
+    g->deck_len = 52;
     for (int i = 0; i < 4; i++) g->hand[i % 2][i / 2] = g->deck[--g->deck_len];
     g->n_public = 0;
-    int sb = (int)orc_below(ch, 2), bb = (sb + 1) % 2;
+    if (sb < 0) sb = (int)orc_below(ch, 2);
+    int bb = (sb + 1) % 2;
     g->in_chips[0] = g->in_chips[1] = 0; g->folded[0] = g->folded[1] = 0;
     g->in_chips[bb] = 2; g->in_chips[sb] = 1;
     g->game_pointer = (bb + 1) % 2;

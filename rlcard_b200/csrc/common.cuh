@@ -9,9 +9,15 @@ namespace rlc {
 constexpr int kWarp = 32;
 
 // ------------------------------------------------------------------------------------------
-// Philox4x32-10.  Draw layout (DESIGN.md "Philox streams"): counter = (draw/4, episode, env,
-// stream), key = 64-bit seed; draw d is word d%4 of its block.  stream 0 = chance (deal),
-// stream 1 = policy (uniform-random legal action, one draw per env-step, d = step in episode).
+// Philox4x32-10, throughput-mode draw layout (DESIGN.md "Philox streams").
+// One block per env-step, computed unconditionally (no divergence between lanes whose episodes end
+// at different times):  block(b) of step (episode e, step-in-episode t) of env i has
+//     counter = (t, e, global env id, b),  key = 64-bit seed.
+//   block 0 = [ policy word | chance draw 0 | chance draw 1 | chance draw 2 ]
+//   block b>=1 = chance draws 3+4(b-1) .. 6+4(b-1)
+// "chance draws of a step" are, in order, every bounded draw the engine makes while applying the
+// action of that step AND while dealing the next episode if the step ended one (auto reset).
+// A reset that is not part of a step (rlc_reset) uses t = 0xffffffff of the episode it starts.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1,
@@ -26,22 +32,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
-
-struct PhiloxStream {   // one (env, episode, stream) sequence with a one-block register cache
-    uint32_t k0, k1, env, episode, stream;
-    uint32_t b0, b1, b2, b3, blk;
-    __device__ __forceinline__ void init(uint64_t seed, uint32_t env_, uint32_t episode_, uint32_t stream_) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; episode = episode_; stream = stream_;
-        blk = 0xffffffffu; b0 = b1 = b2 = b3 = 0;
-    }
-    __device__ __forceinline__ void new_episode(uint32_t e) { episode = e; blk = 0xffffffffu; }
-    __device__ __forceinline__ uint32_t word(uint32_t d) {
-        const uint32_t q = d >> 2;
-        if (q != blk) { philox4x32_10(q, episode, env, stream, k0, k1, b0, b1, b2, b3); blk = q; }
-        const uint32_t lo = (d & 1u) ? b1 : b0, hi = (d & 1u) ? b3 : b2;
-        return (d & 2u) ? hi : lo;
-    }
-};
+constexpr uint32_t kResetStep = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------
 // Chance sources.  All engines draw through below(n) (uniform in [0,n)); skip_fy(i_hi, i_lo)
@@ -51,10 +42,33 @@ struct PhiloxStream {   // one (env, episode, stream) sequence with a one-block 
 // ------------------------------------------------------------------------------------------
 struct ChancePhilox {
     static constexpr int kKind = 0;
-    PhiloxStream s; uint32_t draw; int err;
-    __device__ __forceinline__ uint32_t below(uint32_t n) { return __umulhi(s.word(draw++), n); }
+    uint32_t k0, k1, env, episode, t;
+    uint32_t w0, w1, w2, w3;           // block 0 of the current step
+    uint32_t x0, x1, x2, x3, xblk;     // one cached extra block
+    uint32_t d; int err;
+    __device__ __forceinline__ void init(uint64_t seed, uint32_t env_) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; err = 0; d = 0; xblk = 0;
+        w0 = w1 = w2 = w3 = x0 = x1 = x2 = x3 = 0; episode = t = 0;
+    }
+    __device__ __forceinline__ void begin(uint32_t episode_, uint32_t t_) {
+        episode = episode_; t = t_; d = 0; xblk = 0;
+        philox4x32_10(t, episode, env, 0u, k0, k1, w0, w1, w2, w3);
+    }
+    __device__ __forceinline__ uint32_t policy_word() const { return w0; }
+    __device__ __forceinline__ uint32_t raw() {
+        uint32_t r;
+        if (d < 3u) r = d == 0 ? w1 : (d == 1 ? w2 : w3);
+        else {
+            const uint32_t q = 1u + ((d - 3u) >> 2), l = (d - 3u) & 3u;
+            if (q != xblk) { philox4x32_10(t, episode, env, q, k0, k1, x0, x1, x2, x3); xblk = q; }
+            const uint32_t lo = (l & 1u) ? x1 : x0, hi = (l & 1u) ? x3 : x2;
+            r = (l & 2u) ? hi : lo;
+        }
+        d++;
+        return r;
+    }
+    __device__ __forceinline__ uint32_t below(uint32_t n) { return __umulhi(raw(), n); }
     __device__ __forceinline__ void skip_fy(int, int) {}
-    __device__ __forceinline__ void new_episode(uint32_t e) { s.new_episode(e); draw = 0; }
 };
 
 struct ChanceTape {
@@ -68,7 +82,7 @@ struct ChanceTape {
         return v;
     }
     __device__ __forceinline__ void skip_fy(int i_hi, int i_lo) { if (i_hi >= i_lo) pos += i_hi - i_lo + 1; }
-    __device__ __forceinline__ void new_episode(uint32_t) {}
+    __device__ __forceinline__ void begin(uint32_t, uint32_t) {}
 };
 
 // np.random.RandomState (MT19937) with numpy's legacy bounded draws: mask-and-reject on 32-bit
@@ -102,7 +116,7 @@ struct ChanceMt {
         return v;
     }
     __device__ void skip_fy(int i_hi, int i_lo) { for (int i = i_hi; i >= i_lo; i--) (void)below((uint32_t)i + 1u); }
-    __device__ __forceinline__ void new_episode(uint32_t) {}
+    __device__ __forceinline__ void begin(uint32_t, uint32_t) {}
 };
 
 // RandomState.shuffle on a list: for i = n-1 .. 1: j = below(i+1); swap(x[i], x[j]).
@@ -169,15 +183,10 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
 
 // per-env header words stored in front of the game words of the state
 struct EnvHeader {
-    uint32_t episode;   // episodes started - 1 (Philox counter word)
-    uint32_t t;         // env-steps taken in the current episode (policy draw index)
-    uint32_t draw;      // chance draws made in the current episode (Philox)
-    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) {
-        episode = st[i]; const uint32_t w = st[n + i]; t = w & 0xffffu; draw = w >> 16;
-    }
-    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const {
-        st[i] = episode; st[n + i] = (t & 0xffffu) | (draw << 16);
-    }
+    uint32_t episode;   // episodes started (0 = never reset); the running episode has index episode-1
+    uint32_t t;         // env-steps taken in the running episode
+    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) { episode = st[i]; t = st[n + i]; }
+    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const { st[i] = episode; st[n + i] = t; }
 };
 constexpr int kHeaderWords = 2;
 

@@ -8,6 +8,21 @@ namespace rlc {
 
 enum { kCall = 0, kRaise = 1, kFold = 2, kCheck = 3 };   // envs/leducholdem.py:26
 
+// Reverse Fisher-Yates (RandomState.shuffle) over an identity deck of n cards of which only the last K
+// positions are ever popped: step s swaps positions n-1-s and j[s]; c[s] is the card left at position
+// n-1-s, i.e. the s-th deck.pop().  The card is found by tracing position j[s] back through the earlier
+// swaps (it can only have been moved by a swap whose partner j[r] it equals) -- no deck array needed.
+template <int K>
+__device__ __forceinline__ void fy_tail_cards(int n, const int (&j)[K], int (&c)[K]) {
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        int pos = j[s];
+#pragma unroll
+        for (int r = s - 1; r >= 0; r--) pos = (pos == j[r]) ? n - 1 - r : pos;
+        c[s] = pos;
+    }
+}
+
 // games/limitholdem/round.py as plain registers (2 players)
 struct BetRound {
     int pointer, have_raised, not_raise_num, raised0, raised1;
@@ -64,15 +79,17 @@ struct Leduc {
     }
     // games/leducholdem/game.py:46-95; deck [SJ,HJ,SQ,HQ,SK,HK] (dealer.py:10) kept as nibbles
     template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
-        uint32_t deck = 0x543210u;
-#pragma unroll
-        for (int i = 5; i >= 3; i--) {                       // pops take positions 5,4,3 only
-            const int j = (int)ch.below((uint32_t)i + 1u);
-            const uint32_t a = (deck >> (4 * i)) & 15u, b = (deck >> (4 * j)) & 15u, x = a ^ b;
-            deck ^= (x << (4 * i)) | (x << (4 * j));
+        int j[3];                                            // Fisher-Yates swap partners of positions 5,4,3
+        if constexpr (Ch::kKind == 0) {                      // throughput: one 32-bit word deals all three cards
+            const uint32_t x = ch.below(120u);
+            j[0] = (int)(x / 20u); j[1] = (int)((x >> 2) % 5u); j[2] = (int)(x & 3u);
+        } else {                                             // replay: the reference's draws, i = 5,4,3 (2,1 unobserved)
+            j[0] = (int)ch.below(6u); j[1] = (int)ch.below(5u); j[2] = (int)ch.below(4u);
+            ch.skip_fy(2, 1);
         }
-        ch.skip_fy(2, 1);
-        hand0 = (deck >> 21) & 3; hand1 = (deck >> 17) & 3; pub = (deck >> 13) & 3; pub_dealt = 0;   // rank = card>>1
+        int c[3];
+        fy_tail_cards<3>(6, j, c);                           // cards popped from positions 5,4,3
+        hand0 = c[0] >> 1; hand1 = c[1] >> 1; pub = c[2] >> 1; pub_dealt = 0;   // rank = card>>1
         const int sb = (int)ch.below(2u);
         chips0 = sb == 0 ? 1 : 2; chips1 = sb == 0 ? 2 : 1;
         fold0 = fold1 = 0; rc = 0;
@@ -104,7 +121,7 @@ struct Leduc {
         else if (pub_dealt && hand0 == pub) { w0 = 1; w1 = 0; }
         else if (pub_dealt && hand1 == pub) { w0 = 0; w1 = 1; }
         else { w0 = hand0 >= hand1; w1 = hand1 >= hand0; }
-        const float each = (float)(chips0 + chips1) / (float)(w0 + w1);
+        const float each = (float)(chips0 + chips1) * ((w0 & w1) ? 0.5f : 1.0f);   // total / #winners
         out[0] = (w0 ? each - (float)chips0 : -(float)chips0) * 0.5f;
         out[1] = (w1 ? each - (float)chips1 : -(float)chips1) * 0.5f;
     }
@@ -207,14 +224,22 @@ struct Limit {
         st[3 * n + i] = rn | (rn_shown << 12);
     }
     // games/limitholdem/game.py:46-103: only the last 9 deck positions are ever popped
-    template <class Ch> __device__ void reset(Ch &ch) {
-        uint8_t deck[52];
+    template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
+        int j[9], sb;                                          // swap partners of positions 51..43
+        if constexpr (Ch::kKind == 0) {                        // throughput: three words deal nine cards + blind
+            const uint32_t x1 = ch.below(52u * 51u * 50u), x2 = ch.below(49u * 48u * 47u), x3 = ch.below(46u * 45u * 44u * 2u);
+            j[0] = (int)(x1 / 2550u); j[1] = (int)((x1 / 50u) % 51u); j[2] = (int)(x1 % 50u);
+            j[3] = (int)(x2 / 2256u); j[4] = (int)((x2 / 47u) % 48u); j[5] = (int)(x2 % 47u);
+            const uint32_t z = x3 >> 1;
+            j[6] = (int)(z / 1980u); j[7] = (int)((z / 44u) % 45u); j[8] = (int)(z % 44u);
+            sb = (int)(x3 & 1u);
+        } else {                                               // replay: the reference's 51 shuffle draws + randint
 #pragma unroll
-        for (int i = 0; i < 52; i++) deck[i] = (uint8_t)i;     // utils.py:34-43 order == card2index.json
-        shuffle_tail_u8(ch, deck, 52, 9);
-#pragma unroll
-        for (int k = 0; k < 9; k++) card[k] = deck[51 - k];
-        const int sb = (int)ch.below(2u);
+            for (int s = 0; s < 9; s++) j[s] = (int)ch.below((uint32_t)(52 - s));
+            ch.skip_fy(42, 1);
+            sb = (int)ch.below(2u);
+        }
+        fy_tail_cards<9>(52, j, card);                         // utils.py:34-43 deck order == card2index.json ids
         chips0 = sb == 0 ? 1 : 2; chips1 = sb == 0 ? 2 : 1;
         fold0 = fold1 = 0; rc = 0;
         r.start(sb, chips0, chips1);                          // (bb+1)%2 == sb for two players (game.py:81)

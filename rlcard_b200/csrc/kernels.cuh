@@ -23,30 +23,41 @@ enum { kModeReset = 0, kModeStep = 1, kModeObserve = 2 };
 // ---- chance source plumbing -------------------------------------------------------------
 template <class Ch> struct ChanceIO;
 template <> struct ChanceIO<ChancePhilox> {
-    static __device__ __forceinline__ void open(ChancePhilox &c, const KParams &p, size_t i, const EnvHeader &h) {
-        c.s.init(p.seed, p.env_id_base + (uint32_t)i, h.episode - 1u, 0u); c.draw = h.draw; c.err = 0;
+    static __device__ __forceinline__ void open(ChancePhilox &c, const KParams &p, size_t i) {
+        c.init(p.seed, p.env_id_base + (uint32_t)i);
     }
-    static __device__ __forceinline__ void close(ChancePhilox &c, const KParams &, size_t, EnvHeader &h) { h.draw = c.draw; }
+    static __device__ __forceinline__ void close(ChancePhilox &, const KParams &, size_t) {}
+    // block 0 of step (episode, t): word 0 drives the random policy, the rest feeds the chance draws
+    static __device__ __forceinline__ uint32_t begin_step(ChancePhilox &c, const KParams &, uint32_t episode, uint32_t t) {
+        c.begin(episode, t);
+        return c.policy_word();
+    }
 };
+template <class Ch>
+__device__ __forceinline__ uint32_t policy_word_only(const KParams &p, size_t i, uint32_t episode, uint32_t t) {
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(t, episode, p.env_id_base + (uint32_t)i, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), o0, o1, o2, o3);
+    return o0;
+}
 template <> struct ChanceIO<ChanceTape> {
-    static __device__ __forceinline__ void open(ChanceTape &c, const KParams &p, size_t i, const EnvHeader &) {
+    static __device__ __forceinline__ void open(ChanceTape &c, const KParams &p, size_t i) {
         c.tape = p.tape + i * (size_t)p.tape_stride; c.len = p.tape_stride; c.pos = p.tape_pos[i]; c.err = 0;
     }
-    static __device__ __forceinline__ void close(ChanceTape &c, const KParams &p, size_t i, EnvHeader &) { p.tape_pos[i] = c.pos; }
+    static __device__ __forceinline__ void close(ChanceTape &c, const KParams &p, size_t i) { p.tape_pos[i] = c.pos; }
 };
 template <> struct ChanceIO<ChanceMt> {
-    static __device__ __forceinline__ void open(ChanceMt &c, const KParams &p, size_t i, const EnvHeader &) {
+    static __device__ __forceinline__ void open(ChanceMt &c, const KParams &p, size_t i) {
         c.mt = p.mt + i; c.n = p.n; c.mti = (int)p.mt[(size_t)624 * p.n + i]; c.err = 0;
     }
-    static __device__ __forceinline__ void close(ChanceMt &c, const KParams &p, size_t i, EnvHeader &) {
+    static __device__ __forceinline__ void close(ChanceMt &c, const KParams &p, size_t i) {
         p.mt[(size_t)624 * p.n + i] = (uint32_t)c.mti;
     }
 };
 
+// deal the next episode; the chance draws continue the sequence of the current step
 template <class G, class Ch>
 __device__ __forceinline__ void new_episode(G &g, Ch &ch, EnvHeader &h) {
     h.episode++; h.t = 0;
-    ch.new_episode(h.episode - 1u);
     g.reset(ch);
 }
 
@@ -55,12 +66,28 @@ template <class G>
 __device__ __forceinline__ void write_mask_row(uint8_t *gmask, size_t env, const uint32_t (&m)[G::MASK_WORDS]) {
     if constexpr (G::A == 4) {
         const uint32_t w = (m[0] & 1u) | ((m[0] & 2u) << 7) | ((m[0] & 4u) << 14) | ((m[0] & 8u) << 21);
-        reinterpret_cast<uint32_t *>(gmask)[env] = w;
+        __stcs(reinterpret_cast<uint32_t *>(gmask) + env, w);
     } else if constexpr (G::A == 2) {
         reinterpret_cast<uint16_t *>(gmask)[env] = (uint16_t)((m[0] & 1u) | ((m[0] & 2u) << 7));
     } else {
         uint8_t *rowp = gmask + env * (size_t)G::A;
         for (int a = 0; a < G::A; a++) rowp[a] = (m[a >> 5] >> (a & 31)) & 1u;
+    }
+}
+
+// uniform-random legal action: k-th legal id in ascending order, k = mulhi(policy word, #legal)
+template <class G>
+__device__ __forceinline__ int pick_action(const uint32_t (&m)[G::MASK_WORDS], uint32_t word) {
+    const int cnt = popc_words<G::MASK_WORDS>(m);
+    const int k = (int)__umulhi(word, (uint32_t)cnt);
+    if constexpr (G::A <= 4) {
+        uint32_t mm = m[0];
+        if (k > 0) mm &= mm - 1;
+        if (k > 1) mm &= mm - 1;
+        if (k > 2) mm &= mm - 1;
+        return __ffs(mm) - 1;
+    } else {
+        return kth_set_bit<G::MASK_WORDS>(m, k);
     }
 }
 
@@ -83,16 +110,20 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
     if (valid) {
         h.load(p.state, p.n, i);
         g.load(p.state + kHeaderWords * p.n, p.n, i);
-        ChanceIO<Ch>::open(ch, p, i, h);
+        ChanceIO<Ch>::open(ch, p, i);
         bool done = false;
         float pay[G::P];
 #pragma unroll
         for (int k = 0; k < G::P; k++) pay[k] = 0.f;
         if constexpr (MODE == kModeReset) {
-            if (!p.reset_mask || p.reset_mask[i]) new_episode(g, ch, h);
+            if (!p.reset_mask || p.reset_mask[i]) {
+                ch.begin(h.episode, kResetStep);      // a reset outside a step: t = -1 of the episode it starts
+                new_episode(g, ch, h);
+            }
         } else if constexpr (MODE == kModeStep) {
             const int a = p.actions[i];
             if (a >= 0 && h.episode != 0 && !g.over()) {
+                ch.begin(h.episode - 1u, h.t);
                 g.step(a, ch, err);
                 h.t++;
                 if (g.over()) {
@@ -123,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
             for (int k = 0; k < G::P; k++) p.payoffs[i * G::P + k] = pay[k];
         }
         if constexpr (MODE != kModeObserve) {
-            ChanceIO<Ch>::close(ch, p, i, h);
+            ChanceIO<Ch>::close(ch, p, i);
             h.store(p.state, p.n, i);
             g.store(p.state + kHeaderWords * p.n, p.n, i);
         }
@@ -154,32 +185,32 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     __syncwarp();
 
     G g; EnvHeader h; Ch ch; int err = 0;
-    PhiloxStream pol;
     if (valid) {
         h.load(p.state, p.n, i);
         g.load(p.state + kHeaderWords * p.n, p.n, i);
-        ChanceIO<Ch>::open(ch, p, i, h);
-        if (h.episode == 0) new_episode(g, ch, h);
-        pol.init(p.seed, p.env_id_base + (uint32_t)i, h.episode - 1u, 1u);
+        ChanceIO<Ch>::open(ch, p, i);
+        if (h.episode == 0) { ch.begin(0u, kResetStep); new_episode(g, ch, h); }
     }
-    for (int t = 0; t < p.T; t++) {
-        const size_t rowi = (size_t)t * p.n + i;
+    // per-thread output cursors, advanced by one trajectory row (n envs) per step
+    uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
+    const size_t obs_step = p.n * (size_t)kRowBytes;
+    size_t rowi = i;
+    for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         uint32_t m[G::MASK_WORDS];
         if (valid) {
             if (p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
             g.legal(m);
         }
         __syncwarp();
-        if (p.t_obs)
-            warp_tile_flush(reinterpret_cast<uint8_t *>(p.t_obs) + ((size_t)t * p.n + warp_env0) * (size_t)kRowBytes,
-                            reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        if (p.t_obs) warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         __syncwarp();
         if (valid) {
             if (p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
             if (p.t_player) __stcs(p.t_player + rowi, g.player());
-            const int cnt = popc_words<G::MASK_WORDS>(m);
-            const int k = (int)__umulhi(pol.word(h.t), (uint32_t)cnt);
-            const int a = kth_set_bit<G::MASK_WORDS>(m, k);
+            uint32_t word;
+            if constexpr (Ch::kKind == 0) word = ChanceIO<Ch>::begin_step(ch, p, h.episode - 1u, h.t);
+            else word = policy_word_only<Ch>(p, i, h.episode - 1u, h.t);
+            const int a = pick_action<G>(m, word);
             if (p.t_action) __stcs(p.t_action + rowi, a);
             g.step(a, ch, err);
             h.t++;
@@ -190,7 +221,6 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             if (over) {
                 g.payoffs(pay);
                 new_episode(g, ch, h);
-                pol.new_episode(h.episode - 1u);
             }
             if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
             if (p.t_payoffs) {
@@ -204,7 +234,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         }
     }
     if (valid) {
-        ChanceIO<Ch>::close(ch, p, i, h);
+        ChanceIO<Ch>::close(ch, p, i);
         h.store(p.state, p.n, i);
         g.store(p.state + kHeaderWords * p.n, p.n, i);
         err |= ch.err;

@@ -1,0 +1,154 @@
+"""DouDizhu action table (host side).
+
+The 27 472 action ids are an interface constant of the reference (games/doudizhu/jsondata.zip ->
+action_space.txt, loaded by games/doudizhu/utils.py:21-27); their order is an artefact of how that
+file was produced and cannot be derived from the rules, so it is committed as packed rank counts in
+``tables/doudizhu_actions.npz`` (made by tools/make_doudizhu_table.py).  Everything else is computed
+here from the rules: the (type, weight) of every action (card_type.json / type_card.json in the
+reference, utils.py:29-38) and the 54-d action features (envs/doudizhu.py:153-167).
+"""
+import os
+
+import numpy as np
+
+RANKS = '3456789TJQKA2BR'                       # games/doudizhu/utils.py:41-43
+NUM_ACTIONS = 27472
+PASS_ID = 27471
+
+# type ids: contiguous id ranges in action_space.txt follow this order
+TYPE_NAMES = (['solo', 'pair', 'trio', 'trio_solo', 'trio_pair'] +
+              ['solo_chain_%d' % k for k in range(5, 13)] + ['pair_chain_%d' % k for k in range(3, 11)] +
+              ['trio_chain_%d' % k for k in range(2, 7)] + ['trio_solo_chain_%d' % k for k in range(2, 6)] +
+              ['trio_pair_chain_%d' % k for k in range(2, 5)] + ['four_two_solo', 'four_two_pair', 'bomb', 'rocket', 'pass'])
+TYPE_ID = {n: i for i, n in enumerate(TYPE_NAMES)}
+T_BOMB, T_ROCKET, T_PASS = TYPE_ID['bomb'], TYPE_ID['rocket'], TYPE_ID['pass']
+
+_TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tables', 'doudizhu_actions.npz')
+
+
+def str_to_counts(s):
+    c = [0] * 15
+    if s != 'pass':
+        for ch in s:
+            c[RANKS.index(ch)] += 1
+    return c
+
+
+def counts_to_str(c):
+    return ''.join(RANKS[i] * c[i] for i in range(15)) or 'pass'
+
+
+def pack_counts(c):
+    return sum(int(v) << (4 * i) for i, v in enumerate(c))
+
+
+def unpack_counts(x):
+    return [(int(x) >> (4 * i)) & 15 for i in range(15)]
+
+
+def _solo_kickers_ok(kick, start, length):
+    """games/doudizhu/judger.py:48-89: no bomb among the kickers, no third copy of a rank adjacent to the
+    chain (except '2'), not both jokers; kickers never use a chain rank."""
+    if kick[13] and kick[14]:
+        return False
+    for r in range(15):
+        if kick[r] == 0:
+            continue
+        if start <= r < start + length or kick[r] > 3:
+            return False
+        if kick[r] == 3 and (r == start - 1 or r == start + length) and r != 12:
+            return False
+    return True
+
+
+def classify(c):
+    """rank counts -> (type name, weight).  weight orders actions of one type like the reference's
+    card_type.json (only the order is observable, utils.py:250-260)."""
+    n = sum(c)
+    if n == 0:
+        return 'pass', 0
+    nz = [r for r in range(15) if c[r]]
+    lo, hi = nz[0], nz[-1]
+    consecutive = (hi - lo + 1 == len(nz)) and hi <= 11
+    same = len(set(c[r] for r in nz)) == 1
+    if n == 2 and c[13] == 1 and c[14] == 1:
+        return 'rocket', 0
+    if len(nz) == 1:
+        return {1: 'solo', 2: 'pair', 3: 'trio', 4: 'bomb'}[n], lo
+    if same and consecutive:
+        k, per = len(nz), c[lo]
+        if per == 1 and k >= 5:
+            return 'solo_chain_%d' % k, lo
+        if per == 2 and k >= 3:
+            return 'pair_chain_%d' % k, lo
+        if per == 3 and k >= 2:
+            return 'trio_chain_%d' % k, lo
+    found = []
+    quads = [r for r in nz if c[r] == 4]
+    if n == 6:
+        for q in quads:
+            kick = list(c); kick[q] -= 4
+            if _solo_kickers_ok(kick, q, 1):
+                found.append(('four_two_solo', q))
+    if n == 8:
+        for q in quads:
+            kick = list(c); kick[q] -= 4
+            if all(v in (0, 2) for v in kick) and sum(1 for v in kick if v == 2) == 2:
+                found.append(('four_two_pair', q))
+    for k in range(1, 6):
+        for kind, per_kick in (('solo', 1), ('pair', 2)):
+            if n != (3 + per_kick) * k:
+                continue
+            for start in range(0, 13 - k + 1 if k == 1 else 12 - k + 1):
+                if any(c[r] < 3 for r in range(start, start + k)):
+                    continue
+                kick = list(c)
+                for r in range(start, start + k):
+                    kick[r] -= 3
+                if kind == 'solo':
+                    ok = _solo_kickers_ok(kick, start, k)
+                else:
+                    ok = all(v in (0, 2) for v in kick) and sum(1 for v in kick if v == 2) == k and not kick[13] and not kick[14]
+                if ok:
+                    name = ('trio_%s' % kind) if k == 1 else 'trio_%s_chain_%d' % (kind, k)
+                    found.append((name, start))
+    if len(found) != 1:
+        raise ValueError('cannot classify %s: %r' % (counts_to_str(c), found))
+    return found[0]
+
+
+_cache = {}
+
+
+def load():
+    """-> dict(counts u64 [27472] nibble-packed rank counts, type u8, weight u8, length u8, features int8 [27472, 54])"""
+    if 'tab' in _cache:
+        return _cache['tab']
+    if not os.path.exists(_TABLE):
+        raise FileNotFoundError('%s missing (run tools/make_doudizhu_table.py where the reference is available)' % _TABLE)
+    packed = np.load(_TABLE)['counts'].astype(np.uint64)
+    assert packed.shape == (NUM_ACTIONS,)
+    types = np.zeros(NUM_ACTIONS, np.uint8); weights = np.zeros(NUM_ACTIONS, np.uint8); length = np.zeros(NUM_ACTIONS, np.uint8)
+    feats = np.zeros((NUM_ACTIONS, 54), np.int8)
+    for i, x in enumerate(packed):
+        c = unpack_counts(x)
+        t, w = classify(c)
+        types[i], weights[i], length[i] = TYPE_ID[t], w, sum(c)
+        feats[i] = cards_to_array(c)
+    assert types[PASS_ID] == T_PASS
+    _cache['tab'] = dict(counts=packed, type=types, weight=weights, length=length, features=feats)
+    return _cache['tab']
+
+
+def cards_to_array(c):
+    """envs/doudizhu.py:153-167 _cards2array on rank counts: 4x13 thermometer, column-major, + 2 joker bits."""
+    out = np.zeros(54, np.int8)
+    for r in range(13):
+        out[4 * r:4 * r + c[r]] = 1
+    out[52] = 1 if c[13] else 0
+    out[53] = 1 if c[14] else 0
+    return out
+
+
+def action_strings():
+    return [counts_to_str(unpack_counts(x)) for x in load()['counts']]
