@@ -57,8 +57,23 @@ def lib():
         L.orc_holdem_strength7.restype = C.c_uint32; L.orc_holdem_strength7.argtypes = [vp]
         L.orc_philox_word.restype = C.c_uint32; L.orc_philox_word.argtypes = [C.c_uint32] * 7
         L.orc_philox4x32_10.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+        L.orc_doudizhu_set_table.argtypes = [vp, vp, vp, i32, i32, i32]
         _LIB = L
     return _LIB
+
+
+_DDZ = []
+
+
+def _need_tables(gid):
+    """DouDizhu: install the action table (id -> rank counts, type, weight) in the C oracle.  The table data
+    (the reference's action-id contract) is shared with the product; the legal-set logic is not."""
+    if gid == GAME_IDS['doudizhu'] and not _DDZ:
+        from rlcard_b200 import doudizhu_table as T
+        tab = T.load()
+        c = np.ascontiguousarray(tab['counts'], np.uint64); t = np.ascontiguousarray(tab['type']); w = np.ascontiguousarray(tab['weight'])
+        lib().orc_doudizhu_set_table(c.ctypes.data, t.ctypes.data, w.ctypes.data, len(c), T.T_BOMB, T.T_ROCKET)
+        _DDZ.append((c, t, w))
 
 
 def seed_words(seed):
@@ -91,6 +106,7 @@ class OracleEnv:
         self.game = game
         self.gid = GAME_IDS[game]
         self.L = lib()
+        _need_tables(self.gid)
         self.h = self.L.orc_env_create(self.gid)
         assert self.h
         self.num_players, self.num_actions, self.obs_dim = info(self.gid)
@@ -162,6 +178,7 @@ class OracleVec:
     def __init__(self, game, n, seed, env0=0):
         self.gid = GAME_IDS[game]
         self.L = lib()
+        _need_tables(self.gid)
         self.n = n
         self.num_players, self.num_actions, od = info(self.gid)
         self.obs_stride = max(od)

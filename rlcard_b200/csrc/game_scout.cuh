@@ -1,0 +1,234 @@
+// game_scout.cuh -- Scout, 4 players, 45 cards, 204 actions, one env per warp.
+// Reference: rlcard/games/scout/{game,round,dealer,player,card,judger}.py, games/scout/utils/utils.py,
+// rlcard/envs/scout.py.
+//
+// Hands and the table set are ordered lists of (top, bottom) cards with values 1..10, kept as two
+// 16-nibble words each (slot k = bits [4k, 4k+4)), so that slicing, inserting and the group/run tests
+// are a handful of 64-bit operations.  The whole state is replicated in every lane's registers; the 32
+// lanes split the 204 candidate action ids (lane = id mod 32) and each __ballot_sync yields one word of
+// the legal mask (round.py:225-260).
+//
+// Game words (23): [0..7] hand tops p0..p3 (lo,hi)  [8..15] hand bottoms  [16,17] table tops
+//   [18,19] table bottoms  [20] hl0..3 (5 bits each) | tl [20:25) | owner [25:28) (4 = none) |
+//   consecutive_scouts [28:30) | current player [30:32)   [21] score0 | score1 << 16
+//   [22] score2 | score3 << 16 (15 bits) | game_over << 31
+#pragma once
+#include "common.cuh"
+#include "kernels_warp.cuh"
+
+namespace rlc {
+
+__device__ __forceinline__ uint64_t nib_mask(int len) { return len >= 16 ? ~0ull : ((1ull << (4 * len)) - 1ull); }
+__device__ __forceinline__ uint64_t shr64(uint64_t x, int bits) { return bits >= 64 ? 0ull : (x >> bits); }
+__device__ __forceinline__ uint64_t shl64(uint64_t x, int bits) { return bits >= 64 ? 0ull : (x << bits); }
+__device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * k)) & 15ull); }
+
+struct Scout {
+    static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
+    static constexpr bool kMaskBitpacked = false;
+    static constexpr int kScratchBytes = 48;
+    uint64_t ht[4], hb[4], tt, tb;
+    int hl[4], score[4], tl, owner, consec, cur, over_;
+    bool forced;           // current_player_forced_scout: recomputed by every legal() (round.py:246)
+    uint64_t segtab;       // per lane: (start | (end-1) << 4) of play ids lane, lane+32, ... (utils.py:186-200)
+
+    __device__ __forceinline__ uint64_t sel(const uint64_t (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
+    __device__ __forceinline__ int seli(const int (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
+    __device__ __forceinline__ void put(uint64_t (&a)[4], int p, uint64_t v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
+    __device__ __forceinline__ void puti(int (&a)[4], int p, int v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
+
+    __device__ void load(const uint32_t *w, int lane) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            ht[p] = (uint64_t)w[2 * p] | ((uint64_t)w[2 * p + 1] << 32);
+            hb[p] = (uint64_t)w[8 + 2 * p] | ((uint64_t)w[9 + 2 * p] << 32);
+        }
+        tt = (uint64_t)w[16] | ((uint64_t)w[17] << 32); tb = (uint64_t)w[18] | ((uint64_t)w[19] << 32);
+        const uint32_t m = w[20], s0 = w[21], s1 = w[22];
+#pragma unroll
+        for (int p = 0; p < 4; p++) hl[p] = (m >> (5 * p)) & 31;
+        tl = (m >> 20) & 31; owner = (m >> 25) & 7; consec = (m >> 28) & 3; cur = (m >> 30) & 3;
+        score[0] = s0 & 0xffff; score[1] = s0 >> 16; score[2] = s1 & 0xffff; score[3] = (s1 >> 16) & 0x7fff; over_ = s1 >> 31;
+        forced = false;
+        // play ids of this lane: id = lane + 32 r, r = 0..4 -> (start, end) of the s-major enumeration
+        segtab = 0;
+        int s = 0, base = 0;
+        for (int r = 0; r < 5; r++) {
+            const int id = lane + 32 * r;
+            while (s < 16 && id >= base + (16 - s)) { base += 16 - s; s++; }
+            const int e = s + (id - base) + 1;
+            if (id < 136) segtab |= (uint64_t)(s | ((e - 1) << 4)) << (8 * r);
+        }
+    }
+    __device__ void store(uint32_t *w, int lane) const {
+        if (lane != 0) return;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            w[2 * p] = (uint32_t)ht[p]; w[2 * p + 1] = (uint32_t)(ht[p] >> 32);
+            w[8 + 2 * p] = (uint32_t)hb[p]; w[9 + 2 * p] = (uint32_t)(hb[p] >> 32);
+        }
+        w[16] = (uint32_t)tt; w[17] = (uint32_t)(tt >> 32); w[18] = (uint32_t)tb; w[19] = (uint32_t)(tb >> 32);
+        w[20] = hl[0] | (hl[1] << 5) | (hl[2] << 10) | (hl[3] << 15) | (tl << 20) | (owner << 25) | (consec << 28) | ((uint32_t)cur << 30);
+        w[21] = (uint32_t)score[0] | ((uint32_t)score[1] << 16);
+        w[22] = (uint32_t)score[2] | ((uint32_t)(score[3] & 0x7fff) << 16) | ((uint32_t)over_ << 31);
+    }
+
+    // utils/utils.py:17-67 + 144-184 on a nibble slice: valid?, (type 2 group / 1 run / 0 single, rank)
+    static __device__ __forceinline__ bool segment(uint64_t tops, int s, int len, int &type, int &rank) {
+        const uint64_t mk = nib_mask(len), seg = shr64(tops, 4 * s) & mk;
+        const int first = (int)(seg & 15ull), last = (int)(shr64(seg, 4 * (len - 1)) & 15ull);
+        const uint64_t rep = (uint64_t)first * (0x1111111111111111ull & mk), ramp = 0xFEDCBA9876543210ull & mk;
+        const bool group = seg == rep, asc = seg == rep + ramp, desc = seg == rep - ramp;
+        type = len == 1 ? 0 : (group ? 2 : 1);
+        rank = (len > 1 && !group) ? max(first, last) : first;
+        return len == 1 || group || asc || desc;
+    }
+    // round.py:225-260: 204-bit legal set of the current player, identical in all lanes
+    __device__ void legal_words(uint32_t (&m)[7], int lane) {
+        const uint64_t T = sel(ht, cur);
+        const int n = seli(hl, cur);
+        int ttype = 0, trank = 0;
+        if (tl > 0) segment(tt, 0, tl, ttype, trank);
+        const bool can_scout = tl > 0 && n < 16;
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int id = lane + 32 * r;
+            bool ok = false;
+            if (r < 5 && id < 136) {
+                const int code = (int)((segtab >> (8 * r)) & 255ull), s = code & 15, e = (code >> 4) + 1, len = e - s;
+                int type, rank;
+                const bool valid = segment(T, s, len, type, rank);
+                const bool stronger = tl == 0 || len > tl || (len == tl && (type > ttype || (type == ttype && rank > trank)));   // round.py:262-295
+                ok = e <= n && valid && stronger;
+            }
+            if (id >= 136 && id < 204) {
+                const int k = id - 136, ins = k >> 2;
+                ok = can_scout && ins <= n && ((k & 3) < 2 || tl > 1);
+            }
+            m[r] = __ballot_sync(kFull, ok);
+        }
+        forced = (m[0] | m[1] | m[2] | m[3] | (m[4] & 0xffu)) == 0;
+    }
+    __device__ __forceinline__ void legal(uint32_t *smask, int lane) {
+        uint32_t m[7];
+        legal_words(m, lane);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 7; r++) smask[r] = m[r];
+        }
+    }
+    // games/scout/game.py:37-65, dealer.py:12-22, round.py:22-50: two shuffles (Q-SC1), round-robin deal
+    template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
+        if (lane == 0) {
+            int n = 0;
+            for (int top = 1; top <= 10; top++) for (int bot = top + 1; bot <= 10; bot++) deck[n++] = (uint8_t)((top << 4) | bot);
+        }
+        __syncwarp();
+        for (int pass = 0; pass < 2; pass++)
+            for (int i = 44; i >= 1; i--) {
+                const uint32_t j = ch.below((uint32_t)i + 1u);
+                if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
+            }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; p++) { ht[p] = hb[p] = 0; hl[p] = 0; score[p] = 0; }
+        for (int k = 0; k < 45; k++) {                   // deck.pop() = position 44-k -> player k%4, slot k/4
+            const int c = deck[44 - k], p = k & 3, slot = k >> 2;
+            put(ht, p, sel(ht, p) | ((uint64_t)(c >> 4) << (4 * slot)));
+            put(hb, p, sel(hb, p) | ((uint64_t)(c & 15) << (4 * slot)));
+            puti(hl, p, slot + 1);
+        }
+        __syncwarp();
+        tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
+        cur = (int)ch.below(4u);
+        forced = false;
+    }
+    __device__ __forceinline__ int player() const { return cur; }
+    __device__ __forceinline__ bool over() const { return over_ != 0; }
+    // env.py:65-86, envs/scout.py:53-80,130-133; round.py:63-153.  `forced` must be current (legal() ran).
+    template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *, int lane, int &err) {
+        if (id < 0 || id >= A || !((smask[id >> 5] >> (id & 31)) & 1u)) {   // the reference raises; replay feeds legal ids
+            err |= 4;
+            id = warp_kth_set_bit(smask, MASK_WORDS, 0, lane);
+            if (id < 0) return;
+        }
+        const int p = cur;
+        const bool was_forced = forced;
+        uint64_t T = sel(ht, p), B = sel(hb, p);
+        int n = seli(hl, p);
+        if (id < 136) {
+            int s = 0, k = id;
+            while (k >= 16 - s) { k -= 16 - s; s++; }
+            const int e = s + k + 1, len = e - s;
+            const uint64_t mk = nib_mask(len), lo = nib_mask(s);
+            const uint64_t st = shr64(T, 4 * s) & mk, sb = shr64(B, 4 * s) & mk;
+            T = (T & lo) | shl64(shr64(T, 4 * e), 4 * s);
+            B = (B & lo) | shl64(shr64(B, 4 * e), 4 * s);
+            n -= len;
+            if (tl > 0) puti(score, p, seli(score, p) + tl);
+            tt = st; tb = sb; tl = len; owner = p; consec = 0;
+        } else {
+            const int k = id - 136, front = (k & 3) < 2, flip = k & 1;
+            int ins = k >> 2;
+            int ctop, cbot;
+            if (front) { ctop = nib(tt, 0); cbot = nib(tb, 0); tt >>= 4; tb >>= 4; }
+            else { ctop = nib(tt, tl - 1); cbot = nib(tb, tl - 1); tt &= nib_mask(tl - 1); tb &= nib_mask(tl - 1); }
+            tl--;
+            if (flip) { const int x = ctop; ctop = cbot; cbot = x; }
+            if (ins > n) ins = n;                                           // list.insert clamps
+            const uint64_t lo = nib_mask(ins);
+            T = (T & lo) | ((uint64_t)ctop << (4 * ins)) | shl64(T & ~lo, 4);
+            B = (B & lo) | ((uint64_t)cbot << (4 * ins)) | shl64(B & ~lo, 4);
+            n++;
+            if (was_forced && owner < 4) puti(score, owner, seli(score, owner) + 1);   // Q-SC2
+            consec++;
+            if (tl == 0) { owner = 4; consec = 0; }
+            if (consec == 3 && owner < 4) over_ = 1;
+        }
+        put(ht, p, T); put(hb, p, B); puti(hl, p, n);
+        cur = (p + 1) & 3;
+        uint32_t m[7];
+        legal_words(m, lane);                                               // next player cannot move -> round ends
+        if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6]) == 0) over_ = 1;
+    }
+    __device__ __forceinline__ void payoffs(float *out) const {             // judger.py:15-30
+#pragma unroll
+        for (int p = 0; p < 4; p++) out[p] = (float)(score[p] - hl[p]);
+    }
+    // envs/scout.py:171-235 (row pre-zeroed).  Scalars are float32(python float64 expression).
+    template <class T> __device__ void encode_obs(int seat, bool, T *row, int lane) const {
+        if (lane < 16) {
+            const int s = lane;
+            if (s < seli(hl, seat)) {
+                row[s * 10 + nib(sel(ht, seat), s) - 1] = (T)1;
+                row[160 + s * 10 + nib(sel(hb, seat), s) - 1] = (T)1;
+                row[640 + s] = (T)1;
+            }
+        } else {
+            const int j = lane - 16;
+            if (j < tl) {
+                row[320 + j * 10 + nib(tt, j) - 1] = (T)1;
+                row[480 + j * 10 + nib(tb, j) - 1] = (T)1;
+                row[656 + j] = (T)1;
+            }
+        }
+        if (lane < 16) {
+            float v = 0.f;
+            if (lane < 5) v = owner == lane ? 1.f : 0.f;
+            else if (lane == 5) v = consec == 0 ? 0.f : (consec == 1 ? (float)(1.0 / 3.0) : (consec == 2 ? (float)(2.0 / 3.0) : 1.f));
+            else if (lane < 10) v = (float)seli(hl, lane - 6) * 0.0625f;
+            else if (lane == 10) v = (float)seli(score, seat) * 0.0625f;
+            else if (lane == 11) v = (float)tl * 0.0625f;
+            else if (lane == 13) v = forced ? 1.f : 0.f;
+            else if (lane >= 14) {
+                const int r = tl == 0 ? 0 : (lane == 14 ? nib(tt, 0) : nib(tt, tl - 1));
+                const float tenth[11] = { 0.f, (float)(1 / 10.0), (float)(2 / 10.0), (float)(3 / 10.0), (float)(4 / 10.0), (float)(5 / 10.0),
+                                          (float)(6 / 10.0), (float)(7 / 10.0), (float)(8 / 10.0), (float)(9 / 10.0), 1.f };
+                v = tenth[r];
+            }
+            row[672 + lane] = (T)v;
+        }
+    }
+};
+
+}  // namespace rlc

@@ -1,0 +1,283 @@
+// kernels_warp.cuh -- one-env-per-WARP kernels for the games with combinatorial move generation
+// (Scout, DouDizhu).  8192 envs per GPU would be 256 warps with a thread per env (1.7 warps per SM);
+// a warp per env gives 8192 warps, lets the 32 lanes test 32 candidate actions at a time (one
+// __ballot_sync == one 32-bit word of the legal mask) and write the obs row with coalesced stores.
+//
+// The env state is replicated in the registers of all 32 lanes: every lane executes the (scalar)
+// transition identically, so no shared-memory state, no intra-warp hand-off.  Random draws are made by
+// lane 0 and broadcast.  State rows are array-of-structs uint32 [n][state_words] (one env = one
+// contiguous row, read with warp-uniform loads).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace rlc {
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+// lane 0 owns the chance source; results are broadcast so that all lanes stay in lock step
+template <class Ch>
+struct WarpChance {
+    static constexpr int kKind = Ch::kKind;
+    Ch ch; int lane;
+    __device__ __forceinline__ uint32_t below(uint32_t n) {
+        uint32_t v = 0;
+        if (lane == 0) v = ch.below(n);
+        return __shfl_sync(kFull, v, 0);
+    }
+    __device__ __forceinline__ void skip_fy(int a, int b) { if (lane == 0) ch.skip_fy(a, b); }
+    __device__ __forceinline__ void begin(uint32_t e, uint32_t t) { if (lane == 0) ch.begin(e, t); }
+    __device__ __forceinline__ int err() { return __shfl_sync(kFull, ch.err, 0); }
+};
+template <class Ch>
+__device__ __forceinline__ void wchance_open(WarpChance<Ch> &w, const KParams &p, size_t env, int lane) {
+    w.lane = lane;
+    ChanceIO<Ch>::open(w.ch, p, env);     // every lane builds the (cheap) handle; only lane 0 draws/commits
+}
+template <class Ch>
+__device__ __forceinline__ void wchance_close(WarpChance<Ch> &w, const KParams &p, size_t env) {
+    if (w.lane == 0) ChanceIO<Ch>::close(w.ch, p, env);
+}
+template <class Ch>
+__device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch> &w, const KParams &p, size_t env, uint32_t episode, uint32_t t) {
+    uint32_t word = 0;
+    if (w.lane == 0) {
+        if constexpr (Ch::kKind == 0) { w.ch.begin(episode, t); word = w.ch.policy_word(); }
+        else word = policy_word_only<Ch>(p, env, episode, t);
+    }
+    return __shfl_sync(kFull, word, 0);
+}
+
+// k-th (0-based) set bit over W mask words in shared memory (all lanes get the result)
+__device__ __forceinline__ int warp_kth_set_bit(const uint32_t *sm, int W, int k, int lane) {
+    for (int base = 0; base < W; base += 32) {
+        const int wi = base + lane;
+        const uint32_t word = wi < W ? sm[wi] : 0u;
+        int c = __popc(word), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(kFull, incl, 31);
+        if (k < total) {
+            const uint32_t hit = __ballot_sync(kFull, k < incl);           // first lane whose prefix exceeds k
+            const int src = __ffs(hit) - 1;
+            const int before = __shfl_sync(kFull, incl - c, src);
+            const uint32_t w = __shfl_sync(kFull, word, src);
+            return 32 * (base + src) + (int)__fns(w, 0, k - before + 1);
+        }
+        k -= total;
+    }
+    return -1;
+}
+__device__ __forceinline__ int warp_popc_words(const uint32_t *sm, int W, int lane) {
+    int c = 0;
+    for (int wi = lane; wi < W; wi += 32) c += __popc(sm[wi]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    return c;
+}
+
+// mask row of one env: dense uint8 [A] (4 ids per 32-bit store) or bit-packed uint32 [W]
+template <class G>
+__device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const uint32_t *sm, int lane) {
+    if constexpr (G::kMaskBitpacked) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(gmask) + row * (size_t)G::MASK_WORDS;
+        for (int wi = lane; wi < G::MASK_WORDS; wi += 32) __stcs(dst + wi, sm[wi]);
+    } else {
+        static_assert(G::A % 4 == 0, "dense mask rows are written as 32-bit words");
+        uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gmask) + row * (size_t)G::A);
+        for (int q = lane; q < G::A / 4; q += 32) {
+            const uint32_t b = (sm[q >> 3] >> ((q & 7) * 4)) & 15u;
+            __stcs(dst + q, (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
+        }
+    }
+}
+
+template <class G, class ObsT>
+__device__ __forceinline__ void warp_flush_row(void *gobs, size_t row, ObsT *srow, int lane) {
+    constexpr int kBytes = G::OBS * (int)sizeof(ObsT);
+    warp_tile_flush(reinterpret_cast<uint8_t *>(gobs) + row * (size_t)kBytes, reinterpret_cast<uint8_t *>(srow), kBytes, lane);
+}
+
+template <class G, class Ch, class ObsT, int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t env = (size_t)blockIdx.x * (BLOCK / 32) + wib;
+    if (env >= p.n) return;
+    constexpr int kRowBytes = (G::OBS * (int)sizeof(ObsT) + 15) & ~15;
+    constexpr int kWarpBytes = kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15) + G::kScratchBytes;
+    uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)wib * kWarpBytes;
+    ObsT *srow = reinterpret_cast<ObsT *>(base);
+    uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
+    uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
+    warp_tile_zero(base, kRowBytes, lane);
+    __syncwarp();
+
+    uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
+    EnvHeader h; h.episode = row[0]; h.t = row[1];
+    G g; g.load(row + kHeaderWords, lane);
+    WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
+    int err = 0; bool done = false;
+    float pay[G::P];
+#pragma unroll
+    for (int k = 0; k < G::P; k++) pay[k] = 0.f;
+
+    if constexpr (MODE == kModeReset) {
+        if (!p.reset_mask || p.reset_mask[env]) {
+            ch.begin(h.episode, kResetStep);
+            h.episode++; h.t = 0;
+            g.reset(ch, scratch, lane);
+        }
+    } else if constexpr (MODE == kModeStep) {
+        const int a = p.actions[env];
+        if (a >= 0 && h.episode != 0 && !g.over()) {
+            ch.begin(h.episode - 1u, h.t);
+            g.legal(smask, lane);                        // the step validates against the current legal set
+            __syncwarp();
+            g.step(a, ch, smask, scratch, lane, err);
+            h.t++;
+            if (g.over()) {
+                done = true;
+                g.payoffs(pay);
+                if ((p.flags & RLC_TERMINAL_OBS) && p.terminal_obs) {
+                    g.legal(smask, lane);
+                    __syncwarp();
+                    for (int s = 0; s < G::P; s++) {
+                        g.encode_obs(s, false, srow, lane);
+                        __syncwarp();
+                        warp_flush_row<G, ObsT>(p.terminal_obs, env * G::P + s, srow, lane);
+                        __syncwarp();
+                    }
+                }
+                if (p.flags & RLC_AUTO_RESET) { h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
+            }
+        } else if (g.over()) { done = true; g.payoffs(pay); }
+    } else {
+        if (h.episode != 0 && g.over()) { done = true; g.payoffs(pay); }
+    }
+    __syncwarp();
+    g.legal(smask, lane);
+    __syncwarp();
+    const int seat = (MODE == kModeObserve && p.seat) ? p.seat[env] : g.player();
+    if (p.obs) {
+        g.encode_obs(seat, MODE != kModeObserve && h.t == 0, srow, lane);
+        __syncwarp();
+        warp_flush_row<G, ObsT>(p.obs, env, srow, lane);
+    }
+    if (p.mask) warp_write_mask<G>(p.mask, env, smask, lane);
+    if (lane == 0) {
+        if (p.cur_player) p.cur_player[env] = g.player();
+        if (p.done) p.done[env] = done ? 1 : 0;
+        if (p.payoffs) {
+#pragma unroll
+            for (int k = 0; k < G::P; k++) p.payoffs[env * G::P + k] = pay[k];
+        }
+    }
+    if constexpr (MODE != kModeObserve) {
+        wchance_close(ch, p, env);
+        if (lane == 0) { row[0] = h.episode; row[1] = h.t; }
+        g.store(row + kHeaderWords, lane);
+    }
+    err |= ch.err();
+    if (err && p.err && lane == 0) p.err[env] |= err;
+}
+
+template <class G, class Ch, class ObsT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t env = (size_t)blockIdx.x * (BLOCK / 32) + wib;
+    if (env >= p.n) return;
+    constexpr int kRowBytes = (G::OBS * (int)sizeof(ObsT) + 15) & ~15;
+    constexpr int kWarpBytes = kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15) + G::kScratchBytes;
+    uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)wib * kWarpBytes;
+    ObsT *srow = reinterpret_cast<ObsT *>(base);
+    uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
+    uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
+    warp_tile_zero(base, kRowBytes, lane);
+    __syncwarp();
+
+    uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
+    EnvHeader h; h.episode = row[0]; h.t = row[1];
+    G g; g.load(row + kHeaderWords, lane);
+    WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
+    int err = 0;
+    if (h.episode == 0) { ch.begin(0u, kResetStep); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
+    __syncwarp();
+    g.legal(smask, lane);
+    __syncwarp();
+    size_t rowi = env;
+    for (int t = 0; t < p.T; t++, rowi += p.n) {
+        if (p.t_obs) {
+            g.encode_obs(g.player(), h.t == 0, srow, lane);
+            __syncwarp();
+            warp_flush_row<G, ObsT>(p.t_obs, rowi, srow, lane);
+        }
+        if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
+        const uint32_t word = wpolicy_word(ch, p, env, h.episode - 1u, h.t);
+        const int cnt = warp_popc_words(smask, G::MASK_WORDS, lane);
+        const int k = (int)__umulhi(word, (uint32_t)cnt);
+        const int a = warp_kth_set_bit(smask, G::MASK_WORDS, k, lane);
+        const int pl = g.player();
+        __syncwarp();
+        g.step(a, ch, smask, scratch, lane, err);
+        h.t++;
+        const bool over = g.over();
+        float pay[G::P];
+#pragma unroll
+        for (int q = 0; q < G::P; q++) pay[q] = 0.f;
+        if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
+        __syncwarp();
+        g.legal(smask, lane);                            // legal set of the state the next iteration emits
+        __syncwarp();
+        if (lane == 0) {
+            if (p.t_player) __stcs(p.t_player + rowi, pl);
+            if (p.t_action) __stcs(p.t_action + rowi, a);
+            if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
+        }
+        if (p.t_payoffs && lane < G::P) {
+            float v = pay[0];
+#pragma unroll
+            for (int q = 1; q < G::P; q++) v = lane == q ? pay[q] : v;
+            p.t_payoffs[rowi * G::P + lane] = v;
+        }
+    }
+    wchance_close(ch, p, env);
+    if (lane == 0) { row[0] = h.episode; row[1] = h.t; }
+    g.store(row + kHeaderWords, lane);
+    err |= ch.err();
+    if (err && p.err && lane == 0) p.err[env] |= err;
+}
+
+template <class G, class Ch, class ObsT>
+cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
+    constexpr int BLOCK = 128;
+    const unsigned grid = (unsigned)((p.n + BLOCK / 32 - 1) / (BLOCK / 32));
+    constexpr int kRowBytes = (G::OBS * (int)sizeof(ObsT) + 15) & ~15;
+    const size_t smem = (size_t)(BLOCK / 32) * (kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15) + G::kScratchBytes);
+    cudaError_t e = cudaSuccess;
+#define RLC_WLAUNCH(KERNEL)                                                                          \
+    do {                                                                                             \
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) { KERNEL<<<grid, BLOCK, smem, stream>>>(p); e = cudaGetLastError(); }  \
+    } while (0)
+    switch (op) {
+    case kOpReset: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeReset, BLOCK>)); break;
+    case kOpStep: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeStep, BLOCK>)); break;
+    case kOpObserve: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
+    case kOpRollout: RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK>)); break;
+    default: e = cudaErrorInvalidValue;
+    }
+#undef RLC_WLAUNCH
+    return e;
+}
+
+template <class G, class ObsT>
+cudaError_t dispatch_wgame(int op, int chance, const KParams &p, cudaStream_t stream) {
+    if (chance == RLC_CHANCE_PHILOX) return launch_wop<G, ChancePhilox, ObsT>(op, p, stream);
+    if (chance == RLC_CHANCE_TAPE) return launch_wop<G, ChanceTape, ObsT>(op, p, stream);
+    if (chance == RLC_CHANCE_MT19937) return launch_wop<G, ChanceMt, ObsT>(op, p, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rlc

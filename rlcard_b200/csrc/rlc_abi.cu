@@ -37,7 +37,7 @@ static const rlc_info kInfo[RLC_NUM_GAMES] = {
     { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, {0, 0, 0, 0} },
     { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, {0, 0, 0, 0} },
     { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 901, RLC_U8, 1, 859, 0, 0, 32, {0, 0, 0, 0} },
-    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, 0, 0, 1, {0, 0, 0, 0} },
+    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, {0, 0, 0, 0} },
 };
 
 static int dispatch(int game, int op, const rlc_buffers *b, rlc::KParams &p, void *stream) {

@@ -139,7 +139,11 @@ def record_game(rlcard, game, out_dir):
         def views(always):
             if always or pol.random() < p_view:
                 for seat in range(P):
-                    emit(slot, 2, seat, env, env.get_state(seat))
+                    try:
+                        st = env.get_state(seat)
+                    except UnboundLocalError:      # doudizhu peasants before the landlord has acted (envs/doudizhu.py:62-65)
+                        continue
+                    emit(slot, 2, seat, env, st)
 
         for ep in range(episodes):
             state, pid = env.reset()

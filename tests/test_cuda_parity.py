@@ -170,7 +170,7 @@ def test_full_size_properties(game):
     if game in ('leduc-holdem', 'limit-holdem'):
         assert bool((pay.sum(-1) == 0).all())                              # zero-sum
         assert bool(((pay * 2) == (pay * 2).round()).all())                # multiples of 0.5
-    assert int(done.sum()) > n                                             # episodes finish and restart
+    assert int(done.sum()) > (n if game in ('blackjack', 'leduc-holdem', 'limit-holdem') else 0)   # episodes finish and restart
     # shard invariance: envs [n/2, n) of this run == a second VecEnv with env_id_base n/2
     env2 = rlcard_b200.VecEnv(game, n // 2, seed=7, env_id_base=n // 2)
     env2.reset()
