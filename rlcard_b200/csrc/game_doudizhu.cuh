@@ -1,0 +1,217 @@
+// game_doudizhu.cuh -- DouDizhu, 3 players, 27 472 actions, one env per warp.
+// Reference: rlcard/games/doudizhu/{game,round,player,dealer,judger,utils}.py, rlcard/envs/doudizhu.py.
+//
+// Suits never matter: a hand is 15 rank counts (3456789TJQKA2BR) packed as nibbles in one 64-bit word.
+// The legal set is the reference's, restated over the constant action table (SURVEY F-DDZ1/F-DDZ2):
+//   lead   : every non-pass action whose rank counts are contained in the hand (== the judger's cached
+//            playable_cards, judger.py:124-331)
+//   follow : 'pass' + contained actions of the target's type with larger weight + bombs (larger bombs if
+//            the target is a bomb) + rocket; only 'pass' against a rocket (utils.py:225-262)
+// Containment of a table row in the hand is one SWAR test: (((hand | M) - row) & M) == M, M = 0x88..8
+// (counts <= 4 < 8, so no borrow crosses a nibble).  The 32 lanes test 32 consecutive action ids and one
+// __ballot_sync is one word of the bit-packed mask.  A word-level prefilter (nibble-wise minimum of the
+// 32 rows of a word must be contained, and the word must overlap the candidate id ranges) skips most of
+// the 859 words, so a step reads a few KB of the 220 KB table instead of all of it.
+//
+// Game words (20): [0..5] hands p0..p2 (lo,hi)  [6..11] played counts p0..p2
+//   [12..16] last nine action ids of the trace, oldest first, 16 bits each (initialised to 'pass' = zero
+//            rows; [16] upper half unused)   [17] last action of p0 | p1 << 16   [18] last action of p2 |
+//            greater player's action << 16   [19] greater [0:2) (3 = none) | current [2:4) | winner [4:6) (3 = none)
+#pragma once
+#include "common.cuh"
+#include "kernels_warp.cuh"
+
+namespace rlc {
+
+struct DdzTables {
+    const uint64_t *rows;      // [27472] nibble-packed rank counts ('pass' = 0)
+    const uint64_t *need;      // [864]   nibble-wise min over the 32 rows of each mask word
+    const uint8_t *type;       // [27472]
+    const uint8_t *weight;     // [27472]
+    const uint32_t *tw_start;  // [39][17] first id of type t with weight >= w; [t][16] = end of type t
+};
+constexpr int kDdzPass = 27471, kDdzRocket = 27470, kDdzBomb0 = 27457, kDdzTypeBomb = 35, kDdzTypeRocket = 36;
+constexpr uint64_t kNibHi = 0x8888888888888888ull;
+
+__device__ __forceinline__ bool ddz_contains(uint64_t hand, uint64_t row) { return (((hand | kNibHi) - row) & kNibHi) == kNibHi; }
+__device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of cards = sum of nibbles
+    c = (c & 0x0f0f0f0f0f0f0f0full) + ((c >> 4) & 0x0f0f0f0f0f0f0f0full);
+    return (int)((c * 0x0101010101010101ull) >> 56);
+}
+
+struct Doudizhu {
+    static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 859;
+    static constexpr bool kMaskBitpacked = true;
+    static constexpr int kScratchBytes = 64;
+    DdzTables tab;
+    uint64_t hand[3], played[3];
+    uint32_t tr[5];            // nine 16-bit action ids, entry k in tr[k/2] >> (16*(k&1)), k = 8 is the newest
+    uint32_t last_by[3], greater_action;
+    int greater, cur, winner;
+
+    __device__ __forceinline__ uint64_t sel3(const uint64_t (&a)[3], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : a[2]); }
+    __device__ __forceinline__ void put3(uint64_t (&a)[3], int p, uint64_t v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; }
+    __device__ __forceinline__ uint32_t trace_at(int k) const {
+        const uint32_t w = k < 2 ? tr[0] : (k < 4 ? tr[1] : (k < 6 ? tr[2] : (k < 8 ? tr[3] : tr[4])));
+        return (w >> (16 * (k & 1))) & 0xffffu;
+    }
+    __device__ __forceinline__ void bind(const KParams &p) {
+        tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const uint64_t *>(p.tab[1]);
+        tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
+        tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);
+    }
+    __device__ void load(const uint32_t *w, int) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            hand[p] = (uint64_t)w[2 * p] | ((uint64_t)w[2 * p + 1] << 32);
+            played[p] = (uint64_t)w[6 + 2 * p] | ((uint64_t)w[7 + 2 * p] << 32);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) tr[k] = w[12 + k];
+        last_by[0] = w[17] & 0xffffu; last_by[1] = w[17] >> 16; last_by[2] = w[18] & 0xffffu; greater_action = w[18] >> 16;
+        greater = w[19] & 3; cur = (w[19] >> 2) & 3; winner = (w[19] >> 4) & 3;
+    }
+    __device__ void store(uint32_t *w, int lane) const {
+        if (lane != 0) return;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            w[2 * p] = (uint32_t)hand[p]; w[2 * p + 1] = (uint32_t)(hand[p] >> 32);
+            w[6 + 2 * p] = (uint32_t)played[p]; w[7 + 2 * p] = (uint32_t)(played[p] >> 32);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) w[12 + k] = tr[k];
+        w[17] = last_by[0] | (last_by[1] << 16); w[18] = last_by[2] | (greater_action << 16);
+        w[19] = (uint32_t)greater | (cur << 2) | (winner << 4);
+    }
+    // game.py:23-51, round.py:25-39, dealer.py:12-76: rank-sorted deck, one shuffle, 17/17/17 + 3 to seat 0
+    template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
+        if (lane == 0) {
+            for (int i = 0; i < 52; i++) deck[i] = (uint8_t)(i >> 2);
+            deck[52] = 13; deck[53] = 14;
+        }
+        __syncwarp();
+        for (int i = 53; i >= 1; i--) {
+            const uint32_t j = ch.below((uint32_t)i + 1u);
+            if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
+        }
+        __syncwarp();
+        hand[0] = hand[1] = hand[2] = 0; played[0] = played[1] = played[2] = 0;
+        for (int k = 0; k < 54; k++) {
+            const int p = k < 51 ? k / 17 : 0;
+            put3(hand, p, sel3(hand, p) + (1ull << (4 * deck[k])));
+        }
+        __syncwarp();
+        const uint32_t pp = (uint32_t)kDdzPass | ((uint32_t)kDdzPass << 16);
+        tr[0] = tr[1] = tr[2] = tr[3] = tr[4] = pp;
+        last_by[0] = last_by[1] = last_by[2] = kDdzPass; greater_action = kDdzPass;
+        greater = 3; cur = 0; winner = 3;
+    }
+    __device__ __forceinline__ int player() const { return cur; }
+    __device__ __forceinline__ bool over() const { return winner != 3; }      // game.py:155-163
+
+    // player.py:60-76 / game.py:110-128: bit-packed legal set of the current player into smask[859]
+    __device__ void legal(uint32_t *smask, int lane) {
+        for (int j = lane; j < MASK_WORDS; j += 32) smask[j] = 0;
+        __syncwarp();
+        if (winner != 3) return;                                               // terminal: actions = []
+        const uint64_t H = sel3(hand, cur);
+        const bool lead = greater == 3 || greater == cur;
+        // candidate id ranges [lo1,hi1) u [lo2,hi2) (+ rocket, handled as part of range 2 when adjacent)
+        int lo1 = 0, hi1 = kDdzPass, lo2 = 0, hi2 = 0;
+        if (!lead) {
+            const int tt = tab.type[greater_action], tw = tab.weight[greater_action];
+            if (tt == kDdzTypeRocket) { lo1 = hi1 = 0; }
+            else if (tt == kDdzTypeBomb) { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = kDdzRocket + 1; }   // larger bombs + rocket
+            else { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = (int)tab.tw_start[tt * 17 + 16]; lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
+        }
+        for (int wb = 0; wb < (MASK_WORDS + 31) / 32; wb++) {
+            const int j = wb * 32 + lane;                                      // phase A: which words can hold a legal id
+            bool live = false;
+            if (j < MASK_WORDS) {
+                const int a0 = 32 * j, a1 = a0 + 32;
+                const bool overlap = (a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2);
+                live = overlap && ddz_contains(H, tab.need[j]);
+            }
+            uint32_t lw = __ballot_sync(kFull, live);
+            while (lw) {                                                       // phase B: expand the live words
+                const int b = __ffs(lw) - 1; lw &= lw - 1;
+                const int jj = wb * 32 + b, id = 32 * jj + lane;
+                const bool cand = (id >= lo1 && id < hi1) || (id >= lo2 && id < hi2);
+                const bool ok = cand && ddz_contains(H, tab.rows[id]);
+                const uint32_t word = __ballot_sync(kFull, ok);
+                if (lane == 0) smask[jj] = word;
+            }
+        }
+        __syncwarp();
+        if (!lead && lane == 0) smask[kDdzPass >> 5] |= 1u << (kDdzPass & 31);
+    }
+    // env.py:65-86, game.py:53-81, round.py:52-79, player.py:78-108, judger.py:335-348
+    template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *, int lane, int &err) {
+        if (id < 0 || id >= A || !((smask[id >> 5] >> (id & 31)) & 1u)) {     // replay feeds legal ids only
+            err |= 4;
+            id = warp_kth_set_bit(smask, MASK_WORDS, 0, lane);
+            if (id < 0) return;
+        }
+        const int p = cur;
+        if (id != kDdzPass) {
+            const uint64_t c = tab.rows[id];
+            put3(hand, p, sel3(hand, p) - c);
+            put3(played, p, sel3(played, p) + c);
+            greater = p; greater_action = (uint32_t)id;
+        }
+        tr[0] = (tr[0] >> 16) | (tr[1] << 16); tr[1] = (tr[1] >> 16) | (tr[2] << 16);
+        tr[2] = (tr[2] >> 16) | (tr[3] << 16); tr[3] = (tr[3] >> 16) | (tr[4] << 16);
+        tr[4] = (uint32_t)id;                                                 // entry 8 = newest
+        last_by[0] = p == 0 ? (uint32_t)id : last_by[0]; last_by[1] = p == 1 ? (uint32_t)id : last_by[1];
+        last_by[2] = p == 2 ? (uint32_t)id : last_by[2];
+        if (sel3(hand, p) == 0) winner = p;
+        cur = p == 2 ? 0 : p + 1;
+    }
+    __device__ __forceinline__ void payoffs(float *out) const {              // judger.py:351-359 (landlord = seat 0)
+        out[0] = winner == 0 ? 1.f : 0.f; out[1] = out[2] = winner == 0 ? 0.f : 1.f;
+    }
+    // envs/doudizhu.py:153-167: 54-d block of rank counts c; lane writes elements lane and lane+32
+    template <class T> __device__ __forceinline__ void put54(T *dst, uint64_t c, int lane) const {
+        {
+            const int e = lane, r = e >> 2, k = e & 3;
+            dst[e] = (T)(((int)((c >> (4 * r)) & 15ull) > k) ? 1 : 0);
+        }
+        if (lane < 22) {
+            const int e = lane + 32;
+            int v;
+            if (e < 52) { const int r = e >> 2, k = e & 3; v = ((int)((c >> (4 * r)) & 15ull) > k); }
+            else v = ((c >> (4 * (e - 39))) & 15ull) != 0;                    // e = 52 -> rank 13 (B), 53 -> rank 14 (R)
+            dst[e] = (T)v;
+        }
+    }
+    __device__ __forceinline__ uint64_t action_counts(uint32_t id) const { return tab.rows[id]; }
+    template <class T> __device__ __forceinline__ void one_hot(T *dst, int n, int size, int lane) const {   // :169-173 (Q-DDZ1)
+        if (lane == 0) dst[n >= 1 ? n - 1 : size - 1] = (T)1;
+    }
+    // envs/doudizhu.py:26-91 (row pre-zeroed; 790 used for the landlord, 901 for peasants, stride 912)
+    template <class T> __device__ void encode_obs(int seat, bool, T *row, int lane) const {
+        const int up = seat == 2 ? 0 : seat + 1, down = seat == 0 ? 2 : seat - 1;
+        put54(row, sel3(hand, seat), lane);
+        put54(row + 54, sel3(hand, up) + sel3(hand, down), lane);
+        const uint32_t newest = trace_at(8), prev = trace_at(7);
+        put54(row + 108, action_counts(newest != (uint32_t)kDdzPass ? newest : prev), lane);
+#pragma unroll
+        for (int k = 0; k < 9; k++) put54(row + 162 + 54 * k, action_counts(trace_at(k)), lane);
+        if (seat == 0) {
+            put54(row + 648, played[2], lane);
+            put54(row + 702, played[1], lane);
+            one_hot(row + 756, ddz_cards(hand[2]), 17, lane);
+            one_hot(row + 773, ddz_cards(hand[1]), 17, lane);
+        } else {
+            const int mate = 3 - seat;
+            put54(row + 648, played[0], lane);
+            put54(row + 702, sel3(played, mate), lane);
+            put54(row + 756, action_counts(last_by[0]), lane);
+            put54(row + 810, action_counts(mate == 1 ? last_by[1] : last_by[2]), lane);
+            one_hot(row + 864, ddz_cards(hand[0]), 20, lane);
+            one_hot(row + 884, ddz_cards(sel3(hand, mate)), 17, lane);
+        }
+    }
+};
+
+}  // namespace rlc

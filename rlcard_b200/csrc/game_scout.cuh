@@ -37,6 +37,7 @@ struct Scout {
     __device__ __forceinline__ void put(uint64_t (&a)[4], int p, uint64_t v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
     __device__ __forceinline__ void puti(int (&a)[4], int p, int v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
 
+    __device__ __forceinline__ void bind(const KParams &) {}
     __device__ void load(const uint32_t *w, int lane) {
 #pragma unroll
         for (int p = 0; p < 4; p++) {

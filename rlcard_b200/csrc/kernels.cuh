@@ -16,6 +16,7 @@ struct KParams {
     void *obs; void *mask; int32_t *cur_player; uint8_t *done; float *payoffs; void *terminal_obs; int32_t *err;
     const int32_t *actions; const uint8_t *reset_mask; const int32_t *seat; int flags;
     void *t_obs; void *t_mask; int32_t *t_action; int32_t *t_player; uint8_t *t_done; float *t_payoffs; int T;
+    const void *tables; const void *tab[5];      // per-game constant tables (device pointers), see Game::bind
 };
 
 enum { kModeReset = 0, kModeStep = 1, kModeObserve = 2 };

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
     EnvHeader h; h.episode = row[0]; h.t = row[1];
-    G g; g.load(row + kHeaderWords, lane);
+    G g; g.bind(p); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0; bool done = false;
     float pay[G::P];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
     EnvHeader h; h.episode = row[0]; h.t = row[1];
-    G g; g.load(row + kHeaderWords, lane);
+    G g; g.bind(p); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0;
     if (h.episode == 0) { ch.begin(0u, kResetStep); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }

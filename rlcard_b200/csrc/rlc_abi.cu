@@ -36,7 +36,7 @@ static const rlc_info kInfo[RLC_NUM_GAMES] = {
     { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, {0, 0, 0, 0} },
     { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, {0, 0, 0, 0} },
     { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, {0, 0, 0, 0} },
-    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 901, RLC_U8, 1, 859, 0, 0, 32, {0, 0, 0, 0} },
+    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, {0, 0, 0, 0} },
     { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, {0, 0, 0, 0} },
 };
 
@@ -58,6 +58,7 @@ static int dispatch(int game, int op, const rlc_buffers *b, rlc::KParams &p, voi
 #endif
     default: return fail(RLC_ENOTIMPL, "game %d has no kernels in this build", game);
     }
+    if (e == cudaErrorNotReady) return fail(RLC_ENOTABLE, "game %d needs rlc_upload_tables() on this device first", game);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? RLC_EINVAL : RLC_ECUDA, "CUDA: %s", cudaGetErrorString(e));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return RLC_OK;

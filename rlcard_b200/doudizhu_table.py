@@ -152,3 +152,45 @@ def cards_to_array(c):
 
 def action_strings():
     return [counts_to_str(unpack_counts(x)) for x in load()['counts']]
+
+
+def build_blob():
+    """Device table blob for rlc_upload_tables(RLC_DOUDIZHU, ...) (layout: csrc/tu_doudizhu.cu DdzBlobHeader):
+    rows u64[27472] | need u64[864] (nibble-wise min of the 32 rows of each mask word) | type u8[27472] |
+    weight u8[27472] | tw_start u32[38][17] (first id of type t with weight >= w; [t][16] = end of type t)."""
+    import struct
+    tab = load()
+    rows = tab['counts'].astype(np.uint64)
+    n_words = (NUM_ACTIONS + 31) // 32
+    nib = np.stack([(rows >> np.uint64(4 * r)) & np.uint64(15) for r in range(15)], axis=1).astype(np.uint8)   # [A, 15]
+    pad = np.full((n_words * 32 - NUM_ACTIONS, 15), 15, np.uint8)
+    mins = np.concatenate([nib, pad]).reshape(n_words, 32, 15).min(axis=1)
+    need = np.zeros(864, np.uint64)
+    for r in range(15):
+        need[:n_words] |= mins[:, r].astype(np.uint64) << np.uint64(4 * r)
+    ntypes = len(TYPE_NAMES)
+    tw = np.zeros((ntypes, 17), np.uint32)
+    types, weights = tab['type'].astype(np.int64), tab['weight'].astype(np.int64)
+    for t in range(ntypes):
+        ids = np.nonzero(types == t)[0]
+        lo, hi = int(ids.min()), int(ids.max()) + 1
+        assert np.array_equal(ids, np.arange(lo, hi)), 'type ids must be contiguous'
+        w = weights[lo:hi]
+        assert np.all(np.diff(w) >= 0), 'weights must be non-decreasing inside a type'
+        for k in range(16):
+            tw[t, k] = lo + int(np.searchsorted(w, k, side='left'))
+        tw[t, 16] = hi
+    parts = [rows.tobytes(), need.tobytes(), tab['type'].tobytes(), tab['weight'].tobytes(), tw.tobytes()]
+    hdr_size = 64
+    offs, cur = [], hdr_size
+    for b in parts:
+        cur = (cur + 15) & ~15
+        offs.append(cur)
+        cur += len(b)
+    total = (cur + 15) & ~15
+    hdr = struct.pack('<4sIII6Q', b'DDZ1', NUM_ACTIONS, 864, ntypes, *offs, total)
+    blob = bytearray(total)
+    blob[:len(hdr)] = hdr
+    for o, b in zip(offs, parts):
+        blob[o:o + len(b)] = b
+    return bytes(blob)

@@ -35,12 +35,17 @@ def _scout_actions():
     return acts
 
 
+def _doudizhu_actions():
+    from . import doudizhu_table
+    return doudizhu_table.action_strings()                                 # games/doudizhu/utils.py:21-27 ID_2_ACTION
+
+
 _SPECS = {
     'blackjack': dict(actions=lambda: ['hit', 'stand'], dtype=np.int64, shape=lambda d: (d,)),
     'leduc-holdem': dict(actions=lambda: _POKER_ACTIONS, dtype=np.float64, shape=lambda d: (d,)),
     'limit-holdem': dict(actions=lambda: _POKER_ACTIONS, dtype=np.float64, shape=lambda d: (d,)),
     'uno': dict(actions=_uno_actions, dtype=np.int64, shape=lambda d: (4, 4, 15)),
-    'doudizhu': dict(actions=lambda: None, dtype=np.int8, shape=lambda d: (d,)),
+    'doudizhu': dict(actions=lambda: _doudizhu_actions(), dtype=np.int8, shape=lambda d: (d,)),
     'scout': dict(actions=_scout_actions, dtype=np.float32, shape=lambda d: (d,)),
 }
 _STATE_SHAPE = {'uno': [4, 4, 15]}
@@ -70,6 +75,9 @@ class Env:
         self.state_shape = [list(_STATE_SHAPE.get(env_id, [d])) for d in self._vec.obs_dims]
         self.action_shape = [[54] if env_id == 'doudizhu' else None for _ in range(self.num_players)]
         self.actions = self._spec['actions']()
+        if env_id == 'doudizhu':
+            from . import doudizhu_table
+            self._features = doudizhu_table.load()['features']
         self.timestep = 0
         self.action_recorder = []
         self.agents = None
@@ -95,8 +103,14 @@ class Env:
     def _dict_from(self, obs_row, mask_row, seat_for_dim):
         d = self._vec.obs_dims[seat_for_dim]
         obs = obs_row[:d].cpu().numpy().astype(self._spec['dtype']).reshape(self._spec['shape'](d))
-        ids = np.nonzero(mask_row.cpu().numpy())[0].tolist()
-        state = {'obs': obs, 'legal_actions': OrderedDict((int(a), None) for a in ids)}
+        m = mask_row.cpu().numpy()
+        if self._vec.mask_bitpacked:
+            m = np.unpackbits(m.view(np.uint8), bitorder='little')[:self.num_actions]
+        ids = np.nonzero(m)[0].tolist()
+        if self.name == 'doudizhu':                                        # envs/doudizhu.py:112-120: id -> 54-d feature
+            state = {'obs': obs, 'legal_actions': OrderedDict((int(a), self._features[a]) for a in ids)}
+        else:
+            state = {'obs': obs, 'legal_actions': OrderedDict((int(a), None) for a in ids)}
         state['raw_legal_actions'] = [self.actions[a] for a in ids] if self.actions else list(ids)
         state['raw_obs'] = {'obs': obs, 'legal_actions': state['raw_legal_actions']}
         state['action_record'] = self.action_recorder
@@ -139,6 +153,8 @@ class Env:
         return p.astype(np.int64) if self.name in _INT_PAYOFF else p
 
     def get_action_feature(self, action):
+        if self.name == 'doudizhu':
+            return self._features[action].copy()               # envs/doudizhu.py:136-142
         feature = np.zeros(self.num_actions, dtype=np.int8)   # env.py:217-226 default one-hot
         feature[action] = 1
         return feature

@@ -22,6 +22,22 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_TABLES_ON = set()
+
+
+def _upload_doudizhu_tables(L, device):
+    """The constant action table (games/doudizhu/jsondata.zip in the reference, utils.py:14-38) goes to the
+    device once; the library keeps it until process exit."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _TABLES_ON:
+        return
+    from . import doudizhu_table
+    blob = doudizhu_table.build_blob()
+    buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+    check(L.rlc_upload_tables(GAME_IDS['doudizhu'], idx, C.cast(buf, C.c_void_p), len(blob)))
+    _TABLES_ON.add(idx)
+
+
 def seed_words(seed):
     """rlcard/utils/seeding.py:33-113: sha512(str(seed))[:8] -> uint32 words given to RandomState.seed."""
     import hashlib
@@ -90,6 +106,8 @@ class VecEnv:
         self.mt = None
         self._buf = None
         self.launches = 0
+        if env_id == 'doudizhu':
+            _upload_doudizhu_tables(self.L, self.device)
 
     # ------------------------------------------------------------------ chance sources
     def set_tape(self, tape):
