@@ -31,8 +31,10 @@ typedef struct orc_chance {
     int kind;
     /* tape (replay of recorded reference draws) */
     const uint8_t *tape; int64_t tape_len, tape_pos; int tape_err;
-    /* philox (throughput mode; spec shared with the CUDA kernels) */
-    uint32_t key0, key1, env_id, episode, t, draw;
+    /* philox (throughput mode; spec shared with the CUDA kernels, see DESIGN.md "Philox streams"):
+     * k = env-steps taken so far, dom = 1 inside a step / 2 reset outside a step, R = chain register,
+     * draw = index of the next fresh word */
+    uint32_t key0, key1, env_id, k, dom, R, draw;
     /* numpy-legacy MT19937 (np.random.RandomState) */
     uint32_t mt[624]; int mti;
     /* optional recording of the draws made (any kind) */
@@ -40,12 +42,15 @@ typedef struct orc_chance {
 } orc_chance;
 
 uint32_t orc_below(orc_chance *ch, uint32_t n);          /* uniform in [0, n) */
+uint32_t orc_chain(orc_chance *ch, uint32_t n);          /* philox: peeled off the step's base word; else = orc_below */
+uint32_t orc_philox_begin_step(orc_chance *ch, uint32_t k, uint32_t n_legal);   /* -> index of the policy's action */
+void orc_philox_begin_reset(orc_chance *ch, uint32_t k);
 void orc_shuffle_u8(orc_chance *ch, uint8_t *x, int n);   /* numpy legacy list shuffle */
 void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail);
 void orc_mt_init_by_array(orc_chance *ch, const uint32_t *key, int len);
 uint32_t orc_mt_next(orc_chance *ch);
 void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t out[4]);
-uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t t, uint32_t block, uint32_t word);
+uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t c0, uint32_t c1, uint32_t dom, uint32_t word);
 
 /* ---- per-game engines ---- */
 typedef struct orc_game_vt {

@@ -69,13 +69,27 @@ void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-/* throughput-mode draw layout (DESIGN.md "Philox streams"): block b of step (episode e, step t) of an
- * env has counter = (t, e, env_id, b), key = seed.  Block 0 = [policy word, chance draw 0, 1, 2];
- * block b >= 1 = chance draws 3+4(b-1) .. 6+4(b-1).  word 0..3 selects inside the block. */
-uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t episode, uint32_t t, uint32_t block, uint32_t word) {
-    uint32_t ctr[4] = { t, episode, env_id, block }, out[4];
+/* throughput-mode draw layout (DESIGN.md "Philox streams"; rlcard_b200/csrc/common.cuh is the CUDA twin).
+ * A word is Philox(ctr = (c0, c1, env_id, dom), key = seed)[word]:
+ *   base word of step k      W_k = (k >> 2, 0, env, dom 0)[k & 3]
+ *   policy                   index among the n legal actions = mulhi(W_k, n); chain register R = lo32(W_k * n)
+ *   chain(m)                 v = mulhi(R, m), R = lo32(R * m)
+ *   fresh draw j of step k   F_j = (k, j >> 2, env, dom 1)[j & 3]
+ *   reset outside a step     F_j = (k, j >> 2, env, dom 2)[j & 3]; R starts as F_0, fresh draws at j = 1 */
+uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t c0, uint32_t c1, uint32_t dom, uint32_t word) {
+    uint32_t ctr[4] = { c0, c1, env_id, dom }, out[4];
     orc_philox4x32_10(ctr, k0, k1, out);
     return out[word & 3u];
+}
+uint32_t orc_philox_begin_step(orc_chance *ch, uint32_t k, uint32_t n_legal) {
+    uint32_t w = orc_philox_word(ch->key0, ch->key1, ch->env_id, k >> 2, 0u, 0u, k & 3u);
+    ch->k = k; ch->dom = 1u; ch->draw = 0u;
+    ch->R = w * n_legal;
+    return (uint32_t)(((uint64_t)w * n_legal) >> 32);
+}
+void orc_philox_begin_reset(orc_chance *ch, uint32_t k) {
+    ch->k = k; ch->dom = 2u; ch->draw = 1u;
+    ch->R = orc_philox_word(ch->key0, ch->key1, ch->env_id, k, 0u, 2u, 0u);
 }
 
 /* ------------------------------------------------------------------ bounded draws */
@@ -92,8 +106,8 @@ uint32_t orc_below(orc_chance *ch, uint32_t n) {
         break;
     case ORC_CHANCE_PHILOX:
         {
-            uint32_t d = ch->draw++, blk = d < 3 ? 0u : 1u + ((d - 3u) >> 2), word = d < 3 ? d + 1u : ((d - 3u) & 3u);
-            v = (uint32_t)(((uint64_t)orc_philox_word(ch->key0, ch->key1, ch->env_id, ch->episode, ch->t, blk, word) * n) >> 32);
+            uint32_t j = ch->draw++;
+            v = (uint32_t)(((uint64_t)orc_philox_word(ch->key0, ch->key1, ch->env_id, ch->k, j >> 2, ch->dom, j & 3u) * n) >> 32);
         }
         break;
     default: {
@@ -102,6 +116,14 @@ uint32_t orc_below(orc_chance *ch, uint32_t n) {
         mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
         while ((v = (orc_mt_next(ch) & mask)) > max) {}
     } }
+    if (ch->rec) { if (ch->rec_len < ch->rec_cap) ch->rec[ch->rec_len] = (uint8_t)v; ch->rec_len++; }
+    return v;
+}
+uint32_t orc_chain(orc_chance *ch, uint32_t n) {
+    if (ch->kind != ORC_CHANCE_PHILOX) return orc_below(ch, n);
+    uint64_t p = (uint64_t)ch->R * n;
+    ch->R = (uint32_t)p;
+    uint32_t v = (uint32_t)(p >> 32);
     if (ch->rec) { if (ch->rec_len < ch->rec_cap) ch->rec[ch->rec_len] = (uint8_t)v; ch->rec_len++; }
     return v;
 }
@@ -137,7 +159,7 @@ const orc_game_vt *orc_game(int g) {
     }
     return NULL;
 }
-struct orc_env { const orc_game_vt *vt; void *st; orc_chance ch; uint32_t t, episode; };
+struct orc_env { const orc_game_vt *vt; void *st; orc_chance ch; uint32_t t, episode, k; };
 
 static void env_init(orc_env *e, int game_id) {
     memset(e, 0, sizeof *e);
@@ -157,15 +179,27 @@ void orc_env_set_tape(orc_env *e, const uint8_t *tape, int64_t len) {
 }
 void orc_env_set_philox(orc_env *e, uint64_t seed, uint32_t env_id) {
     e->ch.kind = ORC_CHANCE_PHILOX; e->ch.key0 = (uint32_t)seed; e->ch.key1 = (uint32_t)(seed >> 32);
-    e->ch.env_id = env_id; e->ch.episode = 0; e->ch.t = 0xffffffffu; e->ch.draw = 0;
+    e->ch.env_id = env_id; e->k = 0;
+    orc_philox_begin_reset(&e->ch, 0u);
 }
 void orc_env_set_mt(orc_env *e, const uint32_t *key, int len) { orc_mt_init_by_array(&e->ch, key, len); }
 void orc_env_record(orc_env *e, uint8_t *buf, int64_t cap) { e->ch.rec = buf; e->ch.rec_cap = cap; e->ch.rec_len = 0; }
 int64_t orc_env_recorded(const orc_env *e) { return e->ch.rec_len; }
 int64_t orc_env_tape_pos(const orc_env *e) { return e->ch.tape_pos; }
 int orc_env_tape_err(const orc_env *e) { return e->ch.tape_err; }
-int orc_env_reset(orc_env *e) { e->t = 0; return e->vt->reset(e->st, &e->ch); }
-int orc_env_step(orc_env *e, int a) { e->t++; return e->vt->step(e->st, &e->ch, a); }
+int orc_env_reset(orc_env *e) {
+    e->t = 0;
+    if (e->ch.kind == ORC_CHANCE_PHILOX) orc_philox_begin_reset(&e->ch, e->k);
+    return e->vt->reset(e->st, &e->ch);
+}
+int orc_env_step(orc_env *e, int a) {
+    if (e->ch.kind == ORC_CHANCE_PHILOX) {
+        uint8_t m[32768];
+        (void)orc_philox_begin_step(&e->ch, e->k, (uint32_t)e->vt->legal(e->st, m));
+    }
+    e->t++; e->k++;
+    return e->vt->step(e->st, &e->ch, a);
+}
 int orc_env_legal(const orc_env *e, uint8_t *mask) { return e->vt->legal(e->st, mask); }
 int orc_env_obs(const orc_env *e, int seat, float *out) { return e->vt->obs(e->st, seat, out); }
 int orc_env_is_over(const orc_env *e) { return e->vt->is_over(e->st); }
@@ -202,10 +236,10 @@ typedef struct {
     uint8_t *done; float *payoffs; int64_t episodes;
 } rollout_job;
 
-/* first deal: a reset outside any step (t = 0xffffffff of episode 0); later deals happen inside the step
- * that ended the previous episode and continue that step's chance draws */
+/* first deal: a reset outside any step (Philox domain 2); later deals happen inside the step that ended
+ * the previous episode and continue that step's chance draws */
 static void env_new_episode(orc_env *e, int first) {
-    if (first) { e->ch.episode = 0; e->ch.t = 0xffffffffu; e->ch.draw = 0; e->episode = 0; }
+    if (first) { orc_philox_begin_reset(&e->ch, e->k); e->episode = 0; }
     else e->episode++;
     e->t = 0;
     e->vt->reset(e->st, &e->ch);
@@ -233,12 +267,10 @@ static void *rollout_worker(void *arg) {
             if (J->mask) memcpy(J->mask + row * A, m, (size_t)A);
             if (J->player) J->player[row] = pl;
             /* uniform-random legal action: k-th legal id in ascending order, k from the policy stream */
-            e->ch.episode = e->episode; e->ch.t = e->t; e->ch.draw = 0;      /* this step's Philox coordinates */
-            uint32_t r = orc_philox_word(e->ch.key0, e->ch.key1, e->ch.env_id, e->episode, e->t, 0u, 0u);
-            int k = (int)(((uint64_t)r * (uint32_t)cnt) >> 32), a = 0;
+            int k = (int)orc_philox_begin_step(&e->ch, e->k, (uint32_t)cnt), a = 0;   /* this step's Philox coordinates */
             for (a = 0; a < A; a++) if (m[a] && k-- == 0) break;
             if (J->action) J->action[row] = a;
-            e->t++;
+            e->t++; e->k++;
             vt->step(e->st, &e->ch, a);
             int over = vt->is_over(e->st);
             if (J->done) J->done[row] = (uint8_t)over;

@@ -67,14 +67,14 @@ static void leduc_create(void *s) { (void)s; }
 static int leduc_reset(void *s, orc_chance *ch) {
     leduc_t *g = (leduc_t *)s;
     for (int i = 0; i < 6; i++) g->deck[i] = (uint8_t)i;
-    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: one word deals the three cards */
-        uint32_t x = orc_below(ch, 120);
+    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: the three cards ride on the step's base word */
+        uint32_t x = orc_chain(ch, 120);
         int j[3] = { (int)(x / 20), (int)((x / 4) % 5), (int)(x % 4) };
         for (int s = 0; s < 3; s++) { uint8_t t = g->deck[5 - s]; g->deck[5 - s] = g->deck[j[s]]; g->deck[j[s]] = t; }
     } else orc_shuffle_tail_u8(ch, g->deck, 6, 3);
     g->deck_len = 6;
     for (int i = 0; i < 2; i++) { g->hand[i] = g->deck[--g->deck_len]; g->in_chips[i] = 0; g->folded[i] = 0; }
-    int sb = (int)orc_below(ch, 2), bb = (sb + 1) % 2;
+    int sb = (int)orc_chain(ch, 2), bb = (sb + 1) % 2;
     g->in_chips[bb] = 2; g->in_chips[sb] = 1;
     g->public_card = -1; g->game_pointer = sb;
     g->round.raise_amount = 2; g->round.allowed_raise_num = 2;

@@ -9,15 +9,19 @@ namespace rlc {
 constexpr int kWarp = 32;
 
 // ------------------------------------------------------------------------------------------
-// Philox4x32-10, throughput-mode draw layout (DESIGN.md "Philox streams").
-// One block per env-step, computed unconditionally (no divergence between lanes whose episodes end
-// at different times):  block(b) of step (episode e, step-in-episode t) of env i has
-//     counter = (t, e, global env id, b),  key = 64-bit seed.
-//   block 0 = [ policy word | chance draw 0 | chance draw 1 | chance draw 2 ]
-//   block b>=1 = chance draws 3+4(b-1) .. 6+4(b-1)
-// "chance draws of a step" are, in order, every bounded draw the engine makes while applying the
-// action of that step AND while dealing the next episode if the step ended one (auto reset).
-// A reset that is not part of a step (rlc_reset) uses t = 0xffffffff of the episode it starts.
+// Philox4x32-10, throughput-mode draw layout (DESIGN.md "Philox streams"; oracle/orc_common.c is
+// the CPU twin).  key = 64-bit seed.  Every env counts the env-steps it has taken since creation
+// (k, header word 2); all randomness of step k is a pure function of (seed, global env id, k):
+//   base word   W_k = Philox(ctr = (k >> 2, 0, env, 0))[k & 3]     one block serves 4 consecutive steps
+//   policy      index of the action among the cnt legal ones = mulhi(W_k, cnt); chain register R = lo32(W_k * cnt)
+//   chain(n)    v = mulhi(R, n), R = lo32(R * n)                    small draws peeled off the same word
+//   below(n)    v = mulhi(F_j, n), F_j = Philox(ctr = (k, j >> 2, env, 1))[j & 3], j = 0, 1, ... per step
+// "draws of a step" are, in order, every bounded draw the engine makes while applying the action of
+// that step AND while dealing the next episode if the step ended one (auto reset).  A reset that is
+// not part of a step (rlc_reset, first deal of a rollout) uses domain 2: F_j = Philox(ctr = (k, j >> 2,
+// env, 2))[j & 3]; its chain register starts as R = F_0 and its fresh draws at j = 1.
+// chain() is only used where the product of the ranges stays tiny (Leduc: cnt * 120 * 2 <= 960), so the
+// non-uniformity of the last value is below 2^-22.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1,
@@ -32,7 +36,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
-constexpr uint32_t kResetStep = 0xffffffffu;
+__device__ __forceinline__ uint32_t sel4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t i) {
+    const uint32_t lo = (i & 1u) ? b : a, hi = (i & 1u) ? d : c;
+    return (i & 2u) ? hi : lo;
+}
+enum { kDomBase = 0, kDomStep = 1, kDomReset = 2 };
 
 // ------------------------------------------------------------------------------------------
 // Chance sources.  All engines draw through below(n) (uniform in [0,n)); skip_fy(i_hi, i_lo)
@@ -42,32 +50,37 @@ constexpr uint32_t kResetStep = 0xffffffffu;
 // ------------------------------------------------------------------------------------------
 struct ChancePhilox {
     static constexpr int kKind = 0;
-    uint32_t k0, k1, env, episode, t;
-    uint32_t w0, w1, w2, w3;           // block 0 of the current step
-    uint32_t x0, x1, x2, x3, xblk;     // one cached extra block
-    uint32_t d; int err;
+    uint32_t k0, k1, env, k, dom;
+    uint32_t b0, b1, b2, b3, btag;     // cached base block (index k >> 2)
+    uint32_t x0, x1, x2, x3, xtag;     // cached fresh block of the current (k, dom)
+    uint32_t R, d; int err;
     __device__ __forceinline__ void init(uint64_t seed, uint32_t env_) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; err = 0; d = 0; xblk = 0;
-        w0 = w1 = w2 = w3 = x0 = x1 = x2 = x3 = 0; episode = t = 0;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; err = 0; d = 0; k = 0; dom = kDomStep; R = 0;
+        b0 = b1 = b2 = b3 = x0 = x1 = x2 = x3 = 0; btag = xtag = 0xffffffffu;
     }
-    __device__ __forceinline__ void begin(uint32_t episode_, uint32_t t_) {
-        episode = episode_; t = t_; d = 0; xblk = 0;
-        philox4x32_10(t, episode, env, 0u, k0, k1, w0, w1, w2, w3);
+    // step k begins: returns the base word W_k (policy word)
+    __device__ __forceinline__ uint32_t begin_step(uint32_t k_) {
+        k = k_; dom = kDomStep; d = 0; xtag = 0xffffffffu;
+        const uint32_t q = k_ >> 2;
+        if (q != btag) { philox4x32_10(q, 0u, env, (uint32_t)kDomBase, k0, k1, b0, b1, b2, b3); btag = q; }
+        return sel4(b0, b1, b2, b3, k_ & 3u);
     }
-    __device__ __forceinline__ uint32_t policy_word() const { return w0; }
+    // the policy consumed mulhi(W, cnt); what is left of the word feeds chain()
+    __device__ __forceinline__ void seed_chain(uint32_t w, uint32_t cnt) { R = w * cnt; }
+    // a reset outside a step, at lifetime step count k
+    __device__ __forceinline__ void begin_reset(uint32_t k_) {
+        k = k_; dom = kDomReset;
+        philox4x32_10(k_, 0u, env, (uint32_t)kDomReset, k0, k1, x0, x1, x2, x3); xtag = 0;
+        R = x0; d = 1;
+    }
     __device__ __forceinline__ uint32_t raw() {
-        uint32_t r;
-        if (d < 3u) r = d == 0 ? w1 : (d == 1 ? w2 : w3);
-        else {
-            const uint32_t q = 1u + ((d - 3u) >> 2), l = (d - 3u) & 3u;
-            if (q != xblk) { philox4x32_10(t, episode, env, q, k0, k1, x0, x1, x2, x3); xblk = q; }
-            const uint32_t lo = (l & 1u) ? x1 : x0, hi = (l & 1u) ? x3 : x2;
-            r = (l & 2u) ? hi : lo;
-        }
+        const uint32_t q = d >> 2, l = d & 3u;
+        if (q != xtag) { philox4x32_10(k, q, env, dom, k0, k1, x0, x1, x2, x3); xtag = q; }
         d++;
-        return r;
+        return sel4(x0, x1, x2, x3, l);
     }
     __device__ __forceinline__ uint32_t below(uint32_t n) { return __umulhi(raw(), n); }
+    __device__ __forceinline__ uint32_t chain(uint32_t n) { const uint32_t v = __umulhi(R, n); R *= n; return v; }
     __device__ __forceinline__ void skip_fy(int, int) {}
 };
 
@@ -82,7 +95,10 @@ struct ChanceTape {
         return v;
     }
     __device__ __forceinline__ void skip_fy(int i_hi, int i_lo) { if (i_hi >= i_lo) pos += i_hi - i_lo + 1; }
-    __device__ __forceinline__ void begin(uint32_t, uint32_t) {}
+    __device__ __forceinline__ uint32_t chain(uint32_t n) { return below(n); }
+    __device__ __forceinline__ uint32_t begin_step(uint32_t) { return 0u; }
+    __device__ __forceinline__ void seed_chain(uint32_t, uint32_t) {}
+    __device__ __forceinline__ void begin_reset(uint32_t) {}
 };
 
 // np.random.RandomState (MT19937) with numpy's legacy bounded draws: mask-and-reject on 32-bit
@@ -116,7 +132,10 @@ struct ChanceMt {
         return v;
     }
     __device__ void skip_fy(int i_hi, int i_lo) { for (int i = i_hi; i >= i_lo; i--) (void)below((uint32_t)i + 1u); }
-    __device__ __forceinline__ void begin(uint32_t, uint32_t) {}
+    __device__ __forceinline__ uint32_t chain(uint32_t n) { return below(n); }
+    __device__ __forceinline__ uint32_t begin_step(uint32_t) { return 0u; }
+    __device__ __forceinline__ void seed_chain(uint32_t, uint32_t) {}
+    __device__ __forceinline__ void begin_reset(uint32_t) {}
 };
 
 // RandomState.shuffle on a list: for i = n-1 .. 1: j = below(i+1); swap(x[i], x[j]).
@@ -181,13 +200,32 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
     }
 }
 
+// Full-warp fast path: 32 rows of ROW_BYTES (compile time), destination 16-byte aligned -> the trip
+// count and every guard are compile-time, 128-bit LDS / STG.cs / STS per chunk.
+template <int ROW_BYTES>
+__device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *tile, int lane) {
+    constexpr int kChunks = 2 * ROW_BYTES;                    // 32 * ROW_BYTES / 16
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tile), *g4 = reinterpret_cast<uint4 *>(gdst);
+#pragma unroll
+    for (int c0 = 0; c0 < kChunks; c0 += kWarp) {
+        const int c = c0 + lane;
+        if (c0 + kWarp <= kChunks || c < kChunks) {
+            const uint4 v = t4[c];
+            __stcs(g4 + c, v);
+            t4[c] = z;
+        }
+    }
+}
+
 // per-env header words stored in front of the game words of the state
 struct EnvHeader {
     uint32_t episode;   // episodes started (0 = never reset); the running episode has index episode-1
     uint32_t t;         // env-steps taken in the running episode
-    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) { episode = st[i]; t = st[n + i]; }
-    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const { st[i] = episode; st[n + i] = t; }
+    uint32_t k;         // env-steps taken since the env was created (Philox step index)
+    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) { episode = st[i]; t = st[n + i]; k = st[2 * n + i]; }
+    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const { st[i] = episode; st[n + i] = t; st[2 * n + i] = k; }
 };
-constexpr int kHeaderWords = 2;
+constexpr int kHeaderWords = 3;
 
 }  // namespace rlc

@@ -11,6 +11,10 @@ namespace rlc {
 // w1: deck_len;  w2..w14: deck bytes
 struct Blackjack {
     static constexpr int kGameId = 0, P = 1, A = 2, OBS = 2, GAME_WORDS = 15, MASK_WORDS = 1;
+    static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
+    static constexpr int kSharedBytes = 0;
+    static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
+    __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     static constexpr int kMaxResetDraws = 55;
     int p_sum, p_aces, d_first, d_vis_sum, d_vis_aces, winner, deck_len;
     uint8_t deck[52];

@@ -59,9 +59,24 @@ struct BetRound {
 // ========================================================================================
 struct Leduc {
     static constexpr int kGameId = 1, P = 2, A = 4, OBS = 36, GAME_WORDS = 1, MASK_WORDS = 1;
+    static constexpr bool kUsesChain = true;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 6;
+    static constexpr int kSharedBytes = 128;   // deal table: x in [0,120) -> hand0 | hand1 << 2 | public << 4
     int hand0, hand1, pub, pub_dealt, chips0, chips1, rc, fold0, fold1;
     BetRound r;
+    const uint8_t *deal_lut;
+
+    // the 120 ordered draws of 3 cards out of [SJ,HJ,SQ,HQ,SK,HK] as ranks, by Fisher-Yates code
+    static __device__ __forceinline__ uint32_t deal_code(uint32_t x) {
+        const int j[3] = { (int)(x / 20u), (int)((x >> 2) % 5u), (int)(x & 3u) };
+        int c[3];
+        fy_tail_cards<3>(6, j, c);                           // cards popped from positions 5,4,3; rank = card >> 1
+        return (uint32_t)((c[0] >> 1) | ((c[1] >> 1) << 2) | ((c[2] >> 1) << 4));
+    }
+    static __device__ __forceinline__ void fill_shared(uint8_t *sm, int tid, int nthreads) {
+        for (int x = tid; x < 120; x += nthreads) sm[x] = (uint8_t)deal_code((uint32_t)x);
+    }
+    __device__ __forceinline__ void bind_shared(const uint8_t *sm) { deal_lut = sm; }
 
     __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) {
         const uint32_t w = st[i];
@@ -79,18 +94,16 @@ struct Leduc {
     }
     // games/leducholdem/game.py:46-95; deck [SJ,HJ,SQ,HQ,SK,HK] (dealer.py:10) kept as nibbles
     template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
-        int j[3];                                            // Fisher-Yates swap partners of positions 5,4,3
-        if constexpr (Ch::kKind == 0) {                      // throughput: one 32-bit word deals all three cards
-            const uint32_t x = ch.below(120u);
-            j[0] = (int)(x / 20u); j[1] = (int)((x >> 2) % 5u); j[2] = (int)(x & 3u);
+        uint32_t code;
+        if constexpr (Ch::kKind == 0) {                      // throughput: the three cards ride on the policy word
+            code = deal_lut[ch.chain(120u)];                 // x = 20 j0 + 4 j1 + j2: swap partners of positions 5,4,3
         } else {                                             // replay: the reference's draws, i = 5,4,3 (2,1 unobserved)
-            j[0] = (int)ch.below(6u); j[1] = (int)ch.below(5u); j[2] = (int)ch.below(4u);
+            const uint32_t j0 = ch.below(6u), j1 = ch.below(5u), j2 = ch.below(4u);
             ch.skip_fy(2, 1);
+            code = deal_code(20u * j0 + 4u * j1 + j2);
         }
-        int c[3];
-        fy_tail_cards<3>(6, j, c);                           // cards popped from positions 5,4,3
-        hand0 = c[0] >> 1; hand1 = c[1] >> 1; pub = c[2] >> 1; pub_dealt = 0;   // rank = card>>1
-        const int sb = (int)ch.below(2u);
+        hand0 = code & 3; hand1 = (code >> 2) & 3; pub = (code >> 4) & 3; pub_dealt = 0;
+        const int sb = (int)ch.chain(2u);
         chips0 = sb == 0 ? 1 : 2; chips1 = sb == 0 ? 2 : 1;
         fold0 = fold1 = 0; rc = 0;
         r.start(sb, chips0, chips1);
@@ -121,9 +134,12 @@ struct Leduc {
         else if (pub_dealt && hand0 == pub) { w0 = 1; w1 = 0; }
         else if (pub_dealt && hand1 == pub) { w0 = 0; w1 = 1; }
         else { w0 = hand0 >= hand1; w1 = hand1 >= hand0; }
-        const float each = (float)(chips0 + chips1) * ((w0 & w1) ? 0.5f : 1.0f);   // total / #winners
-        out[0] = (w0 ? each - (float)chips0 : -(float)chips0) * 0.5f;
-        out[1] = (w1 ? each - (float)chips1 : -(float)chips1) * 0.5f;
+        // winner(s) share the pot, minus own chips, / big blind 2 -- in exact quarter-chip integers:
+        // split: ((c0+c1)/2 - c0)/2 = (c1-c0)/4; sole winner: c_other/2; loser: -c_own/2
+        const int tie = w0 & w1;
+        const int q0 = tie ? chips1 - chips0 : (w0 ? 2 * chips1 : -2 * chips0);
+        const int q1 = tie ? chips0 - chips1 : (w1 ? 2 * chips0 : -2 * chips1);
+        out[0] = (float)q0 * 0.25f; out[1] = (float)q1 * 0.25f;
     }
     // envs/leducholdem.py:41-71 (row is pre-zeroed)
     template <class T> __device__ __forceinline__ void encode_obs(int seat, bool, T *row) const {
@@ -194,7 +210,11 @@ __device__ __forceinline__ uint32_t holdem_strength7(const int (&c)[7]) {
 // ========================================================================================
 struct Limit {
     static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
+    static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 52;
+    static constexpr int kSharedBytes = 0;
+    static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
+    __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     int card[9];           // 0,2 = p0 hole; 1,3 = p1 hole; 4..8 board in deal order
     int chips0, chips1, rc, fold0, fold1;
     uint32_t rn, rn_shown;  // 4 x 3-bit raise counters

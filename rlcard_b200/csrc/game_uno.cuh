@@ -21,6 +21,10 @@ namespace rlc {
 
 struct Uno {
     static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = 38, MASK_WORDS = 2;
+    static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
+    static constexpr int kSharedBytes = 0;
+    static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
+    __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     static constexpr int kMaxResetDraws = 256;
     uint8_t cards[108];
     uint32_t hc[2][4], hw[2];

@@ -28,17 +28,12 @@ template <> struct ChanceIO<ChancePhilox> {
         c.init(p.seed, p.env_id_base + (uint32_t)i);
     }
     static __device__ __forceinline__ void close(ChancePhilox &, const KParams &, size_t) {}
-    // block 0 of step (episode, t): word 0 drives the random policy, the rest feeds the chance draws
-    static __device__ __forceinline__ uint32_t begin_step(ChancePhilox &c, const KParams &, uint32_t episode, uint32_t t) {
-        c.begin(episode, t);
-        return c.policy_word();
-    }
 };
-template <class Ch>
-__device__ __forceinline__ uint32_t policy_word_only(const KParams &p, size_t i, uint32_t episode, uint32_t t) {
+// base word W_k of step k for the random policy when the chance draws come from a tape / MT19937
+__device__ __forceinline__ uint32_t policy_word_only(const KParams &p, size_t i, uint32_t k) {
     uint32_t o0, o1, o2, o3;
-    philox4x32_10(t, episode, p.env_id_base + (uint32_t)i, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), o0, o1, o2, o3);
-    return o0;
+    philox4x32_10(k >> 2, 0u, p.env_id_base + (uint32_t)i, (uint32_t)kDomBase, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), o0, o1, o2, o3);
+    return sel4(o0, o1, o2, o3, k & 3u);
 }
 template <> struct ChanceIO<ChanceTape> {
     static __device__ __forceinline__ void open(ChanceTape &c, const KParams &p, size_t i) {
@@ -78,8 +73,8 @@ __device__ __forceinline__ void write_mask_row(uint8_t *gmask, size_t env, const
 
 // uniform-random legal action: k-th legal id in ascending order, k = mulhi(policy word, #legal)
 template <class G>
-__device__ __forceinline__ int pick_action(const uint32_t (&m)[G::MASK_WORDS], uint32_t word) {
-    const int cnt = popc_words<G::MASK_WORDS>(m);
+__device__ __forceinline__ int pick_action(const uint32_t (&m)[G::MASK_WORDS], uint32_t word, int &cnt) {
+    cnt = popc_words<G::MASK_WORDS>(m);
     const int k = (int)__umulhi(word, (uint32_t)cnt);
     if constexpr (G::A <= 4) {
         uint32_t mm = m[0];
@@ -96,18 +91,24 @@ template <class G, class Ch, class ObsT, int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = BLOCK * kRowBytes;
+    if constexpr (G::kSharedBytes > 0) {
+        G::fill_shared(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes, threadIdx.x, BLOCK);
+        __syncthreads();
+    }
     const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
     if (warp_env0 >= p.n) return;
     const size_t i = warp_env0 + lane;
     const bool valid = i < p.n;
     const int nvalid = (int)min((size_t)32, p.n - warp_env0);
-    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
     ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * G::OBS;
     ObsT *row = tile + lane * G::OBS;
     warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
     __syncwarp();
 
     G g; EnvHeader h; Ch ch; int err = 0;
+    g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
     if (valid) {
         h.load(p.state, p.n, i);
         g.load(p.state + kHeaderWords * p.n, p.n, i);
@@ -118,15 +119,20 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
         for (int k = 0; k < G::P; k++) pay[k] = 0.f;
         if constexpr (MODE == kModeReset) {
             if (!p.reset_mask || p.reset_mask[i]) {
-                ch.begin(h.episode, kResetStep);      // a reset outside a step: t = -1 of the episode it starts
+                ch.begin_reset(h.k);                  // a reset outside a step: its own Philox domain
                 new_episode(g, ch, h);
             }
         } else if constexpr (MODE == kModeStep) {
             const int a = p.actions[i];
             if (a >= 0 && h.episode != 0 && !g.over()) {
-                ch.begin(h.episode - 1u, h.t);
+                const uint32_t word = ch.begin_step(h.k);
+                if constexpr (G::kUsesChain) {            // same draw derivation as the fused rollout
+                    uint32_t m0[G::MASK_WORDS];
+                    g.legal(m0);
+                    ch.seed_chain(word, (uint32_t)popc_words<G::MASK_WORDS>(m0));
+                }
                 g.step(a, ch, err);
-                h.t++;
+                h.t++; h.k++;
                 if (g.over()) {
                     done = true;
                     g.payoffs(pay);
@@ -170,51 +176,67 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
 
 // Fused random rollout: T env-steps per env, state in registers for the whole launch; per step the
 // warp emits one coalesced obs tile plus mask/action/player/done/payoff rows of the trajectory.
-template <class G, class Ch, class ObsT, int BLOCK>
+// ALL = every trajectory pointer is present and the obs rows of a full warp are 16-byte aligned (the
+// bench / DMC case): no per-step null checks, compile-time tile flush.
+template <class G, class Ch, class ObsT, int BLOCK, bool ALL>
 __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = BLOCK * kRowBytes;
+    if constexpr (G::kSharedBytes > 0) {                      // per-block constant tables of the game
+        G::fill_shared(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes, threadIdx.x, BLOCK);
+        __syncthreads();
+    }
     const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
     if (warp_env0 >= p.n) return;
     const size_t i = warp_env0 + lane;
     const bool valid = i < p.n;
     const int nvalid = (int)min((size_t)32, p.n - warp_env0);
-    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
     ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * G::OBS;
     ObsT *row = tile + lane * G::OBS;
     warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
     __syncwarp();
 
     G g; EnvHeader h; Ch ch; int err = 0;
+    g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
     if (valid) {
         h.load(p.state, p.n, i);
         g.load(p.state + kHeaderWords * p.n, p.n, i);
         ChanceIO<Ch>::open(ch, p, i);
-        if (h.episode == 0) { ch.begin(0u, kResetStep); new_episode(g, ch, h); }
+        if (h.episode == 0) { ch.begin_reset(h.k); new_episode(g, ch, h); }
     }
     // per-thread output cursors, advanced by one trajectory row (n envs) per step
     uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
     const size_t obs_step = p.n * (size_t)kRowBytes;
+    const bool full_warp = nvalid == 32;                      // ALL: aligned rows were checked by the launcher
     size_t rowi = i;
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         uint32_t m[G::MASK_WORDS];
         if (valid) {
-            if (p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
+            if (ALL || p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
             g.legal(m);
         }
         __syncwarp();
-        if (p.t_obs) warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        if constexpr (ALL) {
+            if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+            else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        } else {
+            if (p.t_obs) warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        }
         __syncwarp();
         if (valid) {
-            if (p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
-            if (p.t_player) __stcs(p.t_player + rowi, g.player());
+            if (ALL || p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
+            if (ALL || p.t_player) __stcs(p.t_player + rowi, g.player());
             uint32_t word;
-            if constexpr (Ch::kKind == 0) word = ChanceIO<Ch>::begin_step(ch, p, h.episode - 1u, h.t);
-            else word = policy_word_only<Ch>(p, i, h.episode - 1u, h.t);
-            const int a = pick_action<G>(m, word);
-            if (p.t_action) __stcs(p.t_action + rowi, a);
+            if constexpr (Ch::kKind == 0) word = ch.begin_step(h.k);
+            else word = policy_word_only(p, i, h.k);
+            int cnt;
+            const int a = pick_action<G>(m, word, cnt);
+            if constexpr (G::kUsesChain) ch.seed_chain(word, (uint32_t)cnt);
+            if (ALL || p.t_action) __stcs(p.t_action + rowi, a);
             g.step(a, ch, err);
-            h.t++;
+            h.t++; h.k++;
             const bool over = g.over();
             float pay[G::P];
 #pragma unroll
@@ -223,8 +245,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
                 g.payoffs(pay);
                 new_episode(g, ch, h);
             }
-            if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
-            if (p.t_payoffs) {
+            if (ALL || p.t_done) p.t_done[rowi] = over ? 1 : 0;
+            if (ALL || p.t_payoffs) {
                 if constexpr (G::P == 2) __stcs(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
                 else if constexpr (G::P == 4) __stcs(reinterpret_cast<float4 *>(p.t_payoffs) + rowi, make_float4(pay[0], pay[1], pay[2], pay[3]));
                 else {
@@ -250,7 +272,10 @@ template <class G, class Ch, class ObsT>
 cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
     constexpr int BLOCK = 64;
     const unsigned grid = (unsigned)((p.n + BLOCK - 1) / BLOCK);
-    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT);
+    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT) + ((G::kSharedBytes + 15) & ~15);
+    // rollout fast path: every trajectory stream requested and obs rows of a full warp 16-byte aligned
+    const bool all = op == kOpRollout && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
+                     ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * G::OBS * sizeof(ObsT))) & 15u) == 0;
     cudaError_t e = cudaSuccess;
 #define RLC_LAUNCH(KERNEL)                                                                           \
     do {                                                                                             \
@@ -261,7 +286,10 @@ cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
     case kOpReset: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeReset, BLOCK>)); break;
     case kOpStep: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeStep, BLOCK>)); break;
     case kOpObserve: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
-    case kOpRollout: RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK>)); break;
+    case kOpRollout:
+        if (all) RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK, true>));
+        else RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK, false>));
+        break;
     default: e = cudaErrorInvalidValue;
     }
 #undef RLC_LAUNCH

@@ -26,7 +26,8 @@ struct WarpChance {
         return __shfl_sync(kFull, v, 0);
     }
     __device__ __forceinline__ void skip_fy(int a, int b) { if (lane == 0) ch.skip_fy(a, b); }
-    __device__ __forceinline__ void begin(uint32_t e, uint32_t t) { if (lane == 0) ch.begin(e, t); }
+    __device__ __forceinline__ void begin_step(uint32_t k) { if (lane == 0) (void)ch.begin_step(k); }
+    __device__ __forceinline__ void begin_reset(uint32_t k) { if (lane == 0) ch.begin_reset(k); }
     __device__ __forceinline__ int err() { return __shfl_sync(kFull, ch.err, 0); }
 };
 template <class Ch>
@@ -39,11 +40,11 @@ __device__ __forceinline__ void wchance_close(WarpChance<Ch> &w, const KParams &
     if (w.lane == 0) ChanceIO<Ch>::close(w.ch, p, env);
 }
 template <class Ch>
-__device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch> &w, const KParams &p, size_t env, uint32_t episode, uint32_t t) {
+__device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch> &w, const KParams &p, size_t env, uint32_t k) {
     uint32_t word = 0;
     if (w.lane == 0) {
-        if constexpr (Ch::kKind == 0) { w.ch.begin(episode, t); word = w.ch.policy_word(); }
-        else word = policy_word_only<Ch>(p, env, episode, t);
+        if constexpr (Ch::kKind == 0) word = w.ch.begin_step(k);
+        else word = policy_word_only(p, env, k);
     }
     return __shfl_sync(kFull, word, 0);
 }
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
     __syncwarp();
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
-    EnvHeader h; h.episode = row[0]; h.t = row[1];
+    EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
     G g; g.bind(p); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0; bool done = false;
@@ -124,18 +125,18 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
 
     if constexpr (MODE == kModeReset) {
         if (!p.reset_mask || p.reset_mask[env]) {
-            ch.begin(h.episode, kResetStep);
+            ch.begin_reset(h.k);
             h.episode++; h.t = 0;
             g.reset(ch, scratch, lane);
         }
     } else if constexpr (MODE == kModeStep) {
         const int a = p.actions[env];
         if (a >= 0 && h.episode != 0 && !g.over()) {
-            ch.begin(h.episode - 1u, h.t);
+            ch.begin_step(h.k);
             g.legal(smask, lane);                        // the step validates against the current legal set
             __syncwarp();
             g.step(a, ch, smask, scratch, lane, err);
-            h.t++;
+            h.t++; h.k++;
             if (g.over()) {
                 done = true;
                 g.payoffs(pay);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
     }
     if constexpr (MODE != kModeObserve) {
         wchance_close(ch, p, env);
-        if (lane == 0) { row[0] = h.episode; row[1] = h.t; }
+        if (lane == 0) { row[0] = h.episode; row[1] = h.t; row[2] = h.k; }
         g.store(row + kHeaderWords, lane);
     }
     err |= ch.err();
@@ -198,11 +199,11 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
     __syncwarp();
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
-    EnvHeader h; h.episode = row[0]; h.t = row[1];
+    EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
     G g; g.bind(p); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0;
-    if (h.episode == 0) { ch.begin(0u, kResetStep); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
+    if (h.episode == 0) { ch.begin_reset(h.k); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
     __syncwarp();
     g.legal(smask, lane);
     __syncwarp();
@@ -214,14 +215,14 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
             warp_flush_row<G, ObsT>(p.t_obs, rowi, srow, lane);
         }
         if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
-        const uint32_t word = wpolicy_word(ch, p, env, h.episode - 1u, h.t);
+        const uint32_t word = wpolicy_word(ch, p, env, h.k);
         const int cnt = warp_popc_words(smask, G::MASK_WORDS, lane);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
         const int a = warp_kth_set_bit(smask, G::MASK_WORDS, k, lane);
         const int pl = g.player();
         __syncwarp();
         g.step(a, ch, smask, scratch, lane, err);
-        h.t++;
+        h.t++; h.k++;
         const bool over = g.over();
         float pay[G::P];
 #pragma unroll
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
         }
     }
     wchance_close(ch, p, env);
-    if (lane == 0) { row[0] = h.episode; row[1] = h.t; }
+    if (lane == 0) { row[0] = h.episode; row[1] = h.t; row[2] = h.k; }
     g.store(row + kHeaderWords, lane);
     err |= ch.err();
     if (err && p.err && lane == 0) p.err[env] |= err;
