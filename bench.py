@@ -154,7 +154,9 @@ def main():
     ap.add_argument('--rollout-len', type=int, default=128, help='env-steps per env per launch (T)')
     ap.add_argument('--obs-dtype', default=None, choices=['uint8', 'float32'])
     ap.add_argument('--seed', type=int, default=20261018)
-    ap.add_argument('--e2e-steps', type=int, default=200)
+    ap.add_argument('--e2e-steps', type=int, default=10, help='bench steps (T-step host rollouts) of the e2e leg')
+    ap.add_argument('--e2e-chunk', type=int, default=16, help='env-steps per rlc_rollout_random launch in the e2e leg')
+    ap.add_argument('--e2e-step-api-steps', type=int, default=100, help='env-steps of the per-step host-agent leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.envs is None:
@@ -230,13 +232,48 @@ def main():
     elapsed_ms = float(t.item())
     value = world * E * T * K / (elapsed_ms * 1e-3)
 
-    # ---- end to end through the public API with HOST buffers: a host-resident agent picks a uniform legal
-    # action from the mask it received (numpy), actions go H2D from pinned memory, Env.step runs, and obs /
-    # mask / player / done / payoffs come back D2H into pinned memory, every step.
+    # ---- end to end through the public API with HOST buffers (VecEnv.rollout_random_host): every bench step
+    # uploads the packed env state from pinned host memory, runs the same T-step random rollout in chunks and
+    # streams the whole trajectory (obs + mask + action + player + done + payoffs) into pinned host memory
+    # (chunk c copies D2H on a second stream while chunk c+1 is simulated), then reads the state back.
     e2e = None
-    if info.num_actions == 4 and args.e2e_steps > 0:
+    if args.e2e_steps > 0:
         Ke = args.e2e_steps
         env2 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 1, env_id_base=rank * E, obs_dtype=odt)
+        env2.reset()
+        h_traj = env2.alloc_host_trajectory(T)
+        h_state = torch.empty(env2.state.shape, dtype=env2.state.dtype).pin_memory()
+        h_state.copy_(env2.state)
+        torch.cuda.synchronize(dev)
+        for _ in range(min(W, 3)):
+            env2.rollout_random_host(T, h_traj, chunk=args.e2e_chunk, host_state=h_state)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            env2.rollout_random_host(T, h_traj, chunk=args.e2e_chunk, host_state=h_state)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        state_bytes = h_state.numel() * h_state.element_size()
+        d2h = sum(x.numel() * x.element_size() for x in h_traj.values()) + state_bytes
+        e2e = {'value': world * E * T * Ke / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': state_bytes,
+               'd2h_bytes_per_step': d2h, 'steps': Ke, 'ms_per_step': 1e3 * float(dt.item()) / Ke,
+               'pcie_gbs': (d2h + state_bytes) * Ke / float(dt.item()) / 1e9,
+               'what': 'VecEnv.rollout_random_host: H2D packed state (pinned) -> %d-step chunks of rlc_rollout_random -> D2H of '
+                       'the full trajectory into pinned host memory overlapped on a copy stream -> D2H state; host wall '
+                       'clock, max over ranks' % args.e2e_chunk}
+        env2.check_errors()
+        done_h = h_traj['done'].numpy()
+        assert done_h.any(), 'e2e trajectory did not reach the host'
+        del h_traj, env2
+
+    # ---- secondary: the per-step API driven by a host-resident agent (numpy uniform-legal policy), one
+    # synchronous H2D(actions) -> rlc_step -> D2H(obs, mask, player, done, payoffs) round trip per env-step
+    e2e_step = None
+    if info.num_actions == 4 and args.e2e_step_api_steps > 0:
+        Ke = args.e2e_step_api_steps
+        env2 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 2, env_id_base=rank * E, obs_dtype=odt)
         h_act = torch.zeros(E, dtype=torch.int32).pin_memory()
         h_obs = torch.zeros((E, info.obs_stride), dtype=odt).pin_memory()
         h_mask = torch.zeros((E, 4), dtype=torch.uint8).pin_memory()
@@ -277,10 +314,10 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         d2h = sum(x.numel() * x.element_size() for x in (h_obs, h_mask, h_cur, h_done, h_pay))
-        e2e = {'value': world * E * Ke / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h_act.numel() * 4,
-               'd2h_bytes_per_step': d2h, 'steps': Ke,
-               'what': 'VecEnv.step per env-step: numpy uniform-legal policy on host -> H2D actions (pinned) -> '
-                       'rlc_step -> D2H obs+mask+player+done+payoffs (pinned), synchronous round trip'}
+        e2e_step = {'value': world * E * Ke / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h_act.numel() * 4,
+                    'd2h_bytes_per_step': d2h, 'steps': Ke,
+                    'what': 'VecEnv.step per env-step: numpy uniform-legal policy on host -> H2D actions (pinned) -> '
+                            'rlc_step -> D2H obs+mask+player+done+payoffs (pinned), synchronous round trip'}
         env2.check_errors()
 
     if rank != 0:
@@ -306,7 +343,7 @@ def main():
         'config': {'workload': '%s, %d envs per GPU, obs %s[%d] + legal mask u8[%d] + action/player/done/payoffs per '
                                'env-step' % (args.game, E, args.obs_dtype, info.obs_stride, info.num_actions),
                    'envs_per_gpu': E, 'env_steps_per_launch_per_env': T, 'policy': 'uniform-random legal (Philox, on device)',
-                   'chance': 'Philox4x32-10 keyed (seed, global env id, episode)', 'auto_reset': True,
+                   'chance': 'Philox4x32-10 keyed (seed, global env id, env-step index)', 'auto_reset': True,
                    'l2': 'trajectory written per launch = %.0f MB > 126 MB L2' % (E * T * per_step / 1e6)},
         'gpu_launches': int(launches),
         'clocks': clocks,
@@ -318,6 +355,8 @@ def main():
     }
     if e2e:
         line['e2e'] = e2e
+    if e2e_step:
+        line['e2e_step_api'] = e2e_step
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, dt, steps, n = cpu_port_run(args.game, E, T, args.seed, threads)

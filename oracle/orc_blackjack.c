@@ -35,7 +35,10 @@ static void bj_create(void *s) { (void)s; }
 static int bj_reset(void *s, orc_chance *ch) {
     bj_t *g = (bj_t *)s;
     for (int i = 0; i < 52; i++) g->deck[i] = (uint8_t)i;
-    orc_shuffle_u8(ch, g->deck, 52); g->deck_len = 52;
+    /* throughput (Philox) spec: deal_card() already draws a uniform index into the remaining deck, so the
+     * shuffle adds nothing to the distribution and is not drawn; the deck stays in id order */
+    if (ch->kind != ORC_CHANCE_PHILOX) orc_shuffle_u8(ch, g->deck, 52);
+    g->deck_len = 52;
     g->np_ = g->nd = 0;
     for (int i = 0; i < 2; i++) { bj_deal(g, ch, g->phand, &g->np_); bj_deal(g, ch, g->dhand, &g->nd); }
     g->p_score = bj_score(g->phand, g->np_); g->p_bust = g->p_score > 21;

@@ -30,17 +30,34 @@ static int uno_init_deck(ucard *d) {
     }
     return n;
 }
+/* Throughput (Philox) spec, shared with the CUDA kernels: the order of the draw pile is only
+ * ever observed through pop(), so "shuffle, then pop" is replaced by "pop a uniformly random remaining
+ * card": shuffles draw nothing, and a pop draws r = below(pile size) and takes the card whose code
+ * (15*original colour + trait) contains position r in ascending-code order.  Cards of one code are
+ * interchangeable (a wild's mutable colour is never read while it is in a pile or a hand). */
 static void uno_shuffle(orc_chance *ch, ucard *x, int n) {              /* dealer.py:14-17 */
+    if (ch->kind == ORC_CHANCE_PHILOX) return;
     for (int i = n - 1; i >= 1; i--) { uint32_t j = orc_below(ch, (uint32_t)i + 1u); ucard t = x[i]; x[i] = x[j]; x[j] = t; }
 }
-static int uno_pop(uno_t *g, ucard *out) {                              /* deck.pop(); Q-UNO4: empty -> flag, not emulated */
+static int uno_pop(uno_t *g, orc_chance *ch, ucard *out) {              /* deck.pop(); Q-UNO4: empty -> flag, not emulated */
     if (g->dl <= 0) { g->err |= 8; return 0; }
+    if (ch->kind == ORC_CHANCE_PHILOX) {
+        int cnt[60], r = (int)orc_below(ch, (uint32_t)g->dl), code = 0;
+        memset(cnt, 0, sizeof cnt);
+        for (int i = 0; i < g->dl; i++) cnt[g->deck[i].code]++;
+        while (r >= cnt[code]) { r -= cnt[code]; code++; }
+        int at = 0;
+        while (g->deck[at].code != code) at++;
+        *out = g->deck[at];
+        g->deck[at] = g->deck[--g->dl];
+        return 1;
+    }
     *out = g->deck[--g->dl];
     return 1;
 }
-static void uno_deal(uno_t *g, int p, int num) {                        /* dealer.py:19-26 */
+static void uno_deal(uno_t *g, orc_chance *ch, int p, int num) {        /* dealer.py:19-26 */
     ucard c;
-    for (int k = 0; k < num; k++) if (uno_pop(g, &c)) g->hand[p][g->hl[p]++] = c;
+    for (int k = 0; k < num; k++) if (uno_pop(g, ch, &c)) g->hand[p][g->hl[p]++] = c;
 }
 static void uno_replace_deck(uno_t *g, orc_chance *ch) {                /* round.py:155-160 */
     for (int k = 0; k < g->pl; k++) g->deck[g->dl++] = g->played[k];
@@ -54,15 +71,16 @@ static int uno_reset(void *s, orc_chance *ch) {
     memset(g, 0, sizeof *g);
     g->dl = uno_init_deck(g->deck);
     uno_shuffle(ch, g->deck, g->dl);
-    uno_deal(g, 0, 7); uno_deal(g, 1, 7);
+    uno_deal(g, ch, 0, 7); uno_deal(g, ch, 1, 7);
     g->direction = 1; g->current = 0; g->winner = -1;
-    ucard top = g->deck[--g->dl];
-    while (TRAIT(top) == 14) { g->deck[g->dl++] = top; uno_shuffle(ch, g->deck, g->dl); top = g->deck[--g->dl]; }
+    ucard top;
+    uno_pop(g, ch, &top);
+    while (TRAIT(top) == 14) { g->deck[g->dl++] = top; uno_shuffle(ch, g->deck, g->dl); uno_pop(g, ch, &top); }
     if (TRAIT(top) == 13) top.color = (uint8_t)orc_below(ch, 4);
     g->target = top; g->played[g->pl++] = top;
     if (TRAIT(top) == 10) g->current = 1;
     else if (TRAIT(top) == 11) { g->direction = -1; g->current = 1; }
-    else if (TRAIT(top) == 12) uno_deal(g, g->current, 2);
+    else if (TRAIT(top) == 12) uno_deal(g, ch, g->current, 2);
     return g->current;
 }
 /* round.py:194-227 */
@@ -73,7 +91,7 @@ static void uno_non_number(uno_t *g, orc_chance *ch, ucard card) {
     else if (t == 12 || t == 14) {
         int need = t == 12 ? 2 : 4;
         if (g->dl < need) uno_replace_deck(g, ch);
-        uno_deal(g, ((current + direction) % 2 + 2) % 2, need);
+        uno_deal(g, ch, ((current + direction) % 2 + 2) % 2, need);
         current = ((current + direction) % 2 + 2) % 2;
     }
     g->current = ((current + g->direction) % 2 + 2) % 2;
@@ -99,7 +117,7 @@ static uint64_t uno_legal_bits(const uno_t *g) {
 static void uno_draw(uno_t *g, orc_chance *ch) {
     ucard card;
     if (g->dl == 0) uno_replace_deck(g, ch);
-    if (!uno_pop(g, &card)) { g->current ^= 1; return; }
+    if (!uno_pop(g, ch, &card)) { g->current ^= 1; return; }
     if (is_wild_type(card)) {
         card.color = (uint8_t)orc_below(ch, 4);
         g->target = card; g->played[g->pl++] = card; g->current = ((g->current + g->direction) % 2 + 2) % 2;

@@ -8,7 +8,10 @@ namespace rlc {
 
 // w0: p_sum [0:7) p_aces [7:10) d_first [10:16) d_vis_sum [16:23) d_vis_aces [23:26) winner [26:28)
 //     (0 ongoing, 1 tie, 2 win, 3 lose; judger.py:25-52) | deck_len [28:32) is too small -> w1
-// w1: deck_len;  w2..w14: deck bytes
+// w1: deck_len;  w2..w14: deck bytes (replay modes)
+// Throughput (Philox) mode: the shuffle is not drawn (deal_card picks a uniform index of the remaining
+// deck anyway), so the deck stays in id order and is a 52-bit membership mask in w2,w3; the idx-th
+// remaining card is the idx-th set bit.
 struct Blackjack {
     static constexpr int kGameId = 0, P = 1, A = 2, OBS = 2, GAME_WORDS = 15, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
@@ -16,35 +19,51 @@ struct Blackjack {
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
     __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     static constexpr int kMaxResetDraws = 55;
+    static constexpr bool kChanceAwareState = true;   // load_k/store_k<chance kind>
     int p_sum, p_aces, d_first, d_vis_sum, d_vis_aces, winner, deck_len;
     uint8_t deck[52];
+    uint32_t mlo, mhi;
 
-    __device__ void load(const uint32_t *st, size_t n, size_t i) {
+    template <int KIND> __device__ void load_k(const uint32_t *st, size_t n, size_t i) {
         const uint32_t w = st[i];
         p_sum = bf_get(w, 0, 7); p_aces = bf_get(w, 7, 3); d_first = bf_get(w, 10, 6); d_vis_sum = bf_get(w, 16, 7);
         d_vis_aces = bf_get(w, 23, 3); winner = bf_get(w, 26, 2); deck_len = (int)st[n + i];
+        if constexpr (KIND == 0) { mlo = st[2 * n + i]; mhi = st[3 * n + i]; }
+        else {
 #pragma unroll
-        for (int k = 0; k < 13; k++) {
-            const uint32_t v = st[(size_t)(2 + k) * n + i];
-            deck[4 * k] = v & 255u; deck[4 * k + 1] = (v >> 8) & 255u; deck[4 * k + 2] = (v >> 16) & 255u; deck[4 * k + 3] = v >> 24;
+            for (int k = 0; k < 13; k++) {
+                const uint32_t v = st[(size_t)(2 + k) * n + i];
+                deck[4 * k] = v & 255u; deck[4 * k + 1] = (v >> 8) & 255u; deck[4 * k + 2] = (v >> 16) & 255u; deck[4 * k + 3] = v >> 24;
+            }
         }
     }
-    __device__ void store(uint32_t *st, size_t n, size_t i) const {
+    template <int KIND> __device__ void store_k(uint32_t *st, size_t n, size_t i) const {
         st[i] = p_sum | (p_aces << 7) | (d_first << 10) | (d_vis_sum << 16) | (d_vis_aces << 23) | (winner << 26);
         st[n + i] = (uint32_t)deck_len;
+        if constexpr (KIND == 0) { st[2 * n + i] = mlo; st[3 * n + i] = mhi; }
+        else {
 #pragma unroll
-        for (int k = 0; k < 13; k++)
-            st[(size_t)(2 + k) * n + i] = deck[4 * k] | (deck[4 * k + 1] << 8) | (deck[4 * k + 2] << 16) | ((uint32_t)deck[4 * k + 3] << 24);
+            for (int k = 0; k < 13; k++)
+                st[(size_t)(2 + k) * n + i] = deck[4 * k] | (deck[4 * k + 1] << 8) | (deck[4 * k + 2] << 16) | ((uint32_t)deck[4 * k + 3] << 24);
+        }
     }
     // judger.py:54-73: A=11, T/J/Q/K=10; card id = 13*suit + rank (A=0, 2..9, T, J, Q, K)
     __device__ static __forceinline__ int card_score(int c) { const int r = c % 13; return r == 0 ? 11 : (r >= 9 ? 10 : r + 1); }
     __device__ static __forceinline__ int soft(int sum, int aces) { while (sum > 21 && aces > 0) { aces--; sum -= 10; } return sum; }
     template <class Ch> __device__ int deal(Ch &ch) {            // dealer.py:26-37
         const int idx = (int)ch.below((uint32_t)deck_len);
-        const int c = deck[idx];
-        for (int k = idx; k + 1 < deck_len; k++) deck[k] = deck[k + 1];
         deck_len--;
-        return c;
+        if constexpr (Ch::kKind == 0) {                          // idx-th remaining card of the id-ordered deck
+            const int nlo = __popc(mlo);
+            int c;
+            if (idx < nlo) { c = (int)__fns(mlo, 0, idx + 1); mlo &= ~(1u << c); }
+            else { const int b = (int)__fns(mhi, 0, idx - nlo + 1); mhi &= ~(1u << b); c = 32 + b; }
+            return c;
+        } else {
+            const int c = deck[idx];
+            for (int k = idx; k < deck_len; k++) deck[k] = deck[k + 1];
+            return c;
+        }
     }
     __device__ __forceinline__ int p_score() const { return soft(p_sum, p_aces); }
     __device__ __forceinline__ int d_score() const {
@@ -54,8 +73,11 @@ struct Blackjack {
     __device__ __forceinline__ void add_d(int c) { d_vis_sum += card_score(c); d_vis_aces += (c % 13 == 0); }
     // game.py:22-54, dealer.py:6-24
     template <class Ch> __device__ void reset(Ch &ch) {
-        for (int i = 0; i < 52; i++) deck[i] = (uint8_t)i;
-        shuffle_tail_u8(ch, deck, 52, 52);
+        if constexpr (Ch::kKind == 0) { mlo = 0xffffffffu; mhi = 0xfffffu; }   // shuffle not drawn (see header)
+        else {
+            for (int i = 0; i < 52; i++) deck[i] = (uint8_t)i;
+            shuffle_tail_u8(ch, deck, 52, 52);
+        }
         deck_len = 52;
         p_sum = p_aces = d_vis_sum = d_vis_aces = 0; winner = 0;
         add_p(deal(ch)); d_first = deal(ch); add_p(deal(ch)); add_d(deal(ch));

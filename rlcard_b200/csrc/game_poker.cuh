@@ -61,6 +61,7 @@ struct Leduc {
     static constexpr int kGameId = 1, P = 2, A = 4, OBS = 36, GAME_WORDS = 1, MASK_WORDS = 1;
     static constexpr bool kUsesChain = true;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 6;
+    static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 128;   // deal table: x in [0,120) -> hand0 | hand1 << 2 | public << 4
     int hand0, hand1, pub, pub_dealt, chips0, chips1, rc, fold0, fold1;
     BetRound r;
@@ -212,6 +213,7 @@ struct Limit {
     static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 52;
+    static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
     __device__ __forceinline__ void bind_shared(const uint8_t *) {}

@@ -14,109 +14,201 @@
 //   [32..35] seat 1 counters                            [36] seat 1 wild lists
 //   [37] dl[0:7) pl[7:14) target code[14:20) target colour[20:22) direction[22] current[23] winner+1[24:26) err8[26]
 // wild list word: wild: count[0:3) entries[3:11) ; wild_draw_4: count[11:14) entries[14:22)
+//
+// BAG = true (throughput / Philox mode): the order of the draw pile is observable only through pop(), so
+// "shuffle, then pop" is replaced by "pop a uniformly random remaining card": draw pile and played pile
+// become multisets (2-bit counters per card code, one word per colour), shuffles draw nothing, a pop is
+// r = below(pile size) resolved by cumulative counts in ascending code order.  Same distribution as the
+// reference, ~20x fewer draws per episode and no per-thread card array.  Game words (19): [0..3] draw
+// pile counters  [4..7] played pile counters  [8..11] seat 0 counters  [12] seat 0 wild lists  [13..16]
+// seat 1 counters  [17] seat 1 wild lists  [18] meta (as word 37 above).
 #pragma once
 #include "common.cuh"
 
 namespace rlc {
 
-struct Uno {
-    static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = 38, MASK_WORDS = 2;
+template <bool BAG>
+struct UnoT {
+    static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = BAG ? 19 : 38, MASK_WORDS = 2;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
+    static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
     __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     static constexpr int kMaxResetDraws = 256;
-    uint8_t cards[108];
+    uint8_t cards[BAG ? 1 : 108];
+    uint32_t dk[4], pk[4];                         // BAG: draw / played pile counters (13 x 2 bits + wild, wd4 per colour)
     uint32_t hc[2][4], hw[2];
     int dl, pl, tcode, tcolor, dir, cur, winner;   // dir: 0 = +1, 1 = -1 ; winner: -1 none
 
+    static constexpr int kBase = BAG ? 8 : 27;     // first hand word
     __device__ void load(const uint32_t *st, size_t n, size_t i) {
+        if constexpr (BAG) {
 #pragma unroll
-        for (int k = 0; k < 27; k++) {
-            const uint32_t v = st[(size_t)k * n + i];
-            cards[4 * k] = v & 255u; cards[4 * k + 1] = (v >> 8) & 255u; cards[4 * k + 2] = (v >> 16) & 255u; cards[4 * k + 3] = v >> 24;
+            for (int c = 0; c < 4; c++) { dk[c] = st[(size_t)c * n + i]; pk[c] = st[(size_t)(4 + c) * n + i]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 27; k++) {
+                const uint32_t v = st[(size_t)k * n + i];
+                cards[4 * k] = v & 255u; cards[4 * k + 1] = (v >> 8) & 255u; cards[4 * k + 2] = (v >> 16) & 255u; cards[4 * k + 3] = v >> 24;
+            }
         }
 #pragma unroll
         for (int p = 0; p < 2; p++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) hc[p][c] = st[(size_t)(27 + 5 * p + c) * n + i];
-            hw[p] = st[(size_t)(31 + 5 * p) * n + i];
+            for (int c = 0; c < 4; c++) hc[p][c] = st[(size_t)(kBase + 5 * p + c) * n + i];
+            hw[p] = st[(size_t)(kBase + 4 + 5 * p) * n + i];
         }
-        const uint32_t m = st[(size_t)37 * n + i];
+        const uint32_t m = st[(size_t)(kBase + 10) * n + i];
         dl = bf_get(m, 0, 7); pl = bf_get(m, 7, 7); tcode = bf_get(m, 14, 6); tcolor = bf_get(m, 20, 2);
         dir = bf_get(m, 22, 1); cur = bf_get(m, 23, 1); winner = (int)bf_get(m, 24, 2) - 1;
     }
     __device__ void store(uint32_t *st, size_t n, size_t i) const {
+        if constexpr (BAG) {
 #pragma unroll
-        for (int k = 0; k < 27; k++)
-            st[(size_t)k * n + i] = cards[4 * k] | (cards[4 * k + 1] << 8) | (cards[4 * k + 2] << 16) | ((uint32_t)cards[4 * k + 3] << 24);
+            for (int c = 0; c < 4; c++) { st[(size_t)c * n + i] = dk[c]; st[(size_t)(4 + c) * n + i] = pk[c]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 27; k++)
+                st[(size_t)k * n + i] = cards[4 * k] | (cards[4 * k + 1] << 8) | (cards[4 * k + 2] << 16) | ((uint32_t)cards[4 * k + 3] << 24);
+        }
 #pragma unroll
         for (int p = 0; p < 2; p++) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) st[(size_t)(27 + 5 * p + c) * n + i] = hc[p][c];
-            st[(size_t)(31 + 5 * p) * n + i] = hw[p];
+            for (int c = 0; c < 4; c++) st[(size_t)(kBase + 5 * p + c) * n + i] = hc[p][c];
+            st[(size_t)(kBase + 4 + 5 * p) * n + i] = hw[p];
         }
-        st[(size_t)37 * n + i] = dl | (pl << 7) | (tcode << 14) | (tcolor << 20) | (dir << 22) | (cur << 23) | ((winner + 1) << 24);
+        st[(size_t)(kBase + 10) * n + i] = dl | (pl << 7) | (tcode << 14) | (tcolor << 20) | (dir << 22) | (cur << 23) | ((winner + 1) << 24);
     }
 
     // ---- list primitives
-    __device__ __forceinline__ int pop_deck(int &err) { if (dl <= 0) { err |= 8; return -1; } return cards[--dl]; }   // Q-UNO4
-    __device__ __forceinline__ void push_played(int code) { cards[107 - pl] = (uint8_t)code; pl++; }
+    // sum of the fifteen 2-bit counters of one colour word
+    static __device__ __forceinline__ int sum2(uint32_t w) {
+        uint32_t s = (w & 0x33333333u) + ((w >> 2) & 0x33333333u);
+        s = (s + (s >> 4)) & 0x0f0f0f0fu;
+        return (int)((s * 0x01010101u) >> 24);
+    }
+    template <class Ch> __device__ __forceinline__ int pop_deck(Ch &ch, int &err) {   // deck.pop(); Q-UNO4: empty -> flag
+        if (dl <= 0) { err |= 8; return -1; }
+        if constexpr (BAG) {                                             // uniformly random remaining card
+            int r = (int)ch.below((uint32_t)dl);
+            dl--;
+            int c = 0;
+            uint32_t w = dk[0];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int s = sum2(w);
+                const bool next = (c == k) && r >= s;
+                r = next ? r - s : r; c = next ? k + 1 : c; w = next ? dk[k + 1] : w;
+            }
+            int t = 0; bool found = false;
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                const int cnt = (int)((w >> (2 * k)) & 3u);
+                const bool here = !found && r < cnt;
+                t = here ? k : t; found = found || here; r = (found ? r : r - cnt);
+            }
+            const uint32_t dec = 1u << (2 * t);
+            dk[0] -= c == 0 ? dec : 0u; dk[1] -= c == 1 ? dec : 0u; dk[2] -= c == 2 ? dec : 0u; dk[3] -= c == 3 ? dec : 0u;
+            return 15 * c + t;
+        } else { (void)ch; return cards[--dl]; }
+    }
+    __device__ __forceinline__ void unpop_deck(int code) {               // dealer.py:33-37 deck.append(top)
+        if constexpr (BAG) {
+            const int c = code / 15, t = code - 15 * c;
+            const uint32_t inc = 1u << (2 * t);
+            dk[0] += c == 0 ? inc : 0u; dk[1] += c == 1 ? inc : 0u; dk[2] += c == 2 ? inc : 0u; dk[3] += c == 3 ? inc : 0u;
+            dl++;
+        } else cards[dl++] = (uint8_t)code;
+    }
+    __device__ __forceinline__ void push_played(int code) {
+        if constexpr (BAG) {
+            const int c = code / 15, t = code - 15 * c;
+            const uint32_t inc = 1u << (2 * t);
+            pk[0] += c == 0 ? inc : 0u; pk[1] += c == 1 ? inc : 0u; pk[2] += c == 2 ? inc : 0u; pk[3] += c == 3 ? inc : 0u;
+        } else cards[107 - pl] = (uint8_t)code;
+        pl++;
+    }
     __device__ __forceinline__ void to_hand(int p, int code) {
         const int c = code / 15, t = code - 15 * c;
-        if (t < 13) hc[p][c] += 1u << (2 * t);
+        if (t < 13) hc_add(p, c, 1u << (2 * t));
         else {
             const int base = t == 13 ? 0 : 11;
-            const int cnt = (hw[p] >> base) & 7;
-            hw[p] = (hw[p] & ~(3u << (base + 3 + 2 * cnt))) | ((uint32_t)c << (base + 3 + 2 * cnt));
-            hw[p] += 1u << base;
+            uint32_t w = hwp(p);
+            const int cnt = (w >> base) & 7;
+            w = (w & ~(3u << (base + 3 + 2 * cnt))) | ((uint32_t)c << (base + 3 + 2 * cnt));
+            set_hw(p, w + (1u << base));
         }
     }
-    __device__ __forceinline__ int wild_count(int p, int t) const { return (hw[p] >> (t == 13 ? 0 : 11)) & 7; }
+    // register-friendly accessors (no dynamically indexed arrays -> no local memory)
+    __device__ __forceinline__ uint32_t hcp(int p, int c_static) const { return p ? hc[1][c_static] : hc[0][c_static]; }
+    __device__ __forceinline__ uint32_t hwp(int p) const { return p ? hw[1] : hw[0]; }
+    __device__ __forceinline__ void set_hw(int p, uint32_t v) { hw[0] = p ? hw[0] : v; hw[1] = p ? v : hw[1]; }
+    __device__ __forceinline__ void hc_add(int p, int c, uint32_t delta) {
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) hc[q][k] += (q == p && k == c) ? delta : 0u;
+    }
+    __device__ __forceinline__ int wild_count(int p, int t) const { return (hwp(p) >> (t == 13 ? 0 : 11)) & 7; }
     __device__ __forceinline__ int take_first_wild(int p, int t) {        // original colour of the first held wild of trait t
         const int base = t == 13 ? 0 : 11;
-        const uint32_t field = (hw[p] >> base) & 0x7ffu;
+        const uint32_t field = (hwp(p) >> base) & 0x7ffu;
         const int cnt = field & 7, first = (field >> 3) & 3;
         const uint32_t rest = ((field >> 5) << 3) | (uint32_t)(cnt - 1);  // drop entry 0, count - 1
-        hw[p] = (hw[p] & ~(0x7ffu << base)) | ((rest & 0x7ffu) << base);
+        set_hw(p, (hwp(p) & ~(0x7ffu << base)) | ((rest & 0x7ffu) << base));
         return first;
     }
-    __device__ __forceinline__ bool hand_empty(int p) const { return (hc[p][0] | hc[p][1] | hc[p][2] | hc[p][3]) == 0 && (hw[p] & 0x3807u) == 0; }
-    template <class Ch> __device__ void shuffle_deck(Ch &ch) { shuffle_tail_u8(ch, cards, dl, dl); }   // dealer.py:14-17
-    template <class Ch> __device__ void replace_deck(Ch &ch) {            // round.py:155-160
-        uint8_t tmp[108];
-        for (int k = 0; k < pl; k++) tmp[k] = cards[107 - k];
-        for (int k = 0; k < pl; k++) cards[dl + k] = tmp[k];
-        dl += pl; pl = 0;
-        shuffle_deck(ch);
+    __device__ __forceinline__ bool hand_empty(int p) const { return (hcp(p, 0) | hcp(p, 1) | hcp(p, 2) | hcp(p, 3)) == 0 && (hwp(p) & 0x3807u) == 0; }
+    template <class Ch> __device__ void shuffle_deck(Ch &ch) {           // dealer.py:14-17 (BAG: nothing to draw)
+        if constexpr (!BAG) shuffle_tail_u8(ch, cards, dl, dl);
     }
-    __device__ __forceinline__ void deal(int p, int num, int &err) {      // dealer.py:19-26
-        for (int k = 0; k < num; k++) { const int c = pop_deck(err); if (c >= 0) to_hand(p, c); }
+    template <class Ch> __device__ void replace_deck(Ch &ch) {            // round.py:155-160
+        if constexpr (BAG) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) { dk[c] += pk[c]; pk[c] = 0; }
+            dl += pl; pl = 0;
+        } else {
+            uint8_t tmp[108];
+            for (int k = 0; k < pl; k++) tmp[k] = cards[107 - k];
+            for (int k = 0; k < pl; k++) cards[dl + k] = tmp[k];
+            dl += pl; pl = 0;
+            shuffle_deck(ch);
+        }
+    }
+    template <class Ch> __device__ __forceinline__ void deal(int p, int num, Ch &ch, int &err) {   // dealer.py:19-26
+        for (int k = 0; k < num; k++) { const int c = pop_deck(ch, err); if (c >= 0) to_hand(p, c); }
     }
 
     // games/uno/game.py:22-56, round.py:24-52, dealer.py:28-39, utils.py:31-52 (deck order)
     template <class Ch> __device__ void reset(Ch &ch) {
-        int n = 0, err = 0;
-        for (int c = 0; c < 4; c++) {
-            for (int t = 0; t < 10; t++) { cards[n++] = (uint8_t)(15 * c + t); if (t) cards[n++] = (uint8_t)(15 * c + t); }
-            for (int t = 10; t < 13; t++) { cards[n++] = (uint8_t)(15 * c + t); cards[n++] = (uint8_t)(15 * c + t); }
-            cards[n++] = (uint8_t)(15 * c + 13); cards[n++] = (uint8_t)(15 * c + 14);
+        int err = 0;
+        if constexpr (BAG) {                                   // one 0, two of 1..9 / skip / reverse / draw_2, one wild, one wd4
+#pragma unroll
+            for (int c = 0; c < 4; c++) { dk[c] = 0x16AAAAA9u; pk[c] = 0; }
+        } else {
+            int n = 0;
+            for (int c = 0; c < 4; c++) {
+                for (int t = 0; t < 10; t++) { cards[n++] = (uint8_t)(15 * c + t); if (t) cards[n++] = (uint8_t)(15 * c + t); }
+                for (int t = 10; t < 13; t++) { cards[n++] = (uint8_t)(15 * c + t); cards[n++] = (uint8_t)(15 * c + t); }
+                cards[n++] = (uint8_t)(15 * c + 13); cards[n++] = (uint8_t)(15 * c + 14);
+            }
         }
         dl = 108; pl = 0;
 #pragma unroll
         for (int p = 0; p < 2; p++) { hc[p][0] = hc[p][1] = hc[p][2] = hc[p][3] = 0; hw[p] = 0; }
         shuffle_deck(ch);
-        deal(0, 7, err); deal(1, 7, err);
+        deal(0, 7, ch, err); deal(1, 7, ch, err);
         dir = 0; cur = 0; winner = -1;
-        int top = cards[--dl];
-        while (top % 15 == 14) { cards[dl++] = (uint8_t)top; shuffle_deck(ch); top = cards[--dl]; }
+        int top = pop_deck(ch, err);
+        while (top % 15 == 14) { unpop_deck(top); shuffle_deck(ch); top = pop_deck(ch, err); }
         tcode = top; tcolor = top / 15;
         if (top % 15 == 13) tcolor = (int)ch.below(4u);
         push_played(top);
         const int t = top % 15;                                            // round.py:38-52
         if (t == 10) cur = 1;
         else if (t == 11) { dir = 1; cur = 1; }
-        else if (t == 12) deal(0, 2, err);
+        else if (t == 12) deal(0, 2, ch, err);
     }
     __device__ __forceinline__ int player() const { return cur; }
     __device__ __forceinline__ bool over() const { return winner >= 0; }   // game.py:154-160
@@ -127,7 +219,7 @@ struct Uno {
         const int ttrait = tcode % 15;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const uint32_t w = hc[cur][c];
+            const uint32_t w = hcp(cur, c);
             uint32_t have = 0;
 #pragma unroll
             for (int t = 0; t < 13; t++) have |= ((w >> (2 * t)) & 3u) ? (1u << t) : 0u;
@@ -149,7 +241,7 @@ struct Uno {
         else if (t == 12 || t == 14) {
             const int need = t == 12 ? 2 : 4;
             if (dl < need) replace_deck(ch);
-            deal(current ^ 1, need, err);
+            deal(current ^ 1, need, ch, err);
             current ^= 1;
         }
         cur = current ^ 1;
@@ -164,7 +256,7 @@ struct Uno {
         }
         if (id == 60) {                                                 // _perform_draw_action
             if (dl == 0) replace_deck(ch);
-            const int card = pop_deck(err);
+            const int card = pop_deck(ch, err);
             if (card < 0) { cur ^= 1; return; }
             const int c = card / 15, t = card - 15 * c;
             if (t >= 13) { tcolor = (int)ch.below(4u); tcode = card; push_played(card); cur ^= 1; }
@@ -178,7 +270,7 @@ struct Uno {
         const int color = id / 15, trait = id - 15 * color;
         int code = id;
         if (trait >= 13) code = 15 * take_first_wild(cur, trait) + trait;
-        else hc[cur][color] -= 1u << (2 * trait);
+        else hc_add(cur, color, 0u - (1u << (2 * trait)));
         if (hand_empty(cur)) winner = cur;
         push_played(code);
         if (trait < 10) { cur ^= 1; tcode = code; tcolor = color; }
@@ -192,7 +284,7 @@ struct Uno {
     template <class T> __device__ void encode_obs(int seat, bool, T *row) const {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const uint32_t w = hc[seat][c];
+            const uint32_t w = hcp(seat, c);
 #pragma unroll
             for (int t = 0; t < 13; t++) {
                 const int k = (w >> (2 * t)) & 3;
@@ -205,5 +297,8 @@ struct Uno {
         row[180 + tcode] = (T)1;                                       // target.str: original colour (Q-UNO1)
     }
 };
+
+using Uno = UnoT<false>;      // replay modes: ordered piles
+using UnoBag = UnoT<true>;    // throughput mode
 
 }  // namespace rlc

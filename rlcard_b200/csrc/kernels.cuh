@@ -50,6 +50,19 @@ template <> struct ChanceIO<ChanceMt> {
     }
 };
 
+// games whose packed state depends on the chance kind (Blackjack: deck mask vs ordered deck) expose
+// load_k/store_k<kind>; the others plain load/store
+template <class G, class Ch>
+__device__ __forceinline__ void game_load(G &g, const uint32_t *st, size_t n, size_t i) {
+    if constexpr (G::kChanceAwareState) g.template load_k<Ch::kKind>(st, n, i);
+    else g.load(st, n, i);
+}
+template <class G, class Ch>
+__device__ __forceinline__ void game_store(const G &g, uint32_t *st, size_t n, size_t i) {
+    if constexpr (G::kChanceAwareState) g.template store_k<Ch::kKind>(st, n, i);
+    else g.store(st, n, i);
+}
+
 // deal the next episode; the chance draws continue the sequence of the current step
 template <class G, class Ch>
 __device__ __forceinline__ void new_episode(G &g, Ch &ch, EnvHeader &h) {
@@ -111,7 +124,7 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
     g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
     if (valid) {
         h.load(p.state, p.n, i);
-        g.load(p.state + kHeaderWords * p.n, p.n, i);
+        game_load<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         ChanceIO<Ch>::open(ch, p, i);
         bool done = false;
         float pay[G::P];
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
         if constexpr (MODE != kModeObserve) {
             ChanceIO<Ch>::close(ch, p, i);
             h.store(p.state, p.n, i);
-            g.store(p.state + kHeaderWords * p.n, p.n, i);
+            game_store<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         }
         err |= ch.err;
         if (err && p.err) p.err[i] |= err;
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
     if (valid) {
         h.load(p.state, p.n, i);
-        g.load(p.state + kHeaderWords * p.n, p.n, i);
+        game_load<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         ChanceIO<Ch>::open(ch, p, i);
         if (h.episode == 0) { ch.begin_reset(h.k); new_episode(g, ch, h); }
     }
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     if (valid) {
         ChanceIO<Ch>::close(ch, p, i);
         h.store(p.state, p.n, i);
-        g.store(p.state + kHeaderWords * p.n, p.n, i);
+        game_store<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         err |= ch.err;
         if (err && p.err) p.err[i] |= err;
     }

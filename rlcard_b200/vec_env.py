@@ -226,6 +226,57 @@ class VecEnv:
         self.launches += 1
         return out
 
+    def alloc_host_trajectory(self, T, pinned=True):
+        """Pinned host buffers with the layout of alloc_trajectory (the destination of rollout_random_host)."""
+        N = self.num_envs
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned)
+        mshape = (T, N, self.mask_words) if self.mask_bitpacked else (T, N, self.num_actions)
+        return {'obs': mk((T, N, self.obs_stride), self.obs_dtype),
+                'mask': mk(mshape, torch.int32 if self.mask_bitpacked else torch.uint8),
+                'action': mk((T, N), torch.int32), 'player': mk((T, N), torch.int32),
+                'done': mk((T, N), torch.uint8), 'payoffs': mk((T, N, self.num_players), torch.float32)}
+
+    def rollout_random_host(self, T, host_out, chunk=16, host_state=None):
+        """The Env.run loop with random agents for a HOST consumer (what examples/run_random.py does: the
+        trajectories end up in host memory).  T env-steps per env are produced in chunks of ``chunk`` steps by
+        rlc_rollout_random into two device staging buffers; while chunk c+1 is being simulated, chunk c is
+        copied device->host into the pinned ``host_out`` tensors on a second stream.  If ``host_state`` (a pinned
+        int32 tensor shaped like ``self.state``) is given, the packed env state is uploaded from it before the
+        first chunk and written back after the last one, i.e. the caller owns the state in host memory.
+        Returns after everything has landed in host memory."""
+        dev = self.device
+        chunk = max(1, min(int(chunk), int(T)))
+        if getattr(self, '_stage', None) is None or self._stage[0]['action'].shape[0] != chunk:
+            self._stage = [self.alloc_trajectory(chunk), self.alloc_trajectory(chunk)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_full = [torch.cuda.Event(), torch.cuda.Event()]
+        main = torch.cuda.current_stream(dev)
+        keys = ('obs', 'mask', 'action', 'player', 'done', 'payoffs')
+        with torch.cuda.device(dev):
+            if host_state is not None:
+                self.state.copy_(host_state, non_blocking=True)
+            t0, c = 0, 0
+            while t0 < T:
+                tc = min(chunk, T - t0)
+                b = c & 1
+                if c >= 2:
+                    main.wait_event(self._stage_free[b])            # the copy of chunk c-2 has left this buffer
+                self.rollout_random(tc, out=self._stage[b])
+                self._stage_full[b].record(main)
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(self._stage_full[b])
+                    for k in keys:
+                        host_out[k][t0:t0 + tc].copy_(self._stage[b][k][:tc], non_blocking=True)
+                    self._stage_free[b].record(self._copy_stream)
+                t0 += tc
+                c += 1
+            if host_state is not None:
+                host_state.copy_(self.state, non_blocking=True)
+            self._copy_stream.synchronize()
+            main.synchronize()
+        return host_out
+
     # ------------------------------------------------------------------ rollout helpers (callers of the path)
     def run(self, policy, num_steps, auto_reset=True):
         """Vector form of Env.run: policy(obs, mask, cur_player) -> int32 actions [N] on the device.

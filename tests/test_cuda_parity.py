@@ -146,6 +146,40 @@ def test_throughput_rollout_equals_oracle(game, obs_dtype):
     assert int(ref['done'].sum()) > 0
 
 
+def test_uno_long_rollout_reshuffles_equal_oracle():
+    """UNO throughput mode long enough for replace_deck (played pile back into the draw pile) to happen many
+    times: the multiset-pile kernel and the oracle's list piles must agree on every action / player / done /
+    payoff and on obs + mask at the end."""
+    if not built('uno'):
+        pytest.skip('uno not built')
+    n, T, seed = 192, 700, 55
+    env = rlcard_b200.VecEnv('uno', n, seed=seed)
+    env.reset()
+    tr = env.rollout_random(T)
+    ref = oracle.OracleVec('uno', n, seed).rollout(T, nthreads=4)
+    for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+        np.testing.assert_array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64), err_msg=k)
+    env.check_errors()
+    assert int(ref['action'][ref['action'] == 60].size) > 1000          # plenty of draws
+
+
+def test_host_rollout_equals_device_rollout():
+    """VecEnv.rollout_random_host (chunked launches + overlapped D2H into pinned memory, state owned by the
+    host) delivers the same trajectory as one device-side rollout."""
+    n, T, seed = 4096, 50, 77
+    a = rlcard_b200.VecEnv('leduc-holdem', n, seed=seed)
+    b = rlcard_b200.VecEnv('leduc-holdem', n, seed=seed)
+    a.reset(); b.reset()
+    ref = a.rollout_random(T)
+    h_state = torch.empty(b.state.shape, dtype=b.state.dtype).pin_memory()
+    h_state.copy_(b.state)
+    torch.cuda.synchronize()
+    out = b.rollout_random_host(T, b.alloc_host_trajectory(T), chunk=16, host_state=h_state)
+    for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+        assert torch.equal(out[k], ref[k].cpu()), k
+    assert torch.equal(h_state, a.state.cpu())
+
+
 @pytest.mark.parametrize('game', GAMES)
 def test_step_api_equals_fused_rollout(game):
     """Env.step kernel == fused rollout kernel: feeding the rollout's actions through step() (auto reset)

@@ -13,7 +13,7 @@ for g in leduc-holdem blackjack limit-holdem uno doudizhu scout; do
 done
 python bench.py --impl reference --steps 3 --warmup 3 > $OUT/bench_reference_$TAG.json 2>&1; echo "reference rc=$?"
 for g in leduc-holdem doudizhu; do
-  CMD="python bench.py --game $g --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 0"
+  CMD="python bench.py --game $g --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 0 --e2e-step-api-steps 0"
   $CMD > $OUT/plain_${g}_$TAG.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_${g}_$TAG.csv $CMD > $OUT/ncu_launches_${g}_$TAG.log 2>&1
   echo "launch list $g rc=$?"
