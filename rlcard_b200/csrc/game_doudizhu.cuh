@@ -42,7 +42,9 @@ __device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of ca
 struct Doudizhu {
     static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 859;
     static constexpr bool kMaskBitpacked = true;
-    static constexpr int kScratchBytes = 64;
+    static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for
+    static constexpr int kScratchBytes = 64 + 4 * 864;   // reset: 54-card deck | legal(): list of non-empty mask words
+    int n_legal, n_live; bool has_pass;                  // summary of the last legal() (warp-uniform)
     DdzTables tab;
     uint64_t hand[3], played[3];
     uint32_t tr[5];            // nine 16-bit action ids, entry k in tr[k/2] >> (16*(k&1)), k = 8 is the newest
@@ -109,11 +111,15 @@ struct Doudizhu {
     __device__ __forceinline__ int player() const { return cur; }
     __device__ __forceinline__ bool over() const { return winner != 3; }      // game.py:155-163
 
-    // player.py:60-76 / game.py:110-128: bit-packed legal set of the current player into smask[859]
-    __device__ void legal(uint32_t *smask, int lane) {
+    // player.py:60-76 / game.py:110-128: bit-packed legal set of the current player into smask[859].
+    // Also leaves, for pick(): the number of legal actions and a list of the non-empty mask words with the
+    // number of legal ids before each (word index | prefix << 10), so the policy never rescans the mask.
+    __device__ int legal(uint32_t *smask, uint8_t *scratch, int lane) {
+        uint32_t *slist = reinterpret_cast<uint32_t *>(scratch + 64);
         for (int j = lane; j < MASK_WORDS; j += 32) smask[j] = 0;
         __syncwarp();
-        if (winner != 3) return;                                               // terminal: actions = []
+        n_legal = 0; n_live = 0; has_pass = false;
+        if (winner != 3) return 0;                                             // terminal: actions = []
         const uint64_t H = sel3(hand, cur);
         const bool lead = greater == 3 || greater == cur;
         // candidate id ranges [lo1,hi1) u [lo2,hi2) (+ rocket, handled as part of range 2 when adjacent)
@@ -124,7 +130,11 @@ struct Doudizhu {
             else if (tt == kDdzTypeBomb) { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = kDdzRocket + 1; }   // larger bombs + rocket
             else { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = (int)tab.tw_start[tt * 17 + 16]; lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
         }
+        // batches of 32 mask words (1024 ids) that intersect the candidate ranges
+        const int b1lo = lo1 >> 10, b1hi = hi1 > lo1 ? (hi1 - 1) >> 10 : -1, b2 = hi2 > lo2 ? (hi2 - 1) >> 10 : -1;
+        int cnt = 0, nl = 0;
         for (int wb = 0; wb < (MASK_WORDS + 31) / 32; wb++) {
+            if (!((wb >= b1lo && wb <= b1hi) || wb == b2)) continue;
             const int j = wb * 32 + lane;                                      // phase A: which words can hold a legal id
             bool live = false;
             if (j < MASK_WORDS) {
@@ -139,18 +149,41 @@ struct Doudizhu {
                 const bool cand = (id >= lo1 && id < hi1) || (id >= lo2 && id < hi2);
                 const bool ok = cand && ddz_contains(H, tab.rows[id]);
                 const uint32_t word = __ballot_sync(kFull, ok);
-                if (lane == 0) smask[jj] = word;
+                if (word) {
+                    if (lane == 0) { smask[jj] = word; slist[nl] = (uint32_t)jj | ((uint32_t)cnt << 10); }
+                    nl++; cnt += __popc(word);
+                }
             }
         }
+        if (!lead) {
+            if (lane == 0) smask[kDdzPass >> 5] |= 1u << (kDdzPass & 31);
+            has_pass = true;
+        }
         __syncwarp();
-        if (!lead && lane == 0) smask[kDdzPass >> 5] |= 1u << (kDdzPass & 31);
+        n_live = nl; n_legal = cnt + (has_pass ? 1 : 0);
+        return n_legal;
+    }
+    // k-th legal id in ascending order (0 <= k < n_legal of the last legal()); 'pass' is the largest id
+    __device__ int pick(const uint32_t *smask, const uint8_t *scratch, int k, int lane) const {
+        if (has_pass && k == n_legal - 1) return kDdzPass;
+        const uint32_t *slist = reinterpret_cast<const uint32_t *>(scratch + 64);
+        int c = 0;                                                            // entries whose prefix <= k (prefixes ascend)
+        for (int base = 0; base < n_live; base += 32) {
+            const int idx = base + lane;
+            const uint32_t le = __ballot_sync(kFull, idx < n_live && (int)(slist[idx] >> 10) <= k);
+            c += __popc(le);
+            if (le != kFull) break;
+        }
+        const uint32_t ee = slist[c - 1];
+        const int jj = (int)(ee & 1023u);
+        return 32 * jj + (int)__fns(smask[jj], 0, k - (int)(ee >> 10) + 1);
     }
     // env.py:65-86, game.py:53-81, round.py:52-79, player.py:78-108, judger.py:335-348
-    template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *, int lane, int &err) {
+    template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *scratch, int lane, int &err) {
         if (id < 0 || id >= A || !((smask[id >> 5] >> (id & 31)) & 1u)) {     // replay feeds legal ids only
             err |= 4;
-            id = warp_kth_set_bit(smask, MASK_WORDS, 0, lane);
-            if (id < 0) return;
+            if (n_legal == 0) return;
+            id = pick(smask, scratch, 0, lane);
         }
         const int p = cur;
         if (id != kDdzPass) {

@@ -26,6 +26,7 @@ __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * 
 struct Scout {
     static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
     static constexpr bool kMaskBitpacked = false;
+    static constexpr int kMinBlocks = 4;          // resident 128-thread blocks per SM the rollout kernel is compiled for
     static constexpr int kScratchBytes = 48;
     uint64_t ht[4], hb[4], tt, tb;
     int hl[4], score[4], tl, owner, consec, cur, over_;
@@ -50,7 +51,7 @@ struct Scout {
         for (int p = 0; p < 4; p++) hl[p] = (m >> (5 * p)) & 31;
         tl = (m >> 20) & 31; owner = (m >> 25) & 7; consec = (m >> 28) & 3; cur = (m >> 30) & 3;
         score[0] = s0 & 0xffff; score[1] = s0 >> 16; score[2] = s1 & 0xffff; score[3] = (s1 >> 16) & 0x7fff; over_ = s1 >> 31;
-        forced = false;
+        forced = false; lm_valid = false;
         // play ids of this lane: id = lane + 32 r, r = 0..4 -> (start, end) of the s-major enumeration
         segtab = 0;
         int s = 0, base = 0;
@@ -110,14 +111,19 @@ struct Scout {
         }
         forced = (m[0] | m[1] | m[2] | m[3] | (m[4] & 0xffu)) == 0;
     }
-    __device__ __forceinline__ void legal(uint32_t *smask, int lane) {
-        uint32_t m[7];
-        legal_words(m, lane);
+    uint32_t lm[7];        // the last legal() set, identical in all lanes
+    bool lm_valid;         // lm / forced already describe the current state (step() computed them)
+    __device__ __forceinline__ int legal(uint32_t *smask, uint8_t *, int lane) {
+        if (!lm_valid) legal_words(lm, lane);
+        lm_valid = true;
         if (lane == 0) {
 #pragma unroll
-            for (int r = 0; r < 7; r++) smask[r] = m[r];
+            for (int r = 0; r < 7; r++) smask[r] = lm[r];
         }
+        return popc_words<7>(lm);
     }
+    // k-th legal id in ascending order
+    __device__ __forceinline__ int pick(const uint32_t *, const uint8_t *, int k, int) const { return kth_set_bit<7>(lm, k); }
     // games/scout/game.py:37-65, dealer.py:12-22, round.py:22-50: two shuffles (Q-SC1), round-robin deal
     template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
         if (lane == 0) {
@@ -142,7 +148,7 @@ struct Scout {
         __syncwarp();
         tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
         cur = (int)ch.below(4u);
-        forced = false;
+        forced = false; lm_valid = false;
     }
     __device__ __forceinline__ int player() const { return cur; }
     __device__ __forceinline__ bool over() const { return over_ != 0; }
@@ -150,7 +156,7 @@ struct Scout {
     template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *, int lane, int &err) {
         if (id < 0 || id >= A || !((smask[id >> 5] >> (id & 31)) & 1u)) {   // the reference raises; replay feeds legal ids
             err |= 4;
-            id = warp_kth_set_bit(smask, MASK_WORDS, 0, lane);
+            id = kth_set_bit<7>(lm, 0);
             if (id < 0) return;
         }
         const int p = cur;
@@ -188,9 +194,9 @@ struct Scout {
         }
         put(ht, p, T); put(hb, p, B); puti(hl, p, n);
         cur = (p + 1) & 3;
-        uint32_t m[7];
-        legal_words(m, lane);                                               // next player cannot move -> round ends
-        if ((m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6]) == 0) over_ = 1;
+        legal_words(lm, lane);                                              // next player cannot move -> round ends
+        lm_valid = true;
+        if ((lm[0] | lm[1] | lm[2] | lm[3] | lm[4] | lm[5] | lm[6]) == 0) over_ = 1;
     }
     __device__ __forceinline__ void payoffs(float *out) const {             // judger.py:15-30
 #pragma unroll

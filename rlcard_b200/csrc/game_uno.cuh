@@ -93,21 +93,15 @@ struct UnoT {
         if constexpr (BAG) {                                             // uniformly random remaining card
             int r = (int)ch.below((uint32_t)dl);
             dl--;
-            int c = 0;
-            uint32_t w = dk[0];
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int s = sum2(w);
-                const bool next = (c == k) && r >= s;
-                r = next ? r - s : r; c = next ? k + 1 : c; w = next ? dk[k + 1] : w;
-            }
-            int t = 0; bool found = false;
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                const int cnt = (int)((w >> (2 * k)) & 3u);
-                const bool here = !found && r < cnt;
-                t = here ? k : t; found = found || here; r = (found ? r : r - cnt);
-            }
+            // counters in unary (v = 1 -> 01, v = 2 -> 11): the r-th remaining card in ascending code order
+            // is the r-th set bit of the four 30-bit words
+            const uint32_t u0 = dk[0] | ((dk[0] >> 1) & 0x15555555u), u1 = dk[1] | ((dk[1] >> 1) & 0x15555555u);
+            const uint32_t u2 = dk[2] | ((dk[2] >> 1) & 0x15555555u), u3 = dk[3] | ((dk[3] >> 1) & 0x15555555u);
+            const int n0 = __popc(u0), n1 = n0 + __popc(u1), n2 = n1 + __popc(u2);
+            const int c = (r >= n0) + (r >= n1) + (r >= n2);
+            const uint32_t u = c == 0 ? u0 : (c == 1 ? u1 : (c == 2 ? u2 : u3));
+            r -= c == 0 ? 0 : (c == 1 ? n0 : (c == 2 ? n1 : n2));
+            const int t = (int)__fns(u, 0, r + 1) >> 1;
             const uint32_t dec = 1u << (2 * t);
             dk[0] -= c == 0 ? dec : 0u; dk[1] -= c == 1 ? dec : 0u; dk[2] -= c == 2 ? dec : 0u; dk[3] -= c == 3 ? dec : 0u;
             return 15 * c + t;

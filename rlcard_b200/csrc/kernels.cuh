@@ -213,6 +213,11 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
 
     G g; EnvHeader h; Ch ch; int err = 0;
     g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
+    // dense mask rows wider than one word (UNO: 61 bytes) are staged per warp too: 32 rows are contiguous
+    // in global memory, byte stores from the lanes would touch 32 different sectors each
+    constexpr bool kStageMask = G::A > 4;
+    constexpr int kMaskTile = kStageMask ? ((32 * G::A + 15) & ~15) : 0;
+    uint8_t *mtile = reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes + ((G::kSharedBytes + 15) & ~15) + wib * kMaskTile;
     if (valid) {
         h.load(p.state, p.n, i);
         game_load<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
@@ -229,8 +234,19 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         if (valid) {
             if (ALL || p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
             g.legal(m);
+            if constexpr (kStageMask) {
+                if (ALL || p.t_mask) {
+                    uint8_t *mr = mtile + lane * G::A;
+#pragma unroll
+                    for (int a = 0; a < G::A; a++) mr[a] = (m[a >> 5] >> (a & 31)) & 1u;
+                }
+            }
         }
         __syncwarp();
+        if constexpr (kStageMask) {
+            if (ALL || p.t_mask)
+                warp_tile_flush(reinterpret_cast<uint8_t *>(p.t_mask) + (rowi - lane) * (size_t)G::A, mtile, nvalid * G::A, lane);
+        }
         if constexpr (ALL) {
             if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
             else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
@@ -239,7 +255,9 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         }
         __syncwarp();
         if (valid) {
-            if (ALL || p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
+            if constexpr (!kStageMask) {
+                if (ALL || p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
+            }
             if (ALL || p.t_player) __stcs(p.t_player + rowi, g.player());
             uint32_t word;
             if constexpr (Ch::kKind == 0) word = ch.begin_step(h.k);
@@ -285,7 +303,8 @@ template <class G, class Ch, class ObsT>
 cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
     constexpr int BLOCK = 64;
     const unsigned grid = (unsigned)((p.n + BLOCK - 1) / BLOCK);
-    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT) + ((G::kSharedBytes + 15) & ~15);
+    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT) + ((G::kSharedBytes + 15) & ~15) +
+                        (G::A > 4 ? (size_t)(BLOCK / 32) * ((32 * G::A + 15) & ~15) : 0);
     // rollout fast path: every trajectory stream requested and obs rows of a full warp 16-byte aligned
     const bool all = op == kOpRollout && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
                      ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * G::OBS * sizeof(ObsT))) & 15u) == 0;

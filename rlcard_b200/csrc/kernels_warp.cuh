@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
         const int a = p.actions[env];
         if (a >= 0 && h.episode != 0 && !g.over()) {
             ch.begin_step(h.k);
-            g.legal(smask, lane);                        // the step validates against the current legal set
+            g.legal(smask, scratch, lane);                        // the step validates against the current legal set
             __syncwarp();
             g.step(a, ch, smask, scratch, lane, err);
             h.t++; h.k++;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
                 done = true;
                 g.payoffs(pay);
                 if ((p.flags & RLC_TERMINAL_OBS) && p.terminal_obs) {
-                    g.legal(smask, lane);
+                    g.legal(smask, scratch, lane);
                     __syncwarp();
                     for (int s = 0; s < G::P; s++) {
                         g.encode_obs(s, false, srow, lane);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
         if (h.episode != 0 && g.over()) { done = true; g.payoffs(pay); }
     }
     __syncwarp();
-    g.legal(smask, lane);
+    g.legal(smask, scratch, lane);
     __syncwarp();
     const int seat = (MODE == kModeObserve && p.seat) ? p.seat[env] : g.player();
     if (p.obs) {
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
 }
 
 template <class G, class Ch, class ObsT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
+__global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t env = (size_t)blockIdx.x * (BLOCK / 32) + wib;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
     int err = 0;
     if (h.episode == 0) { ch.begin_reset(h.k); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
     __syncwarp();
-    g.legal(smask, lane);
+    int cnt = g.legal(smask, scratch, lane);
     __syncwarp();
     size_t rowi = env;
     for (int t = 0; t < p.T; t++, rowi += p.n) {
@@ -216,9 +216,8 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
         }
         if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
-        const int cnt = warp_popc_words(smask, G::MASK_WORDS, lane);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
-        const int a = warp_kth_set_bit(smask, G::MASK_WORDS, k, lane);
+        const int a = g.pick(smask, scratch, k, lane);
         const int pl = g.player();
         __syncwarp();
         g.step(a, ch, smask, scratch, lane, err);
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(BLOCK) k_wrollout(const KParams p) {
         for (int q = 0; q < G::P; q++) pay[q] = 0.f;
         if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
         __syncwarp();
-        g.legal(smask, lane);                            // legal set of the state the next iteration emits
+        cnt = g.legal(smask, scratch, lane);                      // legal set of the state the next iteration emits
         __syncwarp();
         if (lane == 0) {
             if (p.t_player) __stcs(p.t_player + rowi, pl);
