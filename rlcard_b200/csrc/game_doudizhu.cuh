@@ -25,7 +25,8 @@ namespace rlc {
 
 struct DdzTables {
     const uint64_t *rows;      // [27472] nibble-packed rank counts ('pass' = 0)
-    const uint64_t *need;      // [864]   nibble-wise min over the 32 rows of each mask word
+    const uint64_t *need;      // [864]   nibble-wise min over the 32 rows of each mask word; [864 + b] = min over
+                               //         batch b of 32 mask words (1024 ids), b < 27
     const uint8_t *type;       // [27472]
     const uint8_t *weight;     // [27472]
     const uint32_t *tw_start;  // [39][17] first id of type t with weight >= w; [t][16] = end of type t
@@ -130,12 +131,17 @@ struct Doudizhu {
             else if (tt == kDdzTypeBomb) { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = kDdzRocket + 1; }   // larger bombs + rocket
             else { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = (int)tab.tw_start[tt * 17 + 16]; lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
         }
-        // batches of 32 mask words (1024 ids) that intersect the candidate ranges
-        const int b1lo = lo1 >> 10, b1hi = hi1 > lo1 ? (hi1 - 1) >> 10 : -1, b2 = hi2 > lo2 ? (hi2 - 1) >> 10 : -1;
+        // level 0: one lane per batch of 32 mask words (1024 ids): in range and its nibble-wise minimum contained?
+        bool blive = false;
+        if (lane < (MASK_WORDS + 31) / 32) {
+            const int a0 = 1024 * lane, a1 = a0 + 1024;
+            blive = ((a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2)) && ddz_contains(H, tab.need[864 + lane]);
+        }
+        uint32_t lb = __ballot_sync(kFull, blive);
         int cnt = 0, nl = 0;
-        for (int wb = 0; wb < (MASK_WORDS + 31) / 32; wb++) {
-            if (!((wb >= b1lo && wb <= b1hi) || wb == b2)) continue;
-            const int j = wb * 32 + lane;                                      // phase A: which words can hold a legal id
+        while (lb) {
+            const int wb = __ffs(lb) - 1; lb &= lb - 1;
+            const int j = wb * 32 + lane;                                      // level 1: which words can hold a legal id
             bool live = false;
             if (j < MASK_WORDS) {
                 const int a0 = 32 * j, a1 = a0 + 32;
@@ -143,7 +149,7 @@ struct Doudizhu {
                 live = overlap && ddz_contains(H, tab.need[j]);
             }
             uint32_t lw = __ballot_sync(kFull, live);
-            while (lw) {                                                       // phase B: expand the live words
+            while (lw) {                                                       // level 2: expand the live words
                 const int b = __ffs(lw) - 1; lw &= lw - 1;
                 const int jj = wb * 32 + b, id = 32 * jj + lane;
                 const bool cand = (id >= lo1 && id < hi1) || (id >= lo2 && id < hi2);
@@ -205,16 +211,12 @@ struct Doudizhu {
     }
     // envs/doudizhu.py:153-167: 54-d block of rank counts c; lane writes elements lane and lane+32
     template <class T> __device__ __forceinline__ void put54(T *dst, uint64_t c, int lane) const {
-        {
-            const int e = lane, r = e >> 2, k = e & 3;
-            dst[e] = (T)(((int)((c >> (4 * r)) & 15ull) > k) ? 1 : 0);
-        }
-        if (lane < 22) {
-            const int e = lane + 32;
-            int v;
-            if (e < 52) { const int r = e >> 2, k = e & 3; v = ((int)((c >> (4 * r)) & 15ull) > k); }
-            else v = ((c >> (4 * (e - 39))) & 15ull) != 0;                    // e = 52 -> rank 13 (B), 53 -> rank 14 (R)
-            dst[e] = (T)v;
+        const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);             // ranks 0..7 | ranks 8..14
+        const int sh = 4 * (lane >> 2), k = lane & 3;                          // element lane: rank lane/4, copy lane%4
+        dst[lane] = (T)(((lo >> sh) & 15u) > (uint32_t)k ? 1 : 0);
+        if (lane < 22) {                                                       // element lane + 32: ranks 8..12, then B, R
+            const uint32_t v = lane < 20 ? (uint32_t)(((hi >> sh) & 15u) > (uint32_t)k) : (uint32_t)(((hi >> (lane == 20 ? 20 : 24)) & 15u) != 0u);
+            dst[lane + 32] = (T)v;
         }
     }
     __device__ __forceinline__ uint64_t action_counts(uint32_t id) const { return tab.rows[id]; }

@@ -14,7 +14,7 @@ static void *g_dev_blob[64];
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     if (device < 0 || device >= 64 || !blob || nbytes < sizeof(DdzBlobHeader)) return cudaErrorInvalidValue;
     DdzBlobHeader h; memcpy(&h, blob, sizeof h);
-    if (memcmp(h.magic, "DDZ1", 4) != 0 || h.n_actions != 27472 || h.total != nbytes || h.n_types != 38) return cudaErrorInvalidValue;
+    if (memcmp(h.magic, "DDZ1", 4) != 0 || h.n_actions != 27472 || h.n_words_padded != 896 || h.total != nbytes || h.n_types != 38) return cudaErrorInvalidValue;
     int prev = 0; cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;

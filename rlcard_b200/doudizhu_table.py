@@ -156,7 +156,8 @@ def action_strings():
 
 def build_blob():
     """Device table blob for rlc_upload_tables(RLC_DOUDIZHU, ...) (layout: csrc/tu_doudizhu.cu DdzBlobHeader):
-    rows u64[27472] | need u64[864] (nibble-wise min of the 32 rows of each mask word) | type u8[27472] |
+    rows u64[27472] | need u64[864 + 32] (nibble-wise min of the 32 rows of each mask word; entries 864.. =
+    nibble-wise min of each batch of 32 mask words = 1024 ids) | type u8[27472] |
     weight u8[27472] | tw_start u32[38][17] (first id of type t with weight >= w; [t][16] = end of type t)."""
     import struct
     tab = load()
@@ -165,9 +166,11 @@ def build_blob():
     nib = np.stack([(rows >> np.uint64(4 * r)) & np.uint64(15) for r in range(15)], axis=1).astype(np.uint8)   # [A, 15]
     pad = np.full((n_words * 32 - NUM_ACTIONS, 15), 15, np.uint8)
     mins = np.concatenate([nib, pad]).reshape(n_words, 32, 15).min(axis=1)
-    need = np.zeros(864, np.uint64)
+    need = np.zeros(864 + 32, np.uint64)
+    bmins = np.concatenate([mins, np.full((864 - n_words, 15), 15, np.uint8)]).reshape(27, 32, 15).min(axis=1)
     for r in range(15):
         need[:n_words] |= mins[:, r].astype(np.uint64) << np.uint64(4 * r)
+        need[864:864 + 27] |= bmins[:, r].astype(np.uint64) << np.uint64(4 * r)
     ntypes = len(TYPE_NAMES)
     tw = np.zeros((ntypes, 17), np.uint32)
     types, weights = tab['type'].astype(np.int64), tab['weight'].astype(np.int64)
@@ -188,7 +191,7 @@ def build_blob():
         offs.append(cur)
         cur += len(b)
     total = (cur + 15) & ~15
-    hdr = struct.pack('<4sIII6Q', b'DDZ1', NUM_ACTIONS, 864, ntypes, *offs, total)
+    hdr = struct.pack('<4sIII6Q', b'DDZ1', NUM_ACTIONS, 864 + 32, ntypes, *offs, total)
     blob = bytearray(total)
     blob[:len(hdr)] = hdr
     for o, b in zip(offs, parts):
