@@ -133,6 +133,27 @@ int rlc_observe(int game_id, const rlc_buffers *b, const int32_t *seat, int n, v
 int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *traj, int n, int k_steps,
                        void *stream);
 
+/* ---- the judgers / encoders as standalone operators (device pointers; used by the known-answer tests and by
+ * callers that score hands outside an episode) ---- */
+
+/* games/limitholdem/utils.py:526-569 compare_hands: cards uint8 [n][P][7], card id = 13*suit + rank as in
+ * games/limitholdem/card2index.json (S,H,D,C x A,2..K); first card 255 = folded (None).
+ * winners uint8 [n][P]: 1 for every unfolded hand of maximal strength. */
+int rlc_judge_holdem(const uint8_t *cards, int n, int num_players, uint8_t *winners, void *stream);
+
+/* games/leducholdem/judger.py:12-64 judge_game / big blind (game.py:170-178): cases int32 [n][7] =
+ * (rank0, rank1, public rank or -1, chips0, chips1, folded0, folded1), ranks J,Q,K = 0,1,2 -> payoffs float [n][2] */
+int rlc_judge_leduc(const int32_t *cases, int n, float *payoffs, void *stream);
+
+/* games/doudizhu/judger.py:124-258 playable_cards_from_hand (targets NULL or targets[i] < 0: lead) and
+ * games/doudizhu/utils.py:225-262 get_gt_cards (targets[i] = action id to beat): hands uint8 [n][15] rank counts
+ * (3456789TJQKA2BR) -> bit-packed legal sets uint32 [n][859].  Needs rlc_upload_tables(RLC_DOUDIZHU, ...). */
+int rlc_judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint32_t *mask, void *stream);
+
+/* games/uno/utils.py:86-127 encode_hand + encode_target: hands uint8 [n][32] card codes 15*colour + trait
+ * (255 = empty slot), targets uint8 [n] -> obs uint8 [n][240] ([4][4][15] planes of envs/uno.py:24-33) */
+int rlc_encode_uno(const uint8_t *hands, const uint8_t *targets, int n, uint8_t *obs, void *stream);
+
 /* number of kernels this library has launched in this process (bench bookkeeping) */
 int64_t rlc_launch_count(void);
 

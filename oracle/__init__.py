@@ -58,6 +58,10 @@ def lib():
         L.orc_philox_word.restype = C.c_uint32; L.orc_philox_word.argtypes = [C.c_uint32] * 7
         L.orc_philox4x32_10.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
         L.orc_doudizhu_set_table.argtypes = [vp, vp, vp, i32, i32, i32]
+        L.orc_holdem_winners.argtypes = [vp, i32, vp]
+        L.orc_doudizhu_legal_for.argtypes = [vp, i32, vp]
+        L.orc_leduc_judge.argtypes = [i32] * 7 + [vp]
+        L.orc_uno_encode.argtypes = [vp, i32, i32, vp]
         _LIB = L
     return _LIB
 
@@ -89,6 +93,10 @@ def seed_words(seed):
         big, mod = divmod(big, 2 ** 32)
         out.append(mod)
     return out
+
+
+def need_tables(game):
+    _need_tables(GAME_IDS[game] if isinstance(game, str) else game)
 
 
 def info(game):

@@ -109,6 +109,12 @@ int64_t orc_envs_episodes(const orc_envs *v);
  * exactly like limitholdem/utils.py compare_hands. */
 uint32_t orc_holdem_strength7(const uint8_t cards[7]);
 
+/* judger helpers for the known-answer tests (tests/test_reference_kats.py) */
+void orc_holdem_winners(const uint8_t *cards /*[P][7], first card 255 = folded*/, int P, uint8_t *win);
+int orc_doudizhu_legal_for(const uint8_t *hand15, int target_action /* <0: lead */, uint8_t *mask /*[27472]*/);
+void orc_leduc_judge(int r0, int r1, int pub, int c0, int c1, int f0, int f1, double *out);
+int orc_uno_encode(const uint8_t *codes, int n, int target_code, float *out /*[240]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,5 +146,16 @@ static void ddz_payoffs(const void *s, double *out) {              /* judger.py:
     const ddz_t *g = (const ddz_t *)s;
     out[0] = g->winner == 0 ? 1 : 0; out[1] = out[2] = g->winner == 0 ? 0 : 1;
 }
+/* known-answer helper: legal set of an arbitrary hand (rank counts), leading (target < 0 ==
+ * judger.playable_cards_from_hand) or following `target` (== utils.get_gt_cards); returns the count */
+int orc_doudizhu_legal_for(const uint8_t *hand15, int target_action, uint8_t *mask) {
+    ddz_t g;
+    memset(&g, 0, sizeof g);
+    for (int r = 0; r < 15; r++) g.hand[0][r] = hand15[r];
+    g.cur = 0; g.winner = -1;
+    if (target_action < 0) { g.greater = -1; g.greater_action = DDZ_PASS; }
+    else { g.greater = 1; g.greater_action = target_action; }
+    return ddz_legal_list(&g, mask);
+}
 const orc_game_vt orc_vt_doudizhu = { "doudizhu", 3, DDZ_A, {790, 901, 901, 0}, sizeof(ddz_t), ddz_create, ddz_reset, ddz_step,
     ddz_legal, ddz_obs, ddz_over, ddz_player, ddz_payoffs };

@@ -130,6 +130,15 @@ static void leduc_payoffs(const void *s, double *out) {
     double total = g->in_chips[0] + g->in_chips[1], each = total / (winners[0] + winners[1]);
     for (int i = 0; i < 2; i++) out[i] = (winners[i] ? each - g->in_chips[i] : -(double)g->in_chips[i]) / 2.0;
 }
+/* known-answer helper: LeducholdemJudger.judge_game / big blind on an arbitrary showdown
+ * (ranks 0..2 = J,Q,K; pub < 0 = no public card) */
+void orc_leduc_judge(int r0, int r1, int pub, int c0, int c1, int f0, int f1, double *out) {
+    leduc_t g;
+    memset(&g, 0, sizeof g);
+    g.hand[0] = 2 * r0; g.hand[1] = 2 * r1 + 1; g.public_card = pub < 0 ? -1 : 2 * pub + (pub == r0 ? 1 : 0);
+    g.in_chips[0] = c0; g.in_chips[1] = c1; g.folded[0] = f0; g.folded[1] = f1;
+    leduc_payoffs(&g, out);
+}
 const orc_game_vt orc_vt_leduc = { "leduc-holdem", 2, 4, {36, 36, 0, 0}, sizeof(leduc_t), leduc_create, leduc_reset,
     leduc_step, leduc_legal, leduc_obs, leduc_over, leduc_player, leduc_payoffs };
 
@@ -298,6 +307,16 @@ static void limit_payoffs(const void *s, double *out) {
         }
     }
     out[0] = payoffs[0] / 2.0; out[1] = payoffs[1] / 2.0;
+}
+/* known-answer helper: limitholdem/utils.py compare_hands over P hands of 7 card ids (cards[p][0] == 255:
+ * folded / None): winners = the unfolded hands of maximal strength */
+void orc_holdem_winners(const uint8_t *cards, int P, uint8_t *win) {
+    uint32_t best = 0, str[8];
+    for (int p = 0; p < P; p++) {
+        str[p] = cards[7 * p] == 255 ? 0u : 1u + orc_holdem_strength7(cards + 7 * p);
+        if (str[p] > best) best = str[p];
+    }
+    for (int p = 0; p < P; p++) win[p] = (uint8_t)(str[p] != 0 && str[p] == best);
 }
 const orc_game_vt orc_vt_limit = { "limit-holdem", 2, 4, {72, 72, 0, 0}, sizeof(limit_t), limit_create, limit_reset,
     limit_step, limit_legal, limit_obs, limit_over, limit_player, limit_payoffs };

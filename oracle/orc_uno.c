@@ -177,5 +177,15 @@ static void uno_payoffs(const void *s, double *out) {        /* game.py:108-118 
     out[0] = out[1] = 0;
     if (g->winner >= 0) { out[g->winner] = 1; out[1 - g->winner] = -1; }
 }
+/* known-answer helper: encode_hand + encode_target (games/uno/utils.py:86-127) of an arbitrary hand of card
+ * codes (15*colour + trait) and target code */
+int orc_uno_encode(const uint8_t *codes, int n, int target_code, float *out) {
+    static uno_t g;
+    memset(&g, 0, sizeof g);
+    for (int i = 0; i < n; i++) { g.hand[0][i].code = codes[i]; g.hand[0][i].color = (uint8_t)(codes[i] / 15); }
+    g.hl[0] = n; g.current = 0; g.winner = -1;
+    g.target.code = (uint8_t)target_code; g.target.color = (uint8_t)(target_code / 15);
+    return uno_obs(&g, 0, out);
+}
 const orc_game_vt orc_vt_uno = { "uno", 2, 61, {240, 240, 0, 0}, sizeof(uno_t), uno_create, uno_reset, uno_step,
     uno_legal, uno_obs, uno_over, uno_player, uno_payoffs };

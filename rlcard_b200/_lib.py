@@ -38,7 +38,8 @@ class RlcTrajectory(C.Structure):
 
 
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
-           'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count']
+           'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
+           'rlc_judge_doudizhu', 'rlc_encode_uno']
 
 _LIB = None
 
@@ -65,6 +66,10 @@ def lib():
         L.rlc_step.argtypes = [i32, C.POINTER(RlcBuffers), vp, i32, i32, vp]
         L.rlc_observe.argtypes = [i32, C.POINTER(RlcBuffers), vp, i32, vp]
         L.rlc_rollout_random.argtypes = [i32, C.POINTER(RlcBuffers), C.POINTER(RlcTrajectory), i32, i32, vp]
+        L.rlc_judge_holdem.argtypes = [vp, i32, i32, vp, vp]
+        L.rlc_judge_leduc.argtypes = [vp, i32, vp, vp]
+        L.rlc_judge_doudizhu.argtypes = [vp, vp, i32, vp, vp]
+        L.rlc_encode_uno.argtypes = [vp, vp, i32, vp, vp]
         _LIB = L
     return _LIB
 

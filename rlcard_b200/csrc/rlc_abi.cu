@@ -10,8 +10,11 @@ namespace rlc {
 cudaError_t dispatch_blackjack(int, int, int, const KParams &, cudaStream_t);
 cudaError_t dispatch_leduc(int, int, int, const KParams &, cudaStream_t);
 cudaError_t dispatch_limit(int, int, int, const KParams &, cudaStream_t);
+cudaError_t judge_holdem(const uint8_t *, int, int, uint8_t *, cudaStream_t);
+cudaError_t judge_leduc(const int32_t *, int, float *, cudaStream_t);
 #ifdef RLC_HAVE_UNO
 cudaError_t dispatch_uno(int, int, int, const KParams &, cudaStream_t);
+cudaError_t encode_uno(const uint8_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
 #endif
 #ifdef RLC_HAVE_SCOUT
 cudaError_t dispatch_scout(int, int, int, const KParams &, cudaStream_t);
@@ -19,6 +22,7 @@ cudaError_t dispatch_scout(int, int, int, const KParams &, cudaStream_t);
 #ifdef RLC_HAVE_DOUDIZHU
 cudaError_t dispatch_doudizhu(int, int, int, const KParams &, cudaStream_t);
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes);
+cudaError_t judge_doudizhu(const uint8_t *, const int32_t *, int, uint32_t *, cudaStream_t);
 #endif
 }  // namespace rlc
 
@@ -139,6 +143,41 @@ int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *
     }
     p.T = k_steps;
     return dispatch(game_id, rlc::kOpRollout, b, p, stream);
+}
+
+static int judged(cudaError_t e) {
+    if (e == cudaErrorNotReady) return fail(RLC_ENOTABLE, "rlc_upload_tables(RLC_DOUDIZHU, ...) is needed on this device first");
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? RLC_EINVAL : RLC_ECUDA, "CUDA: %s", cudaGetErrorString(e));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return RLC_OK;
+}
+
+int rlc_judge_holdem(const uint8_t *cards, int n, int num_players, uint8_t *winners, void *stream) {
+    if (!cards || !winners || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+    return judged(rlc::judge_holdem(cards, n, num_players, winners, reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int rlc_judge_leduc(const int32_t *cases, int n, float *payoffs, void *stream) {
+    if (!cases || !payoffs || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+    return judged(rlc::judge_leduc(cases, n, payoffs, reinterpret_cast<cudaStream_t>(stream)));
+}
+
+int rlc_judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint32_t *mask, void *stream) {
+    if (!hands || !mask || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+#ifdef RLC_HAVE_DOUDIZHU
+    return judged(rlc::judge_doudizhu(hands, targets, n, mask, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "doudizhu is not in this build");
+#endif
+}
+
+int rlc_encode_uno(const uint8_t *hands, const uint8_t *targets, int n, uint8_t *obs, void *stream) {
+    if (!hands || !targets || !obs || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+#ifdef RLC_HAVE_UNO
+    return judged(rlc::encode_uno(hands, targets, n, obs, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "uno is not in this build");
+#endif
 }
 
 }  // extern "C"

@@ -33,6 +33,41 @@ cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     return e;
 }
 
+// judger.py:124-258 playable_cards_from_hand (target < 0) / utils.py:225-262 get_gt_cards as a standalone
+// operator: one warp per case, bit-packed legal set out
+__global__ void __launch_bounds__(128) k_judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint32_t *mask, KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + wib;
+    if (i >= n) return;
+    constexpr int kWarpBytes = ((Doudizhu::MASK_WORDS * 4 + 15) & ~15) + Doudizhu::kScratchBytes;
+    uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)wib * kWarpBytes;
+    uint32_t *smask = reinterpret_cast<uint32_t *>(base);
+    uint8_t *scratch = base + ((Doudizhu::MASK_WORDS * 4 + 15) & ~15);
+    Doudizhu g; g.bind(p);
+    uint64_t h = 0;
+    for (int r = 0; r < 15; r++) h |= (uint64_t)(hands[(size_t)i * 15 + r] & 15) << (4 * r);
+    g.hand[0] = h; g.hand[1] = g.hand[2] = 0; g.played[0] = g.played[1] = g.played[2] = 0;
+    g.cur = 0; g.winner = 3;
+    const int t = targets ? targets[i] : -1;
+    g.greater = t < 0 ? 3 : 1; g.greater_action = t < 0 ? (uint32_t)kDdzPass : (uint32_t)t;
+    g.legal(smask, scratch, lane);
+    __syncwarp();
+    for (int w = lane; w < Doudizhu::MASK_WORDS; w += 32) mask[(size_t)i * Doudizhu::MASK_WORDS + w] = smask[w];
+}
+cudaError_t judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint32_t *mask, cudaStream_t s) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !g_dev_blob[dev]) return cudaErrorNotReady;
+    KParams q; memset(&q, 0, sizeof q);
+    DdzTables t = g_tab[dev];
+    memcpy(q.tab, &t, sizeof t);
+    const size_t smem = 4 * (size_t)(((Doudizhu::MASK_WORDS * 4 + 15) & ~15) + Doudizhu::kScratchBytes);
+    k_judge_doudizhu<<<(n + 3) / 4, 128, smem, s>>>(hands, targets, n, mask, q);
+    return cudaGetLastError();
+}
+
 cudaError_t dispatch_doudizhu(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t s) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
