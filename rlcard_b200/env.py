@@ -159,8 +159,56 @@ class Env:
         feature[action] = 1
         return feature
 
+    # -- the per-env helpers the reference's callers and tests touch (envs/<game>.py)
+    def _get_legal_actions(self):
+        """OrderedDict of the current player's legal action ids (envs/<game>.py _get_legal_actions)."""
+        if self.name == 'blackjack' and self._vec.state[0, 0].item() == 0:      # before the first reset: {0, 1}
+            return OrderedDict([(0, None), (1, None)])
+        self._vec.get_state(None)
+        return self._dict_from(self._vec.obs[0], self._vec.mask[0], self.get_player_id())['legal_actions']
+
+    def _decode_action(self, action_id):
+        """id -> raw action with the reference's per-env fallback for illegal ids: poker 'check' else 'fold'
+        (envs/leducholdem.py:81-96), UNO a uniform legal action from the global np.random (envs/uno.py:39-45)."""
+        if self.name in ('leduc-holdem', 'limit-holdem'):
+            legal = [self.actions[a] for a in self._get_legal_actions()]
+            if self.actions[action_id] not in legal:
+                return 'check' if 'check' in legal else 'fold'
+        elif self.name == 'uno':
+            legal = list(self._get_legal_actions().keys())
+            if action_id not in legal:
+                return self.actions[int(np.random.choice(legal))]
+        return self.actions[action_id]
+
     def get_perfect_information(self):
-        raise NotImplementedError
+        """envs/<game>.py get_perfect_information from the packed device state.  Exact for limit-holdem; Leduc
+        cards are reported by rank only (the packed state drops the suit, which never influences play); the other
+        games report the fields that do not need a decoder (current player, legal actions)."""
+        self._vec.get_state(None)
+        pid = self.get_player_id()
+        legal = [self.actions[a] for a in self._dict_from(self._vec.obs[0], self._vec.mask[0], pid)['legal_actions']]
+        info = {'current_player': pid, 'legal_actions': legal}
+        w = [int(x) & 0xffffffff for x in self._vec.state[:, 0].cpu().tolist()][3:]       # game words after the header
+        if self.name == 'leduc-holdem':
+            g = w[0]
+            info['chips'] = [(g >> 7) & 15, (g >> 11) & 15]
+            info['hand_cards'] = ['JQK'[g & 3], 'JQK'[(g >> 2) & 3]]
+            info['public_card'] = 'JQK'[(g >> 4) & 3] if (g >> 6) & 1 else None
+            info['current_round'] = (g >> 28) & 3
+        elif self.name == 'limit-holdem':
+            cards = [(w[0] >> (6 * k)) & 63 for k in range(5)] + [(w[1] >> (6 * k)) & 63 for k in range(4)]
+            name = lambda c: 'SHDC'[c // 13] + 'A23456789TJQK'[c % 13]
+            rc = (w[2] >> 22) & 7
+            n_public = {0: 0, 1: 3, 2: 4}.get(rc, 5)
+            info['chips'] = [w[2] & 63, (w[2] >> 6) & 63]
+            info['hand_cards'] = [[name(cards[0]), name(cards[2])], [name(cards[1]), name(cards[3])]]
+            info['public_card'] = [name(c) for c in cards[4:4 + n_public]] or None
+        return info
+
+    @property
+    def game(self):
+        """Minimal stand-in for ``env.game`` (the Python engine object does not exist: the game runs on the GPU)."""
+        return _GameView(self)
 
     # -- the rollout loop, env.py:120-169 verbatim in behaviour
     def run(self, is_training=False):
@@ -180,6 +228,31 @@ class Env:
         for pid in range(self.num_players):
             trajectories[pid].append(self.get_state(pid))
         return trajectories, self.get_payoffs()
+
+
+class _GameView:
+    """The few ``env.game`` methods the reference's rollout helpers and tests call."""
+
+    def __init__(self, env):
+        self._env = env
+
+    def get_num_players(self):
+        return self._env.num_players
+
+    def get_num_actions(self):
+        return self._env.num_actions
+
+    def is_over(self):
+        return self._env.is_over()
+
+    def get_player_id(self):
+        return self._env.get_player_id()
+
+    def get_legal_actions(self):
+        return [self._env.actions[a] for a in self._env._get_legal_actions()]
+
+    def get_payoffs(self):
+        return self._env.get_payoffs()
 
 
 class RandomAgent:
