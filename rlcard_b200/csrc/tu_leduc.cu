@@ -1,8 +1,215 @@
 // tu_leduc.cu -- kernel instantiations for Leduc (one translation unit per game: parallel nvcc)
 #include "game_poker.cuh"
 #include "kernels.cuh"
+#include <mutex>
 namespace rlc {
+
+// ==========================================================================================
+// Table-driven Leduc rollout.  Everything about a Leduc state except the three cards is one of < 256
+// "betting states" (round, pointer, raise counters, chips, folds); the transition function over them is
+// tabulated ONCE per device by running the register-level engine (Leduc::step, game_poker.cuh) over every
+// reachable state, so table == engine by construction.  The rollout then costs two shared-memory
+// lookups per env-step instead of the branchy engine.
+//   entry.x = the packed state word (game_poker.cuh layout) with the card bits [0:7) replaced by
+//             legal mask [0:4) | is_over [4]
+//   entry.y = next state id for actions call, raise, fold, check (one byte each)
+// State ids 0 / 1 are the first states of an episode with seat 0 / 1 as small blind.
+// ==========================================================================================
+constexpr int kFsmMax = 256;
+static uint2 *g_fsm[64];
+static std::mutex g_fsm_mu;
+
+__device__ __forceinline__ uint32_t fsm_key(const Leduc &g) {
+    return (g.chips0 << 7) | (g.chips1 << 11) | (g.r.raised0 << 15) | (g.r.raised1 << 19) | (g.r.have_raised << 23) |
+           (g.r.not_raise_num << 25) | (g.r.pointer << 27) | (g.rc << 28) | (g.fold0 << 30) | ((uint32_t)g.fold1 << 31);
+}
+__device__ __forceinline__ void fsm_unkey(Leduc &g, uint32_t w) {
+    g.hand0 = g.hand1 = g.pub = 0; g.pub_dealt = 0;
+    g.chips0 = bf_get(w, 7, 4); g.chips1 = bf_get(w, 11, 4); g.r.raised0 = bf_get(w, 15, 4); g.r.raised1 = bf_get(w, 19, 4);
+    g.r.have_raised = bf_get(w, 23, 2); g.r.not_raise_num = bf_get(w, 25, 2); g.r.pointer = bf_get(w, 27, 1);
+    g.rc = bf_get(w, 28, 2); g.fold0 = bf_get(w, 30, 1); g.fold1 = bf_get(w, 31, 1);
+}
+// single thread: breadth-first closure of the two initial states under Leduc::step
+__global__ void k_leduc_build_fsm(uint2 *tab, int *count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ uint32_t keys[kFsmMax];
+    int n = 0;
+    for (int sb = 0; sb < 2; sb++) {                         // game.py:74-95 with the blind draw fixed
+        Leduc g; fsm_unkey(g, 0);
+        g.chips0 = sb == 0 ? 1 : 2; g.chips1 = sb == 0 ? 2 : 1;
+        g.r.start(sb, g.chips0, g.chips1);
+        keys[n++] = fsm_key(g);
+    }
+    ChancePhilox none; none.init(0, 0);
+    for (int i = 0; i < n; i++) {
+        Leduc g; fsm_unkey(g, keys[i]);
+        uint32_t m[1]; g.legal(m);
+        uint32_t x = keys[i] | (m[0] & 15u) | (g.over() ? 16u : 0u), y = 0;
+        if (!g.over()) {
+            for (int a = 0; a < 4; a++) {
+                if (!((m[0] >> a) & 1u)) continue;
+                Leduc h; fsm_unkey(h, keys[i]);
+                int err = 0;
+                h.step(a, none, err);
+                const uint32_t k2 = fsm_key(h);
+                int j = 0;
+                while (j < n && keys[j] != k2) j++;
+                if (j == n) { if (n >= kFsmMax) { *count = -1; return; } keys[n++] = k2; }
+                y |= (uint32_t)j << (8 * a);
+            }
+        }
+        tab[i] = make_uint2(x, y);
+    }
+    *count = n;
+}
+static cudaError_t leduc_fsm(const uint2 **out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(g_fsm_mu);
+    if (!g_fsm[dev]) {
+        uint2 *tab = nullptr; int *cnt = nullptr, h = 0;
+        if ((e = cudaMalloc(&tab, sizeof(uint2) * kFsmMax)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&cnt, sizeof(int))) != cudaSuccess) return e;
+        cudaMemset(tab, 0, sizeof(uint2) * kFsmMax);
+        k_leduc_build_fsm<<<1, 32>>>(tab, cnt);
+        e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
+        cudaFree(cnt);
+        if (e != cudaSuccess) return e;
+        if (h <= 0) return cudaErrorUnknown;
+        g_fsm[dev] = tab;
+    }
+    *out = g_fsm[dev];
+    return cudaSuccess;
+}
+
+// The Env.run loop with random agents (env.py:120-169) over the tabulated engine: same trajectory, state
+// words and Philox draws as k_rollout<Leduc, ChancePhilox, ObsT, 64, true>.
+template <class ObsT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, const uint2 *__restrict__ gtab) {
+    extern __shared__ uint4 smem_raw[];
+    constexpr int kRowBytes = Leduc::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = BLOCK * kRowBytes;
+    uint2 *stab = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
+    uint8_t *lut = reinterpret_cast<uint8_t *>(stab + kFsmMax);
+    for (int j = threadIdx.x; j < kFsmMax; j += BLOCK) stab[j] = gtab[j];
+    Leduc::fill_shared(lut, threadIdx.x, BLOCK);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
+    if (warp_env0 >= p.n) return;
+    const size_t i = warp_env0 + lane;
+    const bool valid = i < p.n;
+    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * Leduc::OBS;
+    ObsT *row = tile + lane * Leduc::OBS;
+    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    __syncwarp();
+
+    EnvHeader h; ChancePhilox ch;
+    uint32_t cards = 0, sid = 0;           // hand0 | hand1 << 2 | public << 4 ; betting-state id
+    if (valid) {
+        h.load(p.state, p.n, i);
+        ch.init(p.seed, p.env_id_base + (uint32_t)i);
+        if (h.episode == 0) {              // first deal: a reset outside a step
+            ch.begin_reset(h.k);
+            cards = lut[ch.chain(120u)];
+            sid = ch.chain(2u);
+            h.episode = 1; h.t = 0;
+        } else {
+            const uint32_t w = p.state[kHeaderWords * p.n + i];
+            cards = w & 63u;
+            const uint32_t key = w & ~127u;
+            for (int j = 0; j < kFsmMax; j++) if ((stab[j].x & ~127u) == key) { sid = (uint32_t)j; break; }
+        }
+    }
+    uint2 e = stab[sid];
+    uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
+    const size_t obs_step = p.n * (size_t)kRowBytes;
+    const bool full_warp = nvalid == 32;
+    size_t rowi = i;
+    for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
+        const uint32_t legal = e.x & 15u, seat = (e.x >> 27) & 1u, rc = (e.x >> 28) & 3u;
+        const uint32_t c0 = (e.x >> 7) & 15u, c1 = (e.x >> 11) & 15u;
+        if (valid) {                       // envs/leducholdem.py:41-71
+            row[(cards >> (2 * seat)) & 3u] = (ObsT)1;
+            if (rc) row[3 + ((cards >> 4) & 3u)] = (ObsT)1;
+            row[6 + (seat ? c1 : c0)] = (ObsT)1;
+            row[21 + (seat ? c0 : c1)] = (ObsT)1;
+        }
+        __syncwarp();
+        if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+        else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        __syncwarp();
+        if (valid) {
+            __stcs(reinterpret_cast<uint32_t *>(p.t_mask) + rowi,
+                   (legal & 1u) | ((legal & 2u) << 7) | ((legal & 4u) << 14) | ((legal & 8u) << 21));
+            __stcs(p.t_player + rowi, (int)seat);
+            const uint32_t word = ch.begin_step(h.k);
+            const uint32_t cnt = (uint32_t)__popc(legal);
+            const int kth = (int)__umulhi(word, cnt);
+            ch.seed_chain(word, cnt);
+            uint32_t mm = legal;
+            if (kth > 0) mm &= mm - 1;
+            if (kth > 1) mm &= mm - 1;
+            if (kth > 2) mm &= mm - 1;
+            const int a = __ffs(mm) - 1;
+            __stcs(p.t_action + rowi, a);
+            sid = (e.y >> (8 * a)) & 255u;
+            e = stab[sid];
+            h.t++; h.k++;
+            const bool over = (e.x >> 4) & 1u;
+            float2 pay = make_float2(0.f, 0.f);
+            if (over) {                    // judger.py:12-64 in quarter-chip integers (see Leduc::payoffs)
+                const int f0 = (e.x >> 30) & 1u, f1 = e.x >> 31, ch0 = (e.x >> 7) & 15u, ch1 = (e.x >> 11) & 15u;
+                const int h0 = cards & 3u, h1 = (cards >> 2) & 3u, pb = (cards >> 4) & 3u;
+                const bool dealt = ((e.x >> 28) & 3u) != 0u;
+                int w0, w1;
+                if (f0 + f1 == 1) { w0 = f1; w1 = f0; }
+                else if (dealt && h0 == pb) { w0 = 1; w1 = 0; }
+                else if (dealt && h1 == pb) { w0 = 0; w1 = 1; }
+                else { w0 = h0 >= h1; w1 = h1 >= h0; }
+                const int tie = w0 & w1;
+                const int q0 = tie ? ch1 - ch0 : (w0 ? 2 * ch1 : -2 * ch0);
+                const int q1 = tie ? ch0 - ch1 : (w1 ? 2 * ch0 : -2 * ch1);
+                pay = make_float2((float)q0 * 0.25f, (float)q1 * 0.25f);
+                cards = lut[ch.chain(120u)];                 // game.py:46-95: the next episode, same step's draws
+                sid = ch.chain(2u);
+                e = stab[sid];
+                h.episode++; h.t = 0;
+            }
+            p.t_done[rowi] = over ? 1 : 0;
+            __stcs(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+        }
+    }
+    if (valid) {
+        h.store(p.state, p.n, i);
+        const uint32_t rc = (e.x >> 28) & 3u;
+        p.state[kHeaderWords * p.n + i] = (e.x & ~127u) | cards | (rc ? 64u : 0u);
+    }
+}
+
+template <class ObsT>
+static cudaError_t launch_leduc_fsm(const KParams &p, cudaStream_t s) {
+    const uint2 *tab = nullptr;
+    cudaError_t e = leduc_fsm(&tab);
+    if (e != cudaSuccess) return e;
+    constexpr int BLOCK = 64;
+    const size_t smem = (size_t)BLOCK * Leduc::OBS * sizeof(ObsT) + sizeof(uint2) * kFsmMax + 128;
+    k_rollout_leduc_fsm<ObsT, BLOCK><<<(unsigned)((p.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(p, tab);
+    return cudaGetLastError();
+}
+
 cudaError_t dispatch_leduc(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t s) {
+    // the bench / training case (throughput mode, every trajectory stream, aligned rows) runs the tabulated engine
+    if (op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & 0x100) && p.t_obs && p.t_mask && p.t_action &&
+        p.t_player && p.t_done && p.t_payoffs) {
+        if (obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Leduc::OBS)) & 15u) == 0)
+            return launch_leduc_fsm<uint8_t>(p, s);
+        if (obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Leduc::OBS * 4)) & 15u) == 0)
+            return launch_leduc_fsm<float>(p, s);
+    }
     return dispatch_game<Leduc>(op, chance, obs_dtype, p, s);
 }
 
