@@ -154,6 +154,32 @@ int rlc_judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint
  * (255 = empty slot), targets uint8 [n] -> obs uint8 [n][240] ([4][4][15] planes of envs/uno.py:24-33) */
 int rlc_encode_uno(const uint8_t *hands, const uint8_t *targets, int n, uint8_t *obs, void *stream);
 
+/* ---- the DMC actor's bookkeeping (rlcard/agents/dmc_agent/utils.py:97-155 `act`) ----
+ * A window of a rollout trajectory ([T][n] rows, auto reset) is folded into per-position row pools: one row per
+ * decision of position p with the state p saw, the feature of the action taken (env.get_action_feature: 54-d for
+ * DouDizhu, one-hot over num_actions otherwise), target = p's payoff at the end of that episode, done = p's last
+ * decision of the episode, episode_return = payoff when done else 0.  Decisions of episodes still running at
+ * the end of the window wait in the per-env open-episode store and are emitted by a later call.  All memory is
+ * caller-owned; open_len / out_count / overflow must be zero-initialised before the first call. */
+typedef struct rlc_dmc_buffers {
+    void *open_obs;                 /* [n][open_capacity][obs row bytes]                                     */
+    int32_t *open_action;           /* [n][open_capacity]                                                    */
+    int8_t *open_player;            /* [n][open_capacity]                                                    */
+    int32_t *open_len;              /* [n]                                                                   */
+    int32_t open_capacity;          /* >= longest episode (decisions of all seats)                            */
+    void *out_state[RLC_MAX_PLAYERS];            /* [out_capacity][obs row bytes], dtype of the trajectory    */
+    int8_t *out_action[RLC_MAX_PLAYERS];         /* [out_capacity][F], F = 54 (doudizhu) or num_actions       */
+    float *out_target[RLC_MAX_PLAYERS];          /* [out_capacity]                                            */
+    float *out_episode_return[RLC_MAX_PLAYERS];  /* [out_capacity]                                            */
+    uint8_t *out_done[RLC_MAX_PLAYERS];          /* [out_capacity]                                            */
+    int32_t *out_count;             /* [RLC_MAX_PLAYERS] rows used per position (in/out, device)              */
+    int32_t out_capacity;
+    int32_t *overflow;              /* [1] device flag: 1 a pool was full (rows dropped), 2 open store too small */
+} rlc_dmc_buffers;
+
+int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_dmc_buffers *b,
+                    void *stream);
+
 /* number of kernels this library has launched in this process (bench bookkeeping) */
 int64_t rlc_launch_count(void);
 

@@ -37,9 +37,18 @@ class RlcTrajectory(C.Structure):
                 ('done', C.c_void_p), ('payoffs', C.c_void_p)]
 
 
+class RlcDmcBuffers(C.Structure):
+    _fields_ = [('open_obs', C.c_void_p), ('open_action', C.c_void_p), ('open_player', C.c_void_p), ('open_len', C.c_void_p),
+                ('open_capacity', C.c_int32),
+                ('out_state', C.c_void_p * RLC_MAX_PLAYERS), ('out_action', C.c_void_p * RLC_MAX_PLAYERS),
+                ('out_target', C.c_void_p * RLC_MAX_PLAYERS), ('out_episode_return', C.c_void_p * RLC_MAX_PLAYERS),
+                ('out_done', C.c_void_p * RLC_MAX_PLAYERS), ('out_count', C.c_void_p), ('out_capacity', C.c_int32),
+                ('overflow', C.c_void_p)]
+
+
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
            'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
-           'rlc_judge_doudizhu', 'rlc_encode_uno']
+           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect']
 
 _LIB = None
 
@@ -70,6 +79,7 @@ def lib():
         L.rlc_judge_leduc.argtypes = [vp, i32, vp, vp]
         L.rlc_judge_doudizhu.argtypes = [vp, vp, i32, vp, vp]
         L.rlc_encode_uno.argtypes = [vp, vp, i32, vp, vp]
+        L.rlc_dmc_collect.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcDmcBuffers), vp]
         _LIB = L
     return _LIB
 

@@ -24,6 +24,9 @@ cudaError_t dispatch_doudizhu(int, int, int, const KParams &, cudaStream_t);
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes);
 cudaError_t judge_doudizhu(const uint8_t *, const int32_t *, int, uint32_t *, cudaStream_t);
 #endif
+#ifdef RLC_HAVE_DMC
+cudaError_t dmc_collect(const rlc_info &, const rlc_trajectory *, int, int, int, const rlc_dmc_buffers *, cudaStream_t);
+#endif
 }  // namespace rlc
 
 static thread_local char g_err[512] = "";
@@ -177,6 +180,23 @@ int rlc_encode_uno(const uint8_t *hands, const uint8_t *targets, int n, uint8_t 
     return judged(rlc::encode_uno(hands, targets, n, obs, reinterpret_cast<cudaStream_t>(stream)));
 #else
     return fail(RLC_ENOTIMPL, "uno is not in this build");
+#endif
+}
+
+int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_dmc_buffers *b, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!traj || !b || T <= 0 || n <= 0) return fail(RLC_EINVAL, "null buffers or empty window");
+    if (!traj->obs || !traj->action || !traj->player || !traj->done || !traj->payoffs)
+        return fail(RLC_EINVAL, "the DMC collector needs the obs, action, player, done and payoffs streams");
+    if (!b->open_obs || !b->open_action || !b->open_player || !b->open_len || !b->out_count || !b->overflow ||
+        b->open_capacity <= 0 || b->out_capacity <= 0) return fail(RLC_EINVAL, "incomplete rlc_dmc_buffers");
+    for (int p = 0; p < kInfo[game_id].num_players; p++)
+        if (!b->out_state[p] || !b->out_action[p] || !b->out_target[p] || !b->out_episode_return[p] || !b->out_done[p])
+            return fail(RLC_EINVAL, "rlc_dmc_buffers: position %d pools missing", p);
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::dmc_collect(kInfo[game_id], traj, obs_dtype, T, n, b, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "the DMC collector is not in this build");
 #endif
 }
 

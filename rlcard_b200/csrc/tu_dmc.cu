@@ -1,0 +1,145 @@
+// tu_dmc.cu -- the DMC actor's bookkeeping on device (rlcard/agents/dmc_agent/utils.py:97-155 `act`).
+//
+// The reference actor runs whole episodes with env.run(is_training=True) and appends, per position p, one
+// row per decision of p: state (int8 obs p saw), action (int8 feature of the action taken,
+// env.get_action_feature), target (payoff of p at the end of that episode), done (this was p's last decision
+// of the episode) and episode_return (payoff when done else 0); rows are handed to the learner in chunks of
+// T.  Here a window of a VecEnv rollout trajectory ([T][n] rows of obs / action / player / done / payoffs,
+// auto reset) is folded into per-position row pools in HBM.  One warp per env walks its T rows; rows of an
+// episode that has not ended inside the window wait in the env's "open episode" store and are emitted by
+// the window in which the episode ends, so no decision is ever dropped or duplicated.
+#include <cstring>
+#include "common.cuh"
+#include "../../include/rlcard_b200.h"
+
+namespace rlc {
+
+const uint64_t *doudizhu_rows_on_device(int device);     // tu_doudizhu.cu (nullptr before rlc_upload_tables)
+
+struct DmcParams {
+    const uint8_t *t_obs; const int32_t *t_action, *t_player; const uint8_t *t_done; const float *t_payoffs;
+    int T, n, P, obs_stride /* bytes per obs row */, F, num_actions;
+    const uint64_t *ddz_rows;                       // DouDizhu: 54-d features from the action table, else one-hot
+    uint8_t *open_obs; int32_t *open_action; int8_t *open_player; int32_t *open_len; int Lmax;
+    uint8_t *out_state[RLC_MAX_PLAYERS]; int8_t *out_action[RLC_MAX_PLAYERS]; float *out_target[RLC_MAX_PLAYERS];
+    float *out_return[RLC_MAX_PLAYERS]; uint8_t *out_done[RLC_MAX_PLAYERS];
+    int32_t *out_count; int cap; int32_t *overflow;
+};
+
+// warp copy of one obs row (obs_stride bytes, a multiple of 4)
+__device__ __forceinline__ void copy_row(uint8_t *dst, const uint8_t *src, int nbytes, int lane) {
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 15u) == 0) {
+        for (int c = lane; c < (nbytes >> 4); c += 32) reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(src)[c];
+    } else {
+        for (int c = lane; c < nbytes; c += 32) dst[c] = src[c];
+    }
+}
+// env.get_action_feature: envs/doudizhu.py:136-167 (54-d thermometer of the action's cards) or the default
+// one-hot over num_actions (envs/env.py:217-226)
+__device__ __forceinline__ void write_feature(const DmcParams &q, int8_t *dst, int action, int lane) {
+    if (q.ddz_rows) {
+        const uint64_t c = q.ddz_rows[action];
+        for (int e = lane; e < 54; e += 32) {
+            int v;
+            if (e < 52) v = (int)((c >> (4 * (e >> 2))) & 15ull) > (e & 3);
+            else v = ((c >> (4 * (e - 39))) & 15ull) != 0;
+            dst[e] = (int8_t)v;
+        }
+    } else {
+        for (int e = lane; e < q.F; e += 32) dst[e] = (int8_t)(e == action ? 1 : 0);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_dmc_collect(const DmcParams q) {
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (env >= q.n) return;
+    const size_t S = (size_t)q.obs_stride;
+    uint8_t *oobs = q.open_obs + (size_t)env * q.Lmax * S;
+    int32_t *oact = q.open_action + (size_t)env * q.Lmax;
+    int8_t *opl = q.open_player + (size_t)env * q.Lmax;
+    int len0 = q.open_len[env];
+    int t_start = 0;
+    for (int t = 0; t < q.T; t++) {
+        if (!q.t_done[(size_t)t * q.n + env]) continue;
+        // an episode ends at row t: its decisions are open[0, len0) followed by window rows [t_start, t]
+        const int nwin = t - t_start + 1, total = len0 + nwin;
+        float pay[RLC_MAX_PLAYERS]; int cnt[RLC_MAX_PLAYERS], base[RLC_MAX_PLAYERS], seen[RLC_MAX_PLAYERS];
+#pragma unroll
+        for (int p = 0; p < RLC_MAX_PLAYERS; p++) {
+            pay[p] = p < q.P ? q.t_payoffs[((size_t)t * q.n + env) * q.P + p] : 0.f;
+            cnt[p] = 0; seen[p] = 0;
+        }
+        for (int r0 = 0; r0 < total; r0 += 32) {              // decisions per position
+            const int r = r0 + lane;
+            int pl = -1;
+            if (r < total) pl = r < len0 ? (int)opl[r] : q.t_player[(size_t)(t_start + r - len0) * q.n + env];
+#pragma unroll
+            for (int p = 0; p < RLC_MAX_PLAYERS; p++) cnt[p] += __popc(__ballot_sync(0xffffffffu, pl == p));
+        }
+#pragma unroll
+        for (int p = 0; p < RLC_MAX_PLAYERS; p++) {          // reserve rows in the pools
+            int b = 0;
+            if (lane == 0 && cnt[p] > 0) b = atomicAdd(q.out_count + p, cnt[p]);
+            base[p] = __shfl_sync(0xffffffffu, b, 0);
+        }
+        for (int r = 0; r < total; r++) {                     // emit in episode order
+            const bool from_open = r < len0;
+            const size_t wrow = (size_t)(t_start + r - len0) * q.n + env;
+            const int pl = from_open ? (int)opl[r] : q.t_player[wrow];
+            const int act = from_open ? oact[r] : q.t_action[wrow];
+            int b = 0, c = 0, s = 0; float py = 0.f;
+#pragma unroll
+            for (int p = 0; p < RLC_MAX_PLAYERS; p++) if (pl == p) { b = base[p]; c = cnt[p]; s = seen[p]; py = pay[p]; seen[p]++; }
+            const int slot = b + s;
+            if (slot >= q.cap) { if (lane == 0) *q.overflow = 1; continue; }
+            const bool last = s == c - 1;
+            uint8_t *st = nullptr; int8_t *ac = nullptr; float *tg = nullptr, *er = nullptr; uint8_t *dn = nullptr;
+#pragma unroll
+            for (int p = 0; p < RLC_MAX_PLAYERS; p++)
+                if (pl == p) { st = q.out_state[p]; ac = q.out_action[p]; tg = q.out_target[p]; er = q.out_return[p]; dn = q.out_done[p]; }
+            copy_row(st + (size_t)slot * S, from_open ? oobs + (size_t)r * S : q.t_obs + wrow * S, (int)S, lane);
+            write_feature(q, ac + (size_t)slot * q.F, act, lane);
+            if (lane == 0) { tg[slot] = py; er[slot] = last ? py : 0.f; dn[slot] = last ? 1 : 0; }
+        }
+        len0 = 0; t_start = t + 1;
+    }
+    // decisions of the episode still running wait in the open store
+    const int tail = q.T - t_start;
+    if (len0 + tail > q.Lmax) { if (lane == 0) *q.overflow = 2; }
+    else {
+        for (int r = 0; r < tail; r++) {
+            const size_t wrow = (size_t)(t_start + r) * q.n + env;
+            copy_row(oobs + (size_t)(len0 + r) * S, q.t_obs + wrow * S, (int)S, lane);
+            if (lane == 0) { oact[len0 + r] = q.t_action[wrow]; opl[len0 + r] = (int8_t)q.t_player[wrow]; }
+        }
+        len0 += tail;
+    }
+    if (lane == 0) q.open_len[env] = len0;
+}
+
+cudaError_t dmc_collect(const rlc_info &info, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_dmc_buffers *b, cudaStream_t s) {
+    DmcParams q; memset(&q, 0, sizeof q);
+    q.t_obs = reinterpret_cast<const uint8_t *>(traj->obs); q.t_action = traj->action; q.t_player = traj->player;
+    q.t_done = traj->done; q.t_payoffs = traj->payoffs;
+    q.T = T; q.n = n; q.P = info.num_players; q.obs_stride = info.obs_stride * (obs_dtype == RLC_F32 ? 4 : 1); q.num_actions = info.num_actions;
+    q.F = info.game_id == RLC_DOUDIZHU ? 54 : info.num_actions;
+    if (info.game_id == RLC_DOUDIZHU) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        q.ddz_rows = doudizhu_rows_on_device(dev);
+        if (!q.ddz_rows) return cudaErrorNotReady;
+    }
+    q.open_obs = reinterpret_cast<uint8_t *>(b->open_obs); q.open_action = b->open_action; q.open_player = b->open_player;
+    q.open_len = b->open_len; q.Lmax = b->open_capacity;
+    for (int p = 0; p < info.num_players; p++) {
+        q.out_state[p] = reinterpret_cast<uint8_t *>(b->out_state[p]); q.out_action[p] = b->out_action[p];
+        q.out_target[p] = b->out_target[p]; q.out_return[p] = b->out_episode_return[p]; q.out_done[p] = b->out_done[p];
+    }
+    q.out_count = b->out_count; q.cap = b->out_capacity; q.overflow = b->overflow;
+    k_dmc_collect<<<(n + 3) / 4, 128, 0, s>>>(q);
+    return cudaGetLastError();
+}
+
+}  // namespace rlc

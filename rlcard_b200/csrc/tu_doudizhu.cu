@@ -11,6 +11,10 @@ struct DdzBlobHeader {
 static DdzTables g_tab[64];
 static void *g_dev_blob[64];
 
+const uint64_t *doudizhu_rows_on_device(int device) {
+    return (device >= 0 && device < 64 && g_dev_blob[device]) ? g_tab[device].rows : nullptr;
+}
+
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     if (device < 0 || device >= 64 || !blob || nbytes < sizeof(DdzBlobHeader)) return cudaErrorInvalidValue;
     DdzBlobHeader h; memcpy(&h, blob, sizeof h);
