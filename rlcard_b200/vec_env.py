@@ -309,11 +309,4 @@ def random_policy(generator=None):
     return policy
 
 
-def vec_tournament(env, num_steps):
-    """rlcard.utils.tournament (utils/utils.py:200-225) over a VecEnv with on-device random agents:
-    mean payoff per seat over the episodes finished in num_steps rollout steps."""
-    tr = env.rollout_random(num_steps, out=env.alloc_trajectory(num_steps, obs=False, mask=False))
-    done = tr['done'].bool()
-    n = int(done.sum().item())
-    tot = (tr['payoffs'] * done.unsqueeze(-1)).sum((0, 1)).double()
-    return (tot / max(n, 1)).tolist(), n
+from .utils import vec_tournament  # noqa: E402,F401  (kept importable from here)

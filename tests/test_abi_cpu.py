@@ -65,3 +65,27 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in txt and 'liboracle' not in txt and 'orc.h' not in txt, f
+
+
+def test_reorganize_matches_reference_outputs():
+    """rlcard/utils/utils.py:153-179 on fixtures produced by the live reference (tests/golden/make_reorganize_golden.py)."""
+    import json
+    from rlcard_b200.utils import reorganize
+    cases = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'reorganize.json')))
+    assert len(cases) >= 20
+    for c in cases:
+        assert reorganize(c['trajectories'], c['payoffs']) == c['expected']
+
+
+def test_tournament_averages_over_games():
+    from rlcard_b200.utils import tournament
+
+    class FakeEnv:
+        num_players = 2
+        calls = 0
+
+        def run(self, is_training=False):
+            FakeEnv.calls += 1
+            import numpy as np
+            return None, np.array([1.0, -1.0]) if FakeEnv.calls % 2 else [np.array([0.0, 0.0]), np.array([2.0, -2.0])]
+    assert tournament(FakeEnv(), 6) == [1.0, -1.0]
