@@ -157,6 +157,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=10, help='bench steps (T-step host rollouts) of the e2e leg')
     ap.add_argument('--e2e-chunk', type=int, default=16, help='env-steps per rlc_rollout_random launch in the e2e leg')
     ap.add_argument('--e2e-step-api-steps', type=int, default=100, help='env-steps of the per-step host-agent leg')
+    ap.add_argument('--dmc-steps', type=int, default=0, help='bench steps of the optional DMC-collector leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.envs is None:
@@ -320,6 +321,31 @@ def main():
                             'rlc_step -> D2H obs+mask+player+done+payoffs (pinned), synchronous round trip'}
         env2.check_errors()
 
+    # ---- optional: the DMC actor data path (config 5): rollout window + rlc_dmc_collect into per-position pools
+    dmc = None
+    if args.dmc_steps > 0:
+        from rlcard_b200.dmc import DMCCollector
+        env3 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 3, env_id_base=rank * E, obs_dtype=odt)
+        env3.reset()
+        col = DMCCollector(env3, pool_rows=E * T + E * 8)
+        traj3 = env3.alloc_trajectory(T)
+        for _ in range(W):
+            col.collect_random(T, traj3); col.count.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rows = 0
+        for _ in range(args.dmc_steps):
+            col.collect_random(T, traj3)
+            rows += sum(col.sizes()); col.count.zero_()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        dmc = {'value': world * E * T * args.dmc_steps / (ms * 1e-3), 'unit': UNIT, 'steps': args.dmc_steps,
+               'rows_per_step': rows / args.dmc_steps, 'ms_per_step': ms / args.dmc_steps,
+               'what': 'rlc_rollout_random (T=%d) + rlc_dmc_collect into per-position (state int8, action feature, target, '
+                       'done, episode_return) pools, device resident' % T}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -357,6 +383,8 @@ def main():
         line['e2e'] = e2e
     if e2e_step:
         line['e2e_step_api'] = e2e_step
+    if dmc:
+        line['dmc'] = dmc
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, dt, steps, n = cpu_port_run(args.game, E, T, args.seed, threads)
