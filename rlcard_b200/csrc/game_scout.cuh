@@ -85,21 +85,33 @@ struct Scout {
         rank = (len > 1 && !group) ? max(first, last) : first;
         return len == 1 || group || asc || desc;
     }
-    // round.py:225-260: 204-bit legal set of the current player, identical in all lanes
+    // round.py:225-260: 204-bit legal set of the current player, identical in all lanes.
+    // Valid play segments (utils/utils.py:17-67) are read off three adjacency masks of the hand (bit i: card i+1
+    // equals / is one above / is one below card i, built with one ballot each): slice [s, s+len) is a group, an
+    // ascending or a descending run iff the mask has len-1 consecutive ones from bit s.
     __device__ void legal_words(uint32_t (&m)[7], int lane) {
         const uint64_t T = sel(ht, cur);
         const int n = seli(hl, cur);
         int ttype = 0, trank = 0;
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
         const bool can_scout = tl > 0 && n < 16;
+        const int a = nib(T, lane & 15), b = nib(T, (lane + 1) & 15);
+        const bool adj = lane < 15 && lane + 1 < n;
+        const uint32_t eqm = __ballot_sync(kFull, adj && b == a);
+        const uint32_t upm = __ballot_sync(kFull, adj && b == a + 1);
+        const uint32_t dnm = __ballot_sync(kFull, adj && b == a - 1);
 #pragma unroll
         for (int r = 0; r < 7; r++) {
             const int id = lane + 32 * r;
             bool ok = false;
             if (r < 5 && id < 136) {
                 const int code = (int)((segtab >> (8 * r)) & 255ull), s = code & 15, e = (code >> 4) + 1, len = e - s;
-                int type, rank;
-                const bool valid = segment(T, s, len, type, rank);
+                const int first = nib(T, s);
+                const int req = __ffs((int)~(eqm >> s)) - 1, rup = __ffs((int)~(upm >> s)) - 1, rdn = __ffs((int)~(dnm >> s)) - 1;
+                const bool group = len - 1 <= req, asc = len - 1 <= rup, desc = len - 1 <= rdn;
+                const bool valid = len == 1 || group || asc || desc;
+                const int type = len == 1 ? 0 : (group ? 2 : 1);
+                const int rank = (len > 1 && !group) ? (asc ? first + len - 1 : first) : first;       // run: max(first, last)
                 const bool stronger = tl == 0 || len > tl || (len == tl && (type > ttype || (type == ttype && rank > trank)));   // round.py:262-295
                 ok = e <= n && valid && stronger;
             }
