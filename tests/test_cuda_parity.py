@@ -241,3 +241,62 @@ def test_illegal_action_fallback_and_noop():
     env.step(torch.full((64,), 3, dtype=torch.int32, device='cuda'))      # 'check' is illegal for the small blind
     assert bool((env.err & 4).all())                                       # -> fold fallback (envs/leducholdem.py:90-96)
     assert bool(env.done.all())
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_partial_streams_and_unaligned_batches(game):
+    """Kernel variants: rollouts that request only some trajectory streams (generic instantiation with null checks),
+    and batch sizes whose obs rows are not 16-byte aligned (byte-wise flush; for Leduc the register engine instead of
+    the tabulated one) must produce the same envs as the full, aligned launch (Philox streams are keyed by env id)."""
+    T, seed = 24, 99
+    n_full = 256
+    full = rlcard_b200.VecEnv(game, n_full, seed=seed)
+    full.reset()
+    ref = full.rollout_random(T)
+    # (1) only action / done / payoffs requested
+    lean = rlcard_b200.VecEnv(game, n_full, seed=seed)
+    lean.reset()
+    out = lean.rollout_random(T, out=lean.alloc_trajectory(T, obs=False, mask=False))
+    for k in ('action', 'player', 'done', 'payoffs'):
+        assert torch.equal(out[k], ref[k]), (game, k)
+    assert torch.equal(lean.state, full.state)
+    # (2) odd batch size: envs [0, 131) of the same id range
+    n_odd = 131
+    odd = rlcard_b200.VecEnv(game, n_odd, seed=seed)
+    odd.reset()
+    out = odd.rollout_random(T)
+    for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+        assert torch.equal(out[k], ref[k][:, :n_odd]), (game, k)
+    odd.check_errors()
+
+
+def test_reset_mask_and_tape_errors():
+    """rlc_reset with a partial mask only deals the selected envs; an exhausted replay tape raises the error flag."""
+    env = rlcard_b200.VecEnv('leduc-holdem', 64, seed=1, auto_reset=False)
+    env.reset()
+    before = env.state.clone()
+    m = torch.zeros(64, dtype=torch.uint8, device='cuda'); m[::2] = 1
+    env.reset(m)
+    changed = (env.state != before).any(0).cpu().numpy()
+    assert not changed[1::2].any() and changed[::2].all()          # episode counter moved only where asked
+    rep = rlcard_b200.VecEnv('leduc-holdem', 4, mode='replay', auto_reset=False)
+    rep.set_tape(np.zeros((4, 2), np.uint8))                          # a Leduc deal needs 6 draws
+    rep.reset()
+    assert bool((rep.err & 1).all())
+    with pytest.raises(rlcard_b200.RlcError):
+        rep.check_errors()
+
+
+def test_illegal_actions_in_every_game_are_flagged():
+    """Out-of-range ids never corrupt the state: the per-env err flag 4 is raised and the env stays consistent
+    (the reference raises or substitutes, envs/leducholdem.py:90-96, envs/uno.py:39-45, games/scout/round.py:92)."""
+    for game in GAMES:
+        if game == 'blackjack':
+            continue                                                  # both ids are always legal
+        env = rlcard_b200.VecEnv(game, 32, seed=5, auto_reset=False)
+        env.reset()
+        env.step(torch.full((32,), env.num_actions + 7, dtype=torch.int32, device='cuda'))
+        assert bool((env.err & 4).all()), game
+        obs, mask, cur, done, pay = env.get_state(None)
+        m = mask if not env.mask_bitpacked else (mask != 0)
+        assert bool(((m != 0).sum(-1) >= 1)[~done.bool()].all()), game
