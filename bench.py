@@ -374,7 +374,7 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': traffic, 'kernel': 'k_rollout<%s>' % args.game, 'kernel_ms': kernel_ms,
+                     'traffic': traffic, 'kernel': ('k_rollout_leduc_fsm' if args.game == 'leduc-holdem' else ('k_wrollout<%s>' if info.threads_per_env == 32 else 'k_rollout<%s>') % args.game), 'kernel_ms': kernel_ms,
                      'bytes_per_env_step': b_step, 'peak_source': peak_src},
         'episodes_last_launch': float(stats[info.num_players].item()),
         'mean_payoff_per_seat': [float(x) / max(1.0, float(stats[info.num_players].item())) for x in stats[:info.num_players]],
