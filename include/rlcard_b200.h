@@ -180,6 +180,30 @@ typedef struct rlc_dmc_buffers {
 int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_dmc_buffers *b,
                     void *stream);
 
+/* ---- run_rl.py's data path: Env.run(is_training=True) + reorganize (rlcard/utils/utils.py:153-179) as a per-step
+ * stream of [state, action, reward, next_state (+ its legal mask), done] rows per seat.
+ * Call with phase 0 BEFORE rlc_step (b->obs / mask / cur_player hold the state the acting seat sees, `actions` the
+ * ids about to be applied) and with phase 1 AFTER it (done, payoffs, terminal_obs, and the mask of the post-step
+ * state; use rlc_step without RLC_AUTO_RESET but with RLC_TERMINAL_OBS, then rlc_reset the finished envs).
+ * pend_valid / out_count / overflow must be zero-initialised before the first call. */
+typedef struct rlc_rl_buffers {
+    void *pend_obs;                 /* [n][P][obs row bytes] last decision of each seat awaiting its next state */
+    int32_t *pend_action;           /* [n][P]                                                                 */
+    uint8_t *pend_valid;            /* [n][P]                                                                 */
+    void *out_state[RLC_MAX_PLAYERS];        /* [out_capacity][obs row bytes]                                  */
+    int32_t *out_action[RLC_MAX_PLAYERS];    /* [out_capacity]                                                 */
+    float *out_reward[RLC_MAX_PLAYERS];      /* [out_capacity] the seat's payoff on its last transition, else 0 */
+    void *out_next_state[RLC_MAX_PLAYERS];   /* [out_capacity][obs row bytes]                                  */
+    void *out_next_mask[RLC_MAX_PLAYERS];    /* [out_capacity][mask row bytes] legal set of next_state          */
+    uint8_t *out_done[RLC_MAX_PLAYERS];      /* [out_capacity]                                                 */
+    int32_t *out_count;             /* [RLC_MAX_PLAYERS] (in/out, device)                                      */
+    int32_t out_capacity;
+    int32_t *overflow;              /* [1]                                                                     */
+} rlc_rl_buffers;
+
+int rlc_rl_feed(int game_id, int phase, const rlc_buffers *env, const int32_t *actions, int n, const rlc_rl_buffers *b,
+                void *stream);
+
 /* number of kernels this library has launched in this process (bench bookkeeping) */
 int64_t rlc_launch_count(void);
 

@@ -46,9 +46,17 @@ class RlcDmcBuffers(C.Structure):
                 ('overflow', C.c_void_p)]
 
 
+class RlcRlBuffers(C.Structure):
+    _fields_ = [('pend_obs', C.c_void_p), ('pend_action', C.c_void_p), ('pend_valid', C.c_void_p),
+                ('out_state', C.c_void_p * RLC_MAX_PLAYERS), ('out_action', C.c_void_p * RLC_MAX_PLAYERS),
+                ('out_reward', C.c_void_p * RLC_MAX_PLAYERS), ('out_next_state', C.c_void_p * RLC_MAX_PLAYERS),
+                ('out_next_mask', C.c_void_p * RLC_MAX_PLAYERS), ('out_done', C.c_void_p * RLC_MAX_PLAYERS),
+                ('out_count', C.c_void_p), ('out_capacity', C.c_int32), ('overflow', C.c_void_p)]
+
+
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
            'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
-           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect']
+           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed']
 
 _LIB = None
 
@@ -79,6 +87,7 @@ def lib():
         L.rlc_judge_leduc.argtypes = [vp, i32, vp, vp]
         L.rlc_judge_doudizhu.argtypes = [vp, vp, i32, vp, vp]
         L.rlc_encode_uno.argtypes = [vp, vp, i32, vp, vp]
+        L.rlc_rl_feed.argtypes = [i32, i32, C.POINTER(RlcBuffers), vp, i32, C.POINTER(RlcRlBuffers), vp]
         L.rlc_dmc_collect.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcDmcBuffers), vp]
         _LIB = L
     return _LIB

@@ -26,6 +26,7 @@ cudaError_t judge_doudizhu(const uint8_t *, const int32_t *, int, uint32_t *, cu
 #endif
 #ifdef RLC_HAVE_DMC
 cudaError_t dmc_collect(const rlc_info &, const rlc_trajectory *, int, int, int, const rlc_dmc_buffers *, cudaStream_t);
+cudaError_t rl_feed(const rlc_info &, int, const rlc_buffers *, int, const int32_t *, int, const rlc_rl_buffers *, cudaStream_t);
 #endif
 }  // namespace rlc
 
@@ -197,6 +198,25 @@ int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int 
     return judged(rlc::dmc_collect(kInfo[game_id], traj, obs_dtype, T, n, b, reinterpret_cast<cudaStream_t>(stream)));
 #else
     return fail(RLC_ENOTIMPL, "the DMC collector is not in this build");
+#endif
+}
+
+int rlc_rl_feed(int game_id, int phase, const rlc_buffers *env, const int32_t *actions, int n, const rlc_rl_buffers *b, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!env || !b || n <= 0 || (phase != 0 && phase != 1)) return fail(RLC_EINVAL, "null buffers, n <= 0 or bad phase");
+    if (!env->obs || !env->mask || !env->cur_player) return fail(RLC_EINVAL, "rlc_rl_feed needs the env's obs, mask and cur_player");
+    if (phase == 0 && !actions) return fail(RLC_EINVAL, "phase 0 needs the actions about to be applied");
+    if (phase == 1 && (!env->done || !env->payoffs || !env->terminal_obs))
+        return fail(RLC_EINVAL, "phase 1 needs done, payoffs and terminal_obs (step with RLC_TERMINAL_OBS)");
+    if (!b->pend_obs || !b->pend_action || !b->pend_valid || !b->out_count || !b->overflow || b->out_capacity <= 0)
+        return fail(RLC_EINVAL, "incomplete rlc_rl_buffers");
+    for (int p = 0; p < kInfo[game_id].num_players; p++)
+        if (!b->out_state[p] || !b->out_action[p] || !b->out_reward[p] || !b->out_next_state[p] || !b->out_next_mask[p] || !b->out_done[p])
+            return fail(RLC_EINVAL, "rlc_rl_buffers: seat %d pools missing", p);
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::rl_feed(kInfo[game_id], phase, env, env->obs_dtype, actions, n, b, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "the transition collector is not in this build");
 #endif
 }
 

@@ -142,4 +142,84 @@ cudaError_t dmc_collect(const rlc_info &info, const rlc_trajectory *traj, int ob
     return cudaGetLastError();
 }
 
+
+// ==========================================================================================
+// run_rl.py's data path: Env.run(is_training=True) + reorganize (rlcard/utils/utils.py:153-179) as a per-step
+// stream.  For every seat the transitions [state, action, reward, next_state, done] pair each decision of the seat
+// with its next decision, the last one with the seat's terminal view and its payoff.  phase 0 runs BEFORE the env
+// step (the acting seat's previous decision gets its next_state = the state it sees now; the current decision
+// becomes pending), phase 1 AFTER it (finished envs close every pending decision against the terminal views).
+// ==========================================================================================
+struct RlParams {
+    const uint8_t *obs, *mask; const int32_t *player, *action; const uint8_t *done; const float *payoffs; const uint8_t *terminal_obs;
+    int n, P, S /* obs row bytes */, M /* mask row bytes */;
+    uint8_t *pend_obs; int32_t *pend_action; uint8_t *pend_valid;
+    uint8_t *o_state[RLC_MAX_PLAYERS], *o_next[RLC_MAX_PLAYERS], *o_mask[RLC_MAX_PLAYERS], *o_done[RLC_MAX_PLAYERS];
+    int32_t *o_action[RLC_MAX_PLAYERS]; float *o_reward[RLC_MAX_PLAYERS];
+    int32_t *count; int cap; int32_t *overflow;
+};
+
+__device__ __forceinline__ void rl_emit(const RlParams &q, int p, const uint8_t *state, int action, float reward,
+                                         const uint8_t *next, const uint8_t *mask, bool done, int lane) {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(q.count + p, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= q.cap) { if (lane == 0) *q.overflow = 1; return; }
+    uint8_t *st = nullptr, *nx = nullptr, *mk = nullptr, *dn = nullptr; int32_t *ac = nullptr; float *rw = nullptr;
+#pragma unroll
+    for (int k = 0; k < RLC_MAX_PLAYERS; k++)
+        if (k == p) { st = q.o_state[k]; nx = q.o_next[k]; mk = q.o_mask[k]; dn = q.o_done[k]; ac = q.o_action[k]; rw = q.o_reward[k]; }
+    copy_row(st + (size_t)slot * q.S, state, q.S, lane);
+    copy_row(nx + (size_t)slot * q.S, next, q.S, lane);
+    copy_row(mk + (size_t)slot * q.M, mask, q.M, lane);
+    if (lane == 0) { ac[slot] = action; rw[slot] = reward; dn[slot] = done ? 1 : 0; }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(128) k_rl_feed(const RlParams q) {
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (env >= q.n) return;
+    uint8_t *pobs = q.pend_obs + (size_t)env * q.P * q.S;
+    if (PHASE == 0) {
+        const int p = q.player[env], a = q.action[env];
+        if (a < 0 || p < 0 || p >= q.P) return;                       // env not stepped this time
+        const uint8_t *cur = q.obs + (size_t)env * q.S;
+        if (q.pend_valid[env * q.P + p])
+            rl_emit(q, p, pobs + (size_t)p * q.S, q.pend_action[env * q.P + p], 0.f, cur, q.mask + (size_t)env * q.M, false, lane);
+        __syncwarp();
+        copy_row(pobs + (size_t)p * q.S, cur, q.S, lane);
+        if (lane == 0) { q.pend_action[env * q.P + p] = a; q.pend_valid[env * q.P + p] = 1; }
+    } else {
+        if (!q.done[env]) return;
+        for (int p = 0; p < q.P; p++) {
+            if (!q.pend_valid[env * q.P + p]) continue;
+            rl_emit(q, p, pobs + (size_t)p * q.S, q.pend_action[env * q.P + p], q.payoffs[env * q.P + p],
+                    q.terminal_obs + ((size_t)env * q.P + p) * q.S, q.mask + (size_t)env * q.M, true, lane);
+            __syncwarp();
+            if (lane == 0) q.pend_valid[env * q.P + p] = 0;
+        }
+    }
+}
+
+cudaError_t rl_feed(const rlc_info &info, int phase, const rlc_buffers *env, int obs_dtype, const int32_t *actions, int n,
+                    const rlc_rl_buffers *b, cudaStream_t s) {
+    RlParams q; memset(&q, 0, sizeof q);
+    q.obs = reinterpret_cast<const uint8_t *>(env->obs); q.mask = reinterpret_cast<const uint8_t *>(env->mask);
+    q.player = env->cur_player; q.action = actions; q.done = env->done; q.payoffs = env->payoffs;
+    q.terminal_obs = reinterpret_cast<const uint8_t *>(env->terminal_obs);
+    q.n = n; q.P = info.num_players; q.S = info.obs_stride * (obs_dtype == RLC_F32 ? 4 : 1);
+    q.M = info.mask_bitpacked ? info.mask_words * 4 : info.num_actions;
+    q.pend_obs = reinterpret_cast<uint8_t *>(b->pend_obs); q.pend_action = b->pend_action; q.pend_valid = b->pend_valid;
+    for (int p = 0; p < info.num_players; p++) {
+        q.o_state[p] = reinterpret_cast<uint8_t *>(b->out_state[p]); q.o_next[p] = reinterpret_cast<uint8_t *>(b->out_next_state[p]);
+        q.o_mask[p] = reinterpret_cast<uint8_t *>(b->out_next_mask[p]); q.o_done[p] = b->out_done[p];
+        q.o_action[p] = b->out_action[p]; q.o_reward[p] = b->out_reward[p];
+    }
+    q.count = b->out_count; q.cap = b->out_capacity; q.overflow = b->overflow;
+    if (phase == 0) k_rl_feed<0><<<(n + 3) / 4, 128, 0, s>>>(q);
+    else k_rl_feed<1><<<(n + 3) / 4, 128, 0, s>>>(q);
+    return cudaGetLastError();
+}
+
 }  // namespace rlc
