@@ -180,6 +180,13 @@ typedef struct rlc_dmc_buffers {
 int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_dmc_buffers *b,
                     void *stream);
 
+/* The DMC agent's view of a state (rlcard/agents/dmc_agent/model.py:91-110 predict): legal ids in ascending order
+ * (ids int32 [n][max_ids], -1 padded; count int32 [n], may exceed max_ids if the list was cut) from mask rows in the
+ * layout rlc_step writes, and one feature row per action id (env.get_action_feature: 54-d thermometer for doudizhu,
+ * one-hot over num_actions otherwise; id < 0 -> zeros), out int8 [m][F]. */
+int rlc_legal_ids(int game_id, const void *mask, int n, int max_ids, int32_t *ids, int32_t *count, void *stream);
+int rlc_action_features(int game_id, const int32_t *ids, int m, int8_t *out, void *stream);
+
 /* ---- run_rl.py's data path: Env.run(is_training=True) + reorganize (rlcard/utils/utils.py:153-179) as a per-step
  * stream of [state, action, reward, next_state (+ its legal mask), done] rows per seat.
  * Call with phase 0 BEFORE rlc_step (b->obs / mask / cur_player hold the state the acting seat sees, `actions` the

@@ -56,7 +56,7 @@ class RlcRlBuffers(C.Structure):
 
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
            'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
-           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed']
+           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed', 'rlc_legal_ids', 'rlc_action_features']
 
 _LIB = None
 
@@ -87,6 +87,8 @@ def lib():
         L.rlc_judge_leduc.argtypes = [vp, i32, vp, vp]
         L.rlc_judge_doudizhu.argtypes = [vp, vp, i32, vp, vp]
         L.rlc_encode_uno.argtypes = [vp, vp, i32, vp, vp]
+        L.rlc_legal_ids.argtypes = [i32, vp, i32, i32, vp, vp, vp]
+        L.rlc_action_features.argtypes = [i32, vp, i32, vp, vp]
         L.rlc_rl_feed.argtypes = [i32, i32, C.POINTER(RlcBuffers), vp, i32, C.POINTER(RlcRlBuffers), vp]
         L.rlc_dmc_collect.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcDmcBuffers), vp]
         _LIB = L

@@ -26,6 +26,8 @@ cudaError_t judge_doudizhu(const uint8_t *, const int32_t *, int, uint32_t *, cu
 #endif
 #ifdef RLC_HAVE_DMC
 cudaError_t dmc_collect(const rlc_info &, const rlc_trajectory *, int, int, int, const rlc_dmc_buffers *, cudaStream_t);
+cudaError_t legal_ids(const rlc_info &, const void *, int, int, int32_t *, int32_t *, cudaStream_t);
+cudaError_t action_features(const rlc_info &, const int32_t *, int, int8_t *, cudaStream_t);
 cudaError_t rl_feed(const rlc_info &, int, const rlc_buffers *, int, const int32_t *, int, const rlc_rl_buffers *, cudaStream_t);
 #endif
 }  // namespace rlc
@@ -198,6 +200,26 @@ int rlc_dmc_collect(int game_id, const rlc_trajectory *traj, int obs_dtype, int 
     return judged(rlc::dmc_collect(kInfo[game_id], traj, obs_dtype, T, n, b, reinterpret_cast<cudaStream_t>(stream)));
 #else
     return fail(RLC_ENOTIMPL, "the DMC collector is not in this build");
+#endif
+}
+
+int rlc_legal_ids(int game_id, const void *mask, int n, int max_ids, int32_t *ids, int32_t *count, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!mask || !ids || !count || n <= 0 || max_ids <= 0) return fail(RLC_EINVAL, "null buffers, n <= 0 or max_ids <= 0");
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::legal_ids(kInfo[game_id], mask, n, max_ids, ids, count, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "not in this build");
+#endif
+}
+
+int rlc_action_features(int game_id, const int32_t *ids, int m, int8_t *out, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!ids || !out || m <= 0) return fail(RLC_EINVAL, "null buffers or m <= 0");
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::action_features(kInfo[game_id], ids, m, out, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "not in this build");
 #endif
 }
 

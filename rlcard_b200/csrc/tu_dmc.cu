@@ -144,6 +144,77 @@ cudaError_t dmc_collect(const rlc_info &info, const rlc_trajectory *traj, int ob
 
 
 // ==========================================================================================
+// The DMC agent's view of a state (rlcard/agents/dmc_agent/model.py:91-110 predict): the legal action ids in
+// ascending order and one feature row per legal action, for all envs at once.
+// ==========================================================================================
+// one warp per env: mask row (dense uint8 [A] or bit-packed uint32 [W]) -> ids [max_ids] (-1 padded) + count
+__global__ void __launch_bounds__(128) k_legal_ids(const void *mask, int n, int A, int W, int bitpacked, int max_ids,
+                                                    int32_t *ids, int32_t *count) {
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (env >= n) return;
+    int32_t *out = ids + (size_t)env * max_ids;
+    int total = 0;
+    if (bitpacked) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(mask) + (size_t)env * W;
+        for (int base = 0; base < W; base += 32) {
+            const int wi = base + lane;
+            uint32_t word = wi < W ? row[wi] : 0u;
+            if (wi == W - 1 && (A & 31)) word &= (1u << (A & 31)) - 1u;
+            int c = __popc(word), incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int at = total + incl - c;
+            while (word) {
+                const int b = __ffs(word) - 1; word &= word - 1;
+                if (at < max_ids) out[at] = 32 * wi + b;
+                at++;
+            }
+            total += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    } else {
+        const uint8_t *row = reinterpret_cast<const uint8_t *>(mask) + (size_t)env * A;
+        for (int base = 0; base < A; base += 32) {
+            const int a = base + lane;
+            const bool on = a < A && row[a] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, on);
+            const int at = total + __popc(bal & ((1u << lane) - 1u));
+            if (on && at < max_ids) out[at] = a;
+            total += __popc(bal);
+        }
+    }
+    for (int k = total + lane; k < max_ids; k += 32) out[k] = -1;
+    if (lane == 0) count[env] = total;
+}
+
+__global__ void __launch_bounds__(128) k_action_features(DmcParams q, const int32_t *ids, int m, int8_t *out) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const int a = ids[i];
+    if (a >= 0 && a < q.num_actions) write_feature(q, out + (size_t)i * q.F, a, lane);
+    else for (int e = lane; e < q.F; e += 32) out[(size_t)i * q.F + e] = 0;
+}
+
+cudaError_t legal_ids(const rlc_info &info, const void *mask, int n, int max_ids, int32_t *ids, int32_t *count, cudaStream_t s) {
+    k_legal_ids<<<(n + 3) / 4, 128, 0, s>>>(mask, n, info.num_actions, info.mask_words, info.mask_bitpacked, max_ids, ids, count);
+    return cudaGetLastError();
+}
+cudaError_t action_features(const rlc_info &info, const int32_t *ids, int m, int8_t *out, cudaStream_t s) {
+    DmcParams q; memset(&q, 0, sizeof q);
+    q.num_actions = info.num_actions; q.F = info.game_id == RLC_DOUDIZHU ? 54 : info.num_actions;
+    if (info.game_id == RLC_DOUDIZHU) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        q.ddz_rows = doudizhu_rows_on_device(dev);
+        if (!q.ddz_rows) return cudaErrorNotReady;
+    }
+    k_action_features<<<(m + 3) / 4, 128, 0, s>>>(q, ids, m, out);
+    return cudaGetLastError();
+}
+
+// ==========================================================================================
 // run_rl.py's data path: Env.run(is_training=True) + reorganize (rlcard/utils/utils.py:153-179) as a per-step
 // stream.  For every seat the transitions [state, action, reward, next_state, done] pair each decision of the seat
 // with its next decision, the last one with the seat's terminal view and its payoff.  phase 0 runs BEFORE the env

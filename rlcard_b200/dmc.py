@@ -14,6 +14,70 @@ import torch
 from ._lib import DTYPE_F32, DTYPE_U8, RlcDmcBuffers, RlcTrajectory, check, lib
 
 
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def legal_ids(env, mask=None, max_ids=None):
+    """Legal action ids of every env in ascending order: (ids int32 [N, max_ids] padded with -1, count int32 [N]).
+    ``mask`` defaults to the env's current mask; ``max_ids`` to 512 for doudizhu (the widest legal set seen is
+    452) and num_actions otherwise."""
+    mask = env.mask if mask is None else mask
+    if max_ids is None:
+        max_ids = 512 if env.name == 'doudizhu' else env.num_actions
+    n = mask.shape[0]
+    ids = torch.empty((n, max_ids), dtype=torch.int32, device=env.device)
+    count = torch.empty(n, dtype=torch.int32, device=env.device)
+    with torch.cuda.device(env.device):
+        check(lib().rlc_legal_ids(env.gid, C.c_void_p(mask.data_ptr()), n, int(max_ids), C.c_void_p(ids.data_ptr()),
+                                  C.c_void_p(count.data_ptr()), _stream(env.device)))
+    return ids, count
+
+
+def action_features(env, ids):
+    """env.get_action_feature for a tensor of action ids (any shape; -1 -> zeros): int8 [..., F]."""
+    F = 54 if env.name == 'doudizhu' else env.num_actions
+    flat = ids.to(device=env.device, dtype=torch.int32).contiguous().view(-1)
+    out = torch.empty((flat.numel(), F), dtype=torch.int8, device=env.device)
+    with torch.cuda.device(env.device):
+        check(lib().rlc_action_features(env.gid, C.c_void_p(flat.data_ptr()), flat.numel(), C.c_void_p(out.data_ptr()), _stream(env.device)))
+    return out.view(*ids.shape, F)
+
+
+class DMCPolicy:
+    """The DMC agents' action choice (dmc_agent/model.py:60-110) for all envs at once: every legal action of every env
+    is scored by ``nets[position](obs, action_features)`` (the reference repeats the obs row per legal action), the
+    best one is taken, or, with probability ``exp_epsilon``, a uniformly random legal one.  ``nets[p]`` maps
+    (float32 [M, obs_dim_p], float32 [M, F]) -> values [M] or [M, 1]."""
+
+    def __init__(self, env, nets, exp_epsilon=0.01, generator=None):
+        self.env, self.nets, self.eps, self.gen = env, nets, float(exp_epsilon), generator
+
+    def __call__(self, obs, mask, cur_player):
+        env = self.env
+        ids, count = legal_ids(env, mask)
+        N, K = ids.shape
+        valid = ids >= 0
+        feats = action_features(env, ids)                                   # [N, K, F]
+        values = torch.full((N, K), float('-inf'), device=env.device)
+        for p in range(env.num_players):
+            sel = (cur_player == p).nonzero(as_tuple=True)[0]
+            if sel.numel() == 0:
+                continue
+            v = valid[sel]
+            rows = v.nonzero(as_tuple=True)
+            o = obs[sel][:, :env.obs_dims[p]].float()[rows[0]]
+            val = self.nets[p](o, feats[sel][rows].float()).reshape(-1).float()
+            block = torch.full((sel.numel(), K), float('-inf'), device=env.device)
+            block[rows] = val
+            values[sel] = block
+        best = values.argmax(dim=1)                                         # first maximum = lowest id, like np.argmax
+        rnd = (torch.rand(N, device=env.device, generator=self.gen) * count.clamp(min=1)).long().clamp(max=K - 1)
+        explore = torch.rand(N, device=env.device, generator=self.gen) < self.eps
+        pick = torch.where(explore, rnd, best)
+        return ids.gather(1, pick.unsqueeze(1)).squeeze(1)
+
+
 class DMCCollector:
     def __init__(self, env, pool_rows, open_capacity=None):
         """env: VecEnv.  pool_rows: capacity of each position's row pool.  open_capacity: bound on the number of

@@ -144,3 +144,58 @@ def test_cuda_collector_on_vectorised_rollouts(game):
                 float(col.episode_return[p][i])) for i in range(sizes[p])]
         assert sorted(map(key, got)) == sorted(map(key, want[p]))
     assert int(col.open_len.sum().item()) == sum(len(c) for c in carry)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', ['doudizhu', 'uno', 'leduc-holdem'])
+def test_legal_ids_features_and_dmc_policy(game):
+    """rlc_legal_ids / rlc_action_features against numpy on the env's masks, and DMCPolicy (greedy) against a numpy
+    restatement of DMCAgent.step (model.py:60-110): argmax over the legal actions in ascending id order."""
+    import torch
+    import rlcard_b200
+    from rlcard_b200.dmc import DMCCollector, DMCPolicy, action_features, legal_ids
+    n = 200
+    env = rlcard_b200.VecEnv(game, n, seed=17)
+    env.reset()
+    env.rollout_random(23)                                            # some mid-game states
+    obs, mask, cur, _, _ = env.get_state(None)
+    ids, count = legal_ids(env)
+    m = mask.cpu().numpy()
+    if env.mask_bitpacked:
+        m = np.unpackbits(m.view(np.uint8), axis=1, bitorder='little')[:, :env.num_actions]
+    f = feature_fn(game, env.num_actions)
+    ids_np, cnt_np = ids.cpu().numpy(), count.cpu().numpy()
+    feats = action_features(env, ids).cpu().numpy()
+    for i in range(n):
+        want = np.nonzero(m[i])[0]
+        assert cnt_np[i] == len(want)
+        assert ids_np[i, :len(want)].tolist() == want.tolist() and (ids_np[i, len(want):] == -1).all()
+        for k, a in enumerate(want[:5]):
+            np.testing.assert_array_equal(feats[i, k], f(int(a)))
+        assert not feats[i, len(want):].any()
+    F = feats.shape[-1]
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    ws = [(torch.randn(env.obs_dims[p], device='cuda', generator=g), torch.randn(F, device='cuda', generator=g)) for p in range(env.num_players)]
+    nets = [lambda o, a, w=w: o @ w[0] + a @ w[1] for w in ws]
+    acts = DMCPolicy(env, nets, exp_epsilon=0.0)(obs, mask, cur).cpu().numpy()
+    o_np, cur_np = obs.cpu().numpy().astype(np.float32), cur.cpu().numpy()
+    for i in range(n):
+        p = cur_np[i]
+        want = np.nonzero(m[i])[0]
+        w0, w1 = ws[p][0].cpu().numpy(), ws[p][1].cpu().numpy()
+        vals = np.array([o_np[i, :env.obs_dims[p]] @ w0 + f(int(a)).astype(np.float32) @ w1 for a in want])
+        best = vals.max()
+        assert acts[i] in want
+        assert vals[list(want).index(acts[i])] >= best - 1e-3 * max(1.0, abs(best))     # argmax up to float reassociation
+    # the policy drives the env and the collector end to end
+    col = DMCCollector(env, pool_rows=n * 64)
+    traj = {k: [] for k in ('obs', 'action', 'player', 'done', 'payoffs')}
+    pol = DMCPolicy(env, nets, exp_epsilon=0.1)
+    for _ in range(30):
+        a = pol(env.obs, env.mask, env.cur_player)
+        traj['obs'].append(env.obs.clone()); traj['player'].append(env.cur_player.clone()); traj['action'].append(a.int())
+        env.step(a)
+        traj['done'].append(env.done.clone()); traj['payoffs'].append(env.payoffs.clone())
+    env.check_errors()                                                # every chosen action was legal
+    col.add({k: torch.stack(v).contiguous() for k, v in traj.items()})
+    assert sum(col.sizes()) + int(col.open_len.sum().item()) == n * 30
