@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DEFAULT_ENVS = {'blackjack': 65536, 'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384,
-                'doudizhu': 8192, 'scout': 8192}
+                'doudizhu': 8192, 'scout': 8192, 'no-limit-holdem': 16384}
 METRIC = 'env steps/sec (random policy, obs+mask)'
 UNIT = 'env-steps/s'
 

@@ -39,7 +39,8 @@ enum rlc_game {
     RLC_UNO = 3,         /* 'uno'           */
     RLC_DOUDIZHU = 4,    /* 'doudizhu'      */
     RLC_SCOUT = 5,       /* 'scout'         */
-    RLC_NUM_GAMES = 6
+    RLC_NOLIMIT = 6,     /* 'no-limit-holdem' (2 players, 100 chips each: the reference defaults) */
+    RLC_NUM_GAMES = 7
 };
 
 enum rlc_status {

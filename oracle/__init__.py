@@ -16,7 +16,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5}
+GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5, 'no-limit-holdem': 6}
 
 
 def build(force=False):

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-enum { ORC_BLACKJACK = 0, ORC_LEDUC = 1, ORC_LIMIT = 2, ORC_UNO = 3, ORC_DOUDIZHU = 4, ORC_SCOUT = 5, ORC_NUM_GAMES = 6 };
+enum { ORC_BLACKJACK = 0, ORC_LEDUC = 1, ORC_LIMIT = 2, ORC_UNO = 3, ORC_DOUDIZHU = 4, ORC_SCOUT = 5, ORC_NOLIMIT = 6, ORC_NUM_GAMES = 7 };
 enum { ORC_CHANCE_TAPE = 0, ORC_CHANCE_PHILOX = 1, ORC_CHANCE_MT = 2 };
 #define ORC_MAX_PLAYERS 4
 

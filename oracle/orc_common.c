@@ -147,7 +147,7 @@ void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail) {
 }
 
 /* ------------------------------------------------------------------ env handles */
-extern const orc_game_vt orc_vt_blackjack, orc_vt_leduc, orc_vt_limit, orc_vt_uno, orc_vt_doudizhu, orc_vt_scout;
+extern const orc_game_vt orc_vt_blackjack, orc_vt_leduc, orc_vt_limit, orc_vt_uno, orc_vt_doudizhu, orc_vt_scout, orc_vt_nolimit;
 const orc_game_vt *orc_game(int g) {
     switch (g) {
     case ORC_BLACKJACK: return &orc_vt_blackjack;
@@ -156,6 +156,7 @@ const orc_game_vt *orc_game(int g) {
     case ORC_UNO: return &orc_vt_uno;
     case ORC_DOUDIZHU: return &orc_vt_doudizhu;
     case ORC_SCOUT: return &orc_vt_scout;
+    case ORC_NOLIMIT: return &orc_vt_nolimit;
     }
     return NULL;
 }

@@ -11,7 +11,7 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_DIR, 'librlcard_b200.so')
 
 RLC_MAX_PLAYERS = 4
-GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5}
+GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5, 'no-limit-holdem': 6}
 CHANCE_PHILOX, CHANCE_TAPE, CHANCE_MT19937 = 0, 1, 2
 DTYPE_U8, DTYPE_F32 = 0, 1
 AUTO_RESET, TERMINAL_OBS = 1, 2

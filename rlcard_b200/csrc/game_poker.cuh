@@ -312,4 +312,150 @@ struct Limit {
     }
 };
 
+// ========================================================================================
+// No-limit Hold'em, 2 players, 100 chips each, 5 actions (games/nolimitholdem/{game,round,player}.py over
+// games/limitholdem/{dealer,player,judger,utils}.py; envs/nolimitholdem.py).  4 game words:
+//  w0: cards 0..4 (6 bits each): hole p0a, p1a, p0b, p1b (deal order game.py:73-74), flop0
+//  w1: flop1, flop2, turn, river (6 bits each) | status0 [24:26) status1 [26:28) (0 alive 1 folded 2 all-in) |
+//      pointer [28] | dealer_id + 1 [29:31) (0 = not drawn yet: the first init_game draws it and it is kept)
+//  w2: in_chips0 [0:7) in_chips1 [7:14) remained0 [14:21) remained1 [21:28) round_counter [28:31)
+//  w3: raised0 [0:7) raised1 [7:14) not_raise_num [14:16) not_playing_num [16:18) n_public [18:21)
+// ========================================================================================
+struct NoLimit {
+    static constexpr int kGameId = 6, P = 2, A = 5, OBS = 54, GAME_WORDS = 4, MASK_WORDS = 1;
+    static constexpr bool kUsesChain = false;
+    static constexpr int kMaxResetDraws = 53;
+    static constexpr bool kChanceAwareState = false;
+    static constexpr int kSharedBytes = 0;
+    static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
+    __device__ __forceinline__ void bind_shared(const uint8_t *) {}
+    enum { kFoldA = 0, kCheckCall = 1, kHalfPot = 2, kPot = 3, kAllIn = 4 };          // round.py:8-18
+    int card[9];
+    int in0, in1, rem0, rem1, st0, st1, pointer, dealer, rc, raised0, raised1, nrn, npn, npub;
+
+    __device__ __forceinline__ void load(const uint32_t *st, size_t n, size_t i) {
+        const uint32_t w0 = st[i], w1 = st[n + i], w2 = st[2 * n + i], w3 = st[3 * n + i];
+#pragma unroll
+        for (int k = 0; k < 5; k++) card[k] = bf_get(w0, 6 * k, 6);
+#pragma unroll
+        for (int k = 0; k < 4; k++) card[5 + k] = bf_get(w1, 6 * k, 6);
+        st0 = bf_get(w1, 24, 2); st1 = bf_get(w1, 26, 2); pointer = bf_get(w1, 28, 1); dealer = (int)bf_get(w1, 29, 2) - 1;
+        in0 = bf_get(w2, 0, 7); in1 = bf_get(w2, 7, 7); rem0 = bf_get(w2, 14, 7); rem1 = bf_get(w2, 21, 7); rc = bf_get(w2, 28, 3);
+        raised0 = bf_get(w3, 0, 7); raised1 = bf_get(w3, 7, 7); nrn = bf_get(w3, 14, 2); npn = bf_get(w3, 16, 2); npub = bf_get(w3, 18, 3);
+    }
+    __device__ __forceinline__ void store(uint32_t *st, size_t n, size_t i) const {
+        uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) w0 |= (uint32_t)card[k] << (6 * k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) w1 |= (uint32_t)card[5 + k] << (6 * k);
+        w1 |= (st0 << 24) | (st1 << 26) | (pointer << 28) | ((uint32_t)(dealer + 1) << 29);
+        st[i] = w0; st[n + i] = w1;
+        st[2 * n + i] = in0 | (in1 << 7) | (rem0 << 14) | (rem1 << 21) | (rc << 28);
+        st[3 * n + i] = raised0 | (raised1 << 7) | (nrn << 14) | (npn << 16) | (npub << 18);
+    }
+    __device__ __forceinline__ void bet(int p, int chips) {                 // nolimitholdem/player.py:16-19
+        const int r = p ? rem1 : rem0, q = min(chips, r);
+        if (p) { in1 += q; rem1 -= q; } else { in0 += q; rem0 -= q; }
+    }
+    // game.py:50-111
+    template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
+        if (dealer < 0) dealer = (int)ch.below(2u);                        // drawn by the first init_game only (game.py:62-63)
+        int j[9];
+        if constexpr (Ch::kKind == 0) {
+            const uint32_t x1 = ch.below(52u * 51u * 50u), x2 = ch.below(49u * 48u * 47u), x3 = ch.below(46u * 45u * 44u);
+            j[0] = (int)(x1 / 2550u); j[1] = (int)((x1 / 50u) % 51u); j[2] = (int)(x1 % 50u);
+            j[3] = (int)(x2 / 2256u); j[4] = (int)((x2 / 47u) % 48u); j[5] = (int)(x2 % 47u);
+            j[6] = (int)(x3 / 1980u); j[7] = (int)((x3 / 44u) % 45u); j[8] = (int)(x3 % 44u);
+        } else {
+#pragma unroll
+            for (int s = 0; s < 9; s++) j[s] = (int)ch.below((uint32_t)(52 - s));
+            ch.skip_fy(42, 1);
+        }
+        fy_tail_cards<9>(52, j, card);
+        in0 = in1 = 0; rem0 = rem1 = 100; st0 = st1 = 0; npub = 0;
+        const int sb = (dealer + 1) & 1, bb = dealer;                      // (dealer + 2) % 2
+        bet(bb, 2); bet(sb, 1);
+        pointer = (bb + 1) & 1;
+        nrn = 0; npn = 0; raised0 = in0; raised1 = in1; rc = 0;
+    }
+    __device__ __forceinline__ int pot() const { return in0 + in1; }       // dealer.pot as refreshed by get_state (game.py:186)
+    // round.py:125-161
+    __device__ __forceinline__ uint32_t legal_bits() const {
+        const int mine = pointer ? raised1 : raised0, mx = max(raised0, raised1), rem = pointer ? rem1 : rem0;
+        const int diff = mx - mine, pt = pot();
+        uint32_t m = 0x1Fu;
+        if (diff > 0 && diff >= rem) m &= ~((1u << kHalfPot) | (1u << kPot) | (1u << kAllIn));
+        else {
+            if (pt > rem) m &= ~(1u << kPot);
+            if ((pt >> 1) > rem || (pt >> 1) + mine <= mx) m &= ~(1u << kHalfPot);
+        }
+        return m;
+    }
+    __device__ __forceinline__ void legal(uint32_t (&m)[1]) const { m[0] = legal_bits(); }
+    __device__ __forceinline__ int player() const { return pointer; }
+    __device__ __forceinline__ bool over() const { return ((st0 != 1) + (st1 != 1) == 1) || rc >= 4; }   // limitholdem/game.py:216-231
+    // env.py:65-86, game.py:113-181, round.py:65-123
+    template <class Ch> __device__ __forceinline__ void step(int id, Ch &, int &err) {
+        const uint32_t m = legal_bits();
+        if (id < 0 || id > 4 || !((m >> id) & 1u)) { id = kFoldA; err |= 4; }   // the reference has no fallback here
+        const int p = pointer, pt = pot();
+        const int mine = p ? raised1 : raised0, mx = max(raised0, raised1), rem = p ? rem1 : rem0;
+        int nr = mine, amount = 0; bool fold = false;
+        if (id == kCheckCall) { amount = mx - mine; nr = mx; nrn++; }
+        else if (id == kAllIn) { amount = rem; nr = mine + rem; nrn = 1; }
+        else if (id == kPot) { amount = pt; nr = mine + pt; nrn = 1; }
+        else if (id == kHalfPot) { amount = pt >> 1; nr = mine + (pt >> 1); nrn = 1; }
+        else fold = true;
+        if (p) raised1 = nr; else raised0 = nr;
+        bet(p, amount);
+        int stp = p ? st1 : st0;
+        if (fold) stp = 1;
+        if ((p ? rem1 : rem0) == 0 && stp != 1) stp = 2;
+        if (p) st1 = stp; else st0 = stp;
+        pointer = p ^ 1;
+        if (stp == 2) { npn++; nrn--; }
+        if (stp == 1) npn++;
+        if ((pointer ? st1 : st0) == 1) pointer ^= 1;                      // skip the folded seat
+        int by0 = st0 != 0, by1 = st1 != 0;                                // game.py:141-147
+        if (by0 + by1 == 1) {
+            const int last = by0 ? 1 : 0;
+            if ((last ? raised1 : raised0) >= max(raised0, raised1)) { if (last) by1 = 1; else by0 = 1; }
+        }
+        if (nrn + npn >= 2) {                                              // round over: game.py:150-177
+            const bool all = by0 + by1 == 2;
+            pointer = (dealer + 1) & 1;
+            if (!all && (pointer ? by1 : by0)) pointer ^= 1;
+            if (rc == 0) { npub = 3; if (all) rc++; }
+            if (rc == 1) { npub = 4; if (all) rc++; }
+            if (rc == 2) { npub = 5; if (all) rc++; }
+            rc++;
+            nrn = 0; raised0 = raised1 = 0;
+        }
+    }
+    // game.py:226-236 + limitholdem/judger.py for two players: the winner takes what the loser can match (chips, not blinds)
+    __device__ __forceinline__ void payoffs(float *out) const {
+        int w0, w1;
+        if ((st0 == 1) != (st1 == 1)) { w0 = st1 == 1; w1 = st0 == 1; }
+        else {
+            const int h0[7] = { card[0], card[2], card[4], card[5], card[6], card[7], card[8] };
+            const int h1[7] = { card[1], card[3], card[4], card[5], card[6], card[7], card[8] };
+            const uint32_t s0 = holdem_strength7(h0), s1 = holdem_strength7(h1);
+            w0 = s0 >= s1; w1 = s1 >= s0;
+        }
+        const int potm = min(in0, in1);
+        float p0 = 0.f;
+        if (w0 != w1) p0 = w0 ? (float)potm : -(float)potm;
+        out[0] = p0; out[1] = -p0;
+    }
+    // envs/nolimitholdem.py:47-79: 52 card bits + my chips + max chips
+    template <class T> __device__ __forceinline__ void encode_obs(int seat, bool, T *row) const {
+        row[card[seat]] = (T)1; row[card[2 + seat]] = (T)1;
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (k < npub) row[card[4 + k]] = (T)1;
+        row[52] = (T)(seat ? in1 : in0);
+        row[53] = (T)max(in0, in1);
+    }
+};
+
 }  // namespace rlc

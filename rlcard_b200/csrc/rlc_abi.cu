@@ -12,6 +12,9 @@ cudaError_t dispatch_leduc(int, int, int, const KParams &, cudaStream_t);
 cudaError_t dispatch_limit(int, int, int, const KParams &, cudaStream_t);
 cudaError_t judge_holdem(const uint8_t *, int, int, uint8_t *, cudaStream_t);
 cudaError_t judge_leduc(const int32_t *, int, float *, cudaStream_t);
+#ifdef RLC_HAVE_NOLIMIT
+cudaError_t dispatch_nolimit(int, int, int, const KParams &, cudaStream_t);
+#endif
 #ifdef RLC_HAVE_UNO
 cudaError_t dispatch_uno(int, int, int, const KParams &, cudaStream_t);
 cudaError_t encode_uno(const uint8_t *, const uint8_t *, int, uint8_t *, cudaStream_t);
@@ -48,6 +51,11 @@ static const rlc_info kInfo[RLC_NUM_GAMES] = {
     { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, {0, 0, 0, 0} },
     { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, {0, 0, 0, 0} },
     { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, {0, 0, 0, 0} },
+#ifdef RLC_HAVE_NOLIMIT
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, {0, 0, 0, 0} },
+#else
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, 0, 53, 1, {0, 0, 0, 0} },
+#endif
 };
 
 static int dispatch(int game, int op, const rlc_buffers *b, rlc::KParams &p, void *stream) {
@@ -57,6 +65,9 @@ static int dispatch(int game, int op, const rlc_buffers *b, rlc::KParams &p, voi
     case RLC_BLACKJACK: e = rlc::dispatch_blackjack(op, b->chance, b->obs_dtype, p, s); break;
     case RLC_LEDUC: e = rlc::dispatch_leduc(op, b->chance, b->obs_dtype, p, s); break;
     case RLC_LIMIT: e = rlc::dispatch_limit(op, b->chance, b->obs_dtype, p, s); break;
+#ifdef RLC_HAVE_NOLIMIT
+    case RLC_NOLIMIT: e = rlc::dispatch_nolimit(op, b->chance, b->obs_dtype, p, s); break;
+#endif
 #ifdef RLC_HAVE_UNO
     case RLC_UNO: e = rlc::dispatch_uno(op, b->chance, b->obs_dtype, p, s); break;
 #endif

@@ -86,7 +86,7 @@ class DMCCollector:
         dev, N, P = env.device, env.num_envs, env.num_players
         self.F = 54 if env.name == 'doudizhu' else env.num_actions
         if open_capacity is None:
-            open_capacity = {'blackjack': 16, 'leduc-holdem': 16, 'limit-holdem': 32, 'doudizhu': 192,
+            open_capacity = {'blackjack': 16, 'leduc-holdem': 16, 'limit-holdem': 32, 'no-limit-holdem': 32, 'doudizhu': 192,
                              'uno': 1024, 'scout': 1024}[env.name]
         self.open_capacity, self.pool_rows = int(open_capacity), int(pool_rows)
         odt = env.obs_dtype

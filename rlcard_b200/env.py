@@ -47,9 +47,12 @@ _SPECS = {
     'uno': dict(actions=_uno_actions, dtype=np.int64, shape=lambda d: (4, 4, 15)),
     'doudizhu': dict(actions=lambda: _doudizhu_actions(), dtype=np.int8, shape=lambda d: (d,)),
     'scout': dict(actions=_scout_actions, dtype=np.float32, shape=lambda d: (d,)),
+    # games/nolimitholdem/round.py:8-18 Action enum names (the reference's raw actions are the enum members)
+    'no-limit-holdem': dict(actions=lambda: ['FOLD', 'CHECK_CALL', 'RAISE_HALF_POT', 'RAISE_POT', 'ALL_IN'], dtype=np.float64,
+                            shape=lambda d: (d,)),
 }
 _STATE_SHAPE = {'uno': [4, 4, 15]}
-_INT_PAYOFF = {'blackjack', 'uno', 'doudizhu', 'scout'}
+_INT_PAYOFF = {'blackjack', 'uno', 'doudizhu', 'scout', 'no-limit-holdem'}
 
 
 class Env:

@@ -100,6 +100,7 @@ GAMES = {
     'uno': (12, 6, 0.0, 0.3),
     'doudizhu': (8, 3, 0.0, 0.25),
     'scout': (8, 2, 0.0, 0.2),
+    'no-limit-holdem': (24, 40, 0.0, 1.0),
 }
 
 

@@ -31,7 +31,8 @@ def test_abi_version_and_info():
     assert L.rlc_abi_version() == 1
     # Env.num_players / num_actions / state_shape of the reference (envs/*.py)
     expect = {'blackjack': (1, 2, [2]), 'leduc-holdem': (2, 4, [36, 36]), 'limit-holdem': (2, 4, [72, 72]),
-              'uno': (2, 61, [240, 240]), 'doudizhu': (3, 27472, [790, 901, 901]), 'scout': (4, 204, [688] * 4)}
+              'uno': (2, 61, [240, 240]), 'doudizhu': (3, 27472, [790, 901, 901]), 'scout': (4, 204, [688] * 4),
+              'no-limit-holdem': (2, 5, [54, 54])}
     for g, (p, a, od) in expect.items():
         i = rlcard_b200.game_info(g)
         assert (i.num_players, i.num_actions, list(i.obs_dim)[:p]) == (p, a, od)

@@ -205,7 +205,7 @@ def test_step_api_equals_fused_rollout(game):
 @pytest.mark.parametrize('game', GAMES)
 def test_full_size_properties(game):
     """BASELINE.json sizes: properties that do not need the oracle."""
-    n = {'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384, 'blackjack': 65536}.get(game, 8192)
+    n = {'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384, 'blackjack': 65536, 'no-limit-holdem': 16384}.get(game, 8192)
     T = 64
     env = rlcard_b200.VecEnv(game, n, seed=7)
     env.reset()
@@ -220,10 +220,10 @@ def test_full_size_properties(game):
         assert bool((mask.gather(2, act.unsqueeze(-1)) == 1).all())
         assert bool((mask.sum(-1) >= 1).all())
     assert bool((pay[~done] == 0).all())
-    if game in ('leduc-holdem', 'limit-holdem'):
+    if game in ('leduc-holdem', 'limit-holdem', 'no-limit-holdem'):
         assert bool((pay.sum(-1) == 0).all())                              # zero-sum
         assert bool(((pay * 2) == (pay * 2).round()).all())                # multiples of 0.5
-    assert int(done.sum()) > (n if game in ('blackjack', 'leduc-holdem', 'limit-holdem') else 0)   # episodes finish and restart
+    assert int(done.sum()) > (n if game in ('blackjack', 'leduc-holdem', 'limit-holdem', 'no-limit-holdem') else 0)   # episodes finish and restart
     # shard invariance: envs [n/2, n) of this run == a second VecEnv with env_id_base n/2
     env2 = rlcard_b200.VecEnv(game, n // 2, seed=7, env_id_base=n // 2)
     env2.reset()

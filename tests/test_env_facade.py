@@ -10,8 +10,8 @@ from rlcard_b200 import RandomAgent
 
 pytestmark = pytest.mark.gpu
 
-GAMES = ['blackjack', 'leduc-holdem', 'limit-holdem', 'uno', 'doudizhu', 'scout']
-OBS_SIZE = {'blackjack': 2, 'leduc-holdem': 36, 'limit-holdem': 72, 'uno': 240, 'doudizhu': 790, 'scout': 688}
+GAMES = ['blackjack', 'leduc-holdem', 'limit-holdem', 'uno', 'doudizhu', 'scout', 'no-limit-holdem']
+OBS_SIZE = {'blackjack': 2, 'leduc-holdem': 36, 'limit-holdem': 72, 'uno': 240, 'doudizhu': 790, 'scout': 688, 'no-limit-holdem': 54}
 
 
 def gather_observations(env, actions, num_rand_steps):      # tests/envs/determism_util.py:22-45
@@ -104,7 +104,7 @@ def test_run(game, is_training):
     env.set_agents([RandomAgent(env.num_actions) for _ in range(env.num_players)])
     trajectories, payoffs = env.run(is_training=is_training)
     assert len(trajectories) == env.num_players
-    if game in ('leduc-holdem', 'limit-holdem', 'uno'):
+    if game in ('leduc-holdem', 'limit-holdem', 'uno', 'no-limit-holdem'):
         assert sum(payoffs) == 0
     if game == 'blackjack':
         assert payoffs[0] in (-1, 0, 1)
