@@ -154,7 +154,6 @@ __device__ __forceinline__ void shuffle_tail_u8(Ch &ch, uint8_t *x, int n, int t
 // bit packing helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bf_get(uint32_t w, int pos, int len) { return (w >> pos) & ((1u << len) - 1u); }
-__device__ __forceinline__ uint32_t bf_put(uint32_t v, int pos) { return v << pos; }
 
 // k-th (0-based) set bit of a multi-word mask
 template <int WORDS>

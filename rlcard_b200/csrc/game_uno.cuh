@@ -82,12 +82,6 @@ struct UnoT {
     }
 
     // ---- list primitives
-    // sum of the fifteen 2-bit counters of one colour word
-    static __device__ __forceinline__ int sum2(uint32_t w) {
-        uint32_t s = (w & 0x33333333u) + ((w >> 2) & 0x33333333u);
-        s = (s + (s >> 4)) & 0x0f0f0f0fu;
-        return (int)((s * 0x01010101u) >> 24);
-    }
     template <class Ch> __device__ __forceinline__ int pop_deck(Ch &ch, int &err) {   // deck.pop(); Q-UNO4: empty -> flag
         if (dl <= 0) { err |= 8; return -1; }
         if constexpr (BAG) {                                             // uniformly random remaining card

@@ -49,34 +49,6 @@ __device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch> &w, const KParam
     return __shfl_sync(kFull, word, 0);
 }
 
-// k-th (0-based) set bit over W mask words in shared memory (all lanes get the result)
-__device__ __forceinline__ int warp_kth_set_bit(const uint32_t *sm, int W, int k, int lane) {
-    for (int base = 0; base < W; base += 32) {
-        const int wi = base + lane;
-        const uint32_t word = wi < W ? sm[wi] : 0u;
-        int c = __popc(word), incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-        const int total = __shfl_sync(kFull, incl, 31);
-        if (k < total) {
-            const uint32_t hit = __ballot_sync(kFull, k < incl);           // first lane whose prefix exceeds k
-            const int src = __ffs(hit) - 1;
-            const int before = __shfl_sync(kFull, incl - c, src);
-            const uint32_t w = __shfl_sync(kFull, word, src);
-            return 32 * (base + src) + (int)__fns(w, 0, k - before + 1);
-        }
-        k -= total;
-    }
-    return -1;
-}
-__device__ __forceinline__ int warp_popc_words(const uint32_t *sm, int W, int lane) {
-    int c = 0;
-    for (int wi = lane; wi < W; wi += 32) c += __popc(sm[wi]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
-    return c;
-}
-
 // mask row of one env: dense uint8 [A] (4 ids per 32-bit store) or bit-packed uint32 [W]
 template <class G>
 __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const uint32_t *sm, int lane) {

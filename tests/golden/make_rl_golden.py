@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 from make_golden import TapeRecorder, import_reference  # noqa: E402
 
-GAMES = {'leduc-holdem': 12, 'limit-holdem': 8, 'uno': 3, 'doudizhu': 2, 'blackjack': 10, 'scout': 1}
+GAMES = {'leduc-holdem': 12, 'limit-holdem': 8, 'uno': 3, 'doudizhu': 2, 'blackjack': 10, 'scout': 1, 'no-limit-holdem': 10}
 
 
 def main():

@@ -8,7 +8,7 @@ import pytest
 import oracle
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-GAMES = ['leduc-holdem', 'limit-holdem', 'uno', 'doudizhu', 'blackjack', 'scout']
+GAMES = ['leduc-holdem', 'limit-holdem', 'uno', 'doudizhu', 'blackjack', 'scout', 'no-limit-holdem']
 
 
 def load(game):
