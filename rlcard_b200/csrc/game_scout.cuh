@@ -26,7 +26,7 @@ __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * 
 struct Scout {
     static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
     static constexpr bool kMaskBitpacked = false;
-    static constexpr int kMinBlocks = 4;          // resident 128-thread blocks per SM the rollout kernel is compiled for
+    static constexpr int kMinBlocks = 5;          // resident 128-thread blocks per SM the rollout kernel is compiled for
     static constexpr int kScratchBytes = 48;
     uint64_t ht[4], hb[4], tt, tb;
     int hl[4], score[4], tl, owner, consec, cur, over_;
