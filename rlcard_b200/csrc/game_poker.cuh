@@ -165,15 +165,22 @@ __device__ __forceinline__ int straight_top(uint32_t m) {   // m bit r = rank (2
     const uint32_t run = x & (x >> 1) & (x >> 2) & (x >> 3) & (x >> 4);
     return run ? (32 - __clz(run)) + 3 : 0;                  // top bit index in x (1-based rank), 5-high wheel -> 4
 }
+// rank bit (2 -> bit 0 .. A -> bit 12) of card id c = 13*suit + rank (A = 0, 2..K = 1..12) into the suit's mask
+__device__ __forceinline__ void holdem_add_card(uint32_t (&s)[4], int c) {
+    const int suit = c / 13, rk = c - 13 * suit;
+    const uint32_t bit = 1u << (rk == 0 ? 12 : rk - 1);
+    s[0] |= suit == 0 ? bit : 0u; s[1] |= suit == 1 ? bit : 0u;
+    s[2] |= suit == 2 ? bit : 0u; s[3] |= suit == 3 ? bit : 0u;
+}
+__device__ __forceinline__ uint32_t holdem_strength_masks(const uint32_t (&s)[4]);
 __device__ __forceinline__ uint32_t holdem_strength7(const int (&c)[7]) {
     uint32_t s[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
-        const int suit = c[i] / 13, rk = c[i] - 13 * suit;
-        const uint32_t bit = 1u << ((rk + 12) % 13);
-        s[0] |= suit == 0 ? bit : 0u; s[1] |= suit == 1 ? bit : 0u;
-        s[2] |= suit == 2 ? bit : 0u; s[3] |= suit == 3 ? bit : 0u;
-    }
+    for (int i = 0; i < 7; i++) holdem_add_card(s, c[i]);
+    return holdem_strength_masks(s);
+}
+// strength of the seven cards given as four per-suit rank masks
+__device__ __forceinline__ uint32_t holdem_strength_masks(const uint32_t (&s)[4]) {
     const uint32_t any = s[0] | s[1] | s[2] | s[3];
     uint32_t fl = 0;
 #pragma unroll
@@ -289,9 +296,13 @@ struct Limit {
         int w0, w1;
         if (fold0 + fold1 == 1) { w0 = fold1; w1 = fold0; }
         else {
-            const int h0[7] = { card[0], card[2], card[4], card[5], card[6], card[7], card[8] };
-            const int h1[7] = { card[1], card[3], card[4], card[5], card[6], card[7], card[8] };
-            const uint32_t s0 = holdem_strength7(h0), s1 = holdem_strength7(h1);
+            uint32_t bd[4] = {0, 0, 0, 0};                           // the five board cards are shared by both hands
+#pragma unroll
+            for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
+            uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
+            holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
+            holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
+            const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
             w0 = s0 >= s1; w1 = s1 >= s0;
         }
         const int pot = min(chips0, chips1);
@@ -301,7 +312,7 @@ struct Limit {
     }
     // envs/limitholdem.py:40-71
     template <class T> __device__ __forceinline__ void encode_obs(int seat, bool reset_view, T *row) const {
-        row[card[seat]] = (T)1; row[card[2 + seat]] = (T)1;
+        row[seat ? card[1] : card[0]] = (T)1; row[seat ? card[3] : card[2]] = (T)1;   // no dynamic index: card[] stays in registers
         const int np_ = n_public();
 #pragma unroll
         for (int k = 0; k < 5; k++) if (k < np_) row[card[4 + k]] = (T)1;
@@ -438,9 +449,13 @@ struct NoLimit {
         int w0, w1;
         if ((st0 == 1) != (st1 == 1)) { w0 = st1 == 1; w1 = st0 == 1; }
         else {
-            const int h0[7] = { card[0], card[2], card[4], card[5], card[6], card[7], card[8] };
-            const int h1[7] = { card[1], card[3], card[4], card[5], card[6], card[7], card[8] };
-            const uint32_t s0 = holdem_strength7(h0), s1 = holdem_strength7(h1);
+            uint32_t bd[4] = {0, 0, 0, 0};                           // the five board cards are shared by both hands
+#pragma unroll
+            for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
+            uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
+            holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
+            holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
+            const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
             w0 = s0 >= s1; w1 = s1 >= s0;
         }
         const int potm = min(in0, in1);
@@ -450,7 +465,7 @@ struct NoLimit {
     }
     // envs/nolimitholdem.py:47-79: 52 card bits + my chips + max chips
     template <class T> __device__ __forceinline__ void encode_obs(int seat, bool, T *row) const {
-        row[card[seat]] = (T)1; row[card[2 + seat]] = (T)1;
+        row[seat ? card[1] : card[0]] = (T)1; row[seat ? card[3] : card[2]] = (T)1;   // no dynamic index: card[] stays in registers
 #pragma unroll
         for (int k = 0; k < 5; k++) if (k < npub) row[card[4 + k]] = (T)1;
         row[52] = (T)(seat ? in1 : in0);

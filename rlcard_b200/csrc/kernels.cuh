@@ -89,11 +89,12 @@ template <class G>
 __device__ __forceinline__ int pick_action(const uint32_t (&m)[G::MASK_WORDS], uint32_t word, int &cnt) {
     cnt = popc_words<G::MASK_WORDS>(m);
     const int k = (int)__umulhi(word, (uint32_t)cnt);
-    if constexpr (G::A <= 4) {
+    if constexpr (G::A <= 5) {
         uint32_t mm = m[0];
         if (k > 0) mm &= mm - 1;
         if (k > 1) mm &= mm - 1;
         if (k > 2) mm &= mm - 1;
+        if (G::A > 4 && k > 3) mm &= mm - 1;
         return __ffs(mm) - 1;
     } else {
         return kth_set_bit<G::MASK_WORDS>(m, k);
