@@ -23,13 +23,17 @@ def to_np(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.mark.parametrize('chance', ['replay', 'mt19937'])
 @pytest.mark.parametrize('obs_dtype', [torch.uint8, torch.float32])
 @pytest.mark.parametrize('game', FIX_GAMES)
-def test_replay_reference_tapes_vectorised(game, obs_dtype):
+def test_replay_reference_tapes_vectorised(game, obs_dtype, chance):
     """Replay mode: all fixture slots side by side in one VecEnv, lock-step over the record streams;
-    every obs / legal set / player / done / payoff must equal the reference's."""
+    every obs / legal set / player / done / payoff must equal the reference's.  chance = 'replay' feeds the recorded
+    draws, 'mt19937' only the slots' seeds (np.random.RandomState runs on the device, one generator per env)."""
     if rlcard_b200.game_info(game).obs_native_dtype == 1 and obs_dtype == torch.uint8:
         pytest.skip('fractional obs')
+    if chance == 'mt19937' and obs_dtype == torch.float32 and rlcard_b200.game_info(game).obs_native_dtype == 0:
+        pytest.skip('covered by the uint8 case')
     fx = load_fixture(game)
     S = len(fx['slot_seed'])
     recs = [slot_records(fx, s) for s in range(S)]
@@ -37,8 +41,11 @@ def test_replay_reference_tapes_vectorised(game, obs_dtype):
     tape = np.zeros((S, L + 8), np.uint8)
     for s in range(S):
         t = slot_tape(fx, s); tape[s, :len(t)] = t
-    env = rlcard_b200.VecEnv(game, S, mode='replay', obs_dtype=obs_dtype, auto_reset=False)
-    env.set_tape(tape)
+    env = rlcard_b200.VecEnv(game, S, mode=chance, obs_dtype=obs_dtype, auto_reset=False)
+    if chance == 'replay':
+        env.set_tape(tape)
+    else:
+        env.seed_mt19937([int(x) for x in fx['slot_seed']])
     checked = 0
     for tick in range(max(len(r) for r in recs)):
         live = [s for s in range(S) if tick < len(recs[s])]
@@ -81,9 +88,10 @@ def test_replay_reference_tapes_vectorised(game, obs_dtype):
     assert checked == len(fx['rec_slot'])
     err = to_np(env.err)
     assert not (err & 3).any()                      # tape never exhausted / out of range
-    pos = to_np(env.tape_pos)
-    for s in range(S):
-        assert pos[s] == len(slot_tape(fx, s))      # and consumed exactly
+    if chance == 'replay':
+        pos = to_np(env.tape_pos)
+        for s in range(S):
+            assert pos[s] == len(slot_tape(fx, s))      # and consumed exactly
 
 
 class FacadeAdapter:

@@ -11,7 +11,7 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytes
 tail -3 $OUT/pytest_gpu_$TAG.log
 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
 python bench.py > $OUT/bench_default_$TAG.json 2> $OUT/bench_default_$TAG.err; echo "bench default rc=$?"
-for g in blackjack limit-holdem uno; do
+for g in blackjack limit-holdem uno no-limit-holdem; do
   python bench.py --game $g --steps 50 --warmup 5 > $OUT/bench_${g}_$TAG.json 2> $OUT/bench_${g}_$TAG.err; echo "bench $g rc=$?"
 done
 for g in doudizhu scout; do
