@@ -365,7 +365,7 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u8', 'data': 'synthetic',
+        'dtype': 'f32' if odt == torch.float32 else 'u8', 'data': 'synthetic',
         'config': {'workload': '%s, %d envs per GPU, obs %s[%d] + legal mask u8[%d] + action/player/done/payoffs per '
                                'env-step' % (args.game, E, args.obs_dtype, info.obs_stride, info.num_actions),
                    'envs_per_gpu': E, 'env_steps_per_launch_per_env': T, 'policy': 'uniform-random legal (Philox, on device)',
