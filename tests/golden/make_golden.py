@@ -101,11 +101,26 @@ GAMES = {
     'doudizhu': (8, 3, 0.0, 0.25),
     'scout': (8, 2, 0.0, 0.2),
     'no-limit-holdem': (24, 40, 0.0, 1.0),
+    # rare path: single long UNO episodes in which the draw pile runs out and UnoRound.replace_deck
+    # (round.py:155-160) reshuffles the played pile back in; seeds are scanned until `slots` such episodes are found
+    'uno-reshuffle': (6, 1, 0.0, 0.3),
 }
 
 
 def record_game(rlcard, game, out_dir):
     slots, episodes, p_raw, p_view = GAMES[game]
+    fixture_name, want_reshuffle = game, game == 'uno-reshuffle'
+    reshuffles = {'n': 0}
+    if want_reshuffle:
+        game = 'uno'
+        from rlcard.games.uno.round import UnoRound
+        if not hasattr(UnoRound, '_orig_replace_deck'):
+            UnoRound._orig_replace_deck = UnoRound.replace_deck
+
+            def counted(self):
+                reshuffles['n'] += 1
+                return UnoRound._orig_replace_deck(self)
+            UnoRound.replace_deck = counted
     probe = rlcard.make(game, config={'seed': 0})
     P, A = probe.num_players, probe.num_actions
     D = max(int(np.prod(s)) for s in probe.state_shape)
@@ -128,8 +143,12 @@ def record_game(rlcard, game, out_dir):
         R['legal'].append(np.packbits(legal, bitorder='little'))
         R['payoffs'].append(np.zeros(P) if payoffs is None else np.asarray(payoffs, np.float64))
 
-    for slot in range(slots):
-        seed = 1000 * (list(GAMES).index(game) + 1) + slot
+    slot, candidate = 0, 0
+    while slot < slots:
+        seed = 1000 * (list(GAMES).index(fixture_name) + 1) + candidate
+        candidate += 1
+        mark = {k: len(v) for k, v in R.items()}
+        reshuffles['n'] = 0
         env = rlcard.make(game, config={'seed': seed})
         rec = TapeRecorder(env.np_random)
         env.np_random = rec
@@ -160,7 +179,13 @@ def record_game(rlcard, game, out_dir):
                 emit(slot, 1, a, env, state)
                 views(env.is_over())
             emit(slot, 3, 0, env, None, env.get_payoffs())
+        if want_reshuffle and reshuffles['n'] == 0:          # no reshuffle in this episode: drop it, try the next seed
+            for k in R:
+                del R[k][mark[k]:]
+            seeds.pop()
+            continue
         tapes.append(np.asarray(rec.tape, np.uint8))
+        slot += 1
 
     off = np.zeros(slots + 1, np.int64)
     off[1:] = np.cumsum([len(t) for t in tapes])
@@ -172,10 +197,10 @@ def record_game(rlcard, game, out_dir):
         rec_done=np.asarray(R['done'], np.uint8), rec_obs=np.stack(R['obs']),
         rec_obs_dim=np.asarray(R['obs_dim'], np.int32), rec_legal=np.stack(R['legal']),
         rec_payoffs=np.stack(R['payoffs']))
-    path = os.path.join(out_dir, game.replace('-', '_') + '.npz')
+    path = os.path.join(out_dir, fixture_name.replace('-', '_') + '.npz')
     np.savez_compressed(path, **out)
     print('%-14s slots=%d records=%d tape=%d bytes -> %s (%.1f KiB)' % (
-        game, slots, len(R['slot']), off[-1], path, os.path.getsize(path) / 1024))
+        fixture_name, slots, len(R['slot']), off[-1], path, os.path.getsize(path) / 1024))
 
 
 if __name__ == '__main__':

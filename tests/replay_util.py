@@ -9,6 +9,15 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 ALL_GAMES = ['blackjack', 'leduc-holdem', 'limit-holdem', 'uno', 'doudizhu', 'scout', 'no-limit-holdem']
 
 
+# extra fixtures of a game that pin rare paths: name -> env id
+EXTRA_FIXTURES = {'uno-reshuffle': 'uno'}
+ALL_FIXTURES = ALL_GAMES + list(EXTRA_FIXTURES)
+
+
+def fixture_game(name):
+    return EXTRA_FIXTURES.get(name, name)
+
+
 def have_fixture(game):
     return os.path.exists(os.path.join(GOLDEN, game.replace('-', '_') + '.npz'))
 

@@ -6,7 +6,7 @@ import torch
 
 import oracle
 import rlcard_b200
-from replay_util import ALL_GAMES, check_slot, have_fixture, load_fixture, slot_records, slot_tape
+from replay_util import ALL_FIXTURES, ALL_GAMES, check_slot, fixture_game, have_fixture, load_fixture, slot_records, slot_tape
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +16,7 @@ def built(game):
 
 
 GAMES = [g for g in ALL_GAMES if built(g)]
-FIX_GAMES = [g for g in GAMES if have_fixture(g)]
+FIX_GAMES = [g for g in ALL_FIXTURES if have_fixture(g) and built(fixture_game(g))]
 
 
 def to_np(t):
@@ -30,11 +30,12 @@ def test_replay_reference_tapes_vectorised(game, obs_dtype, chance):
     """Replay mode: all fixture slots side by side in one VecEnv, lock-step over the record streams;
     every obs / legal set / player / done / payoff must equal the reference's.  chance = 'replay' feeds the recorded
     draws, 'mt19937' only the slots' seeds (np.random.RandomState runs on the device, one generator per env)."""
+    fx = load_fixture(game)
+    game = fixture_game(game)
     if rlcard_b200.game_info(game).obs_native_dtype == 1 and obs_dtype == torch.uint8:
         pytest.skip('fractional obs')
     if chance == 'mt19937' and obs_dtype == torch.float32 and rlcard_b200.game_info(game).obs_native_dtype == 0:
         pytest.skip('covered by the uint8 case')
-    fx = load_fixture(game)
     S = len(fx['slot_seed'])
     recs = [slot_records(fx, s) for s in range(S)]
     L = max(len(slot_tape(fx, s)) for s in range(S))
@@ -121,6 +122,7 @@ def test_make_facade_reproduces_reference_from_seed(game):
     """rlcard_b200.make(env, {'seed': s}) == rlcard.make(env, {'seed': s}): np.random.RandomState runs on
     the device (MT19937 + numpy legacy bounded draws), no tape."""
     fx = load_fixture(game)
+    game = fixture_game(game)
     for slot in range(min(3, len(fx['slot_seed']))):
         env = rlcard_b200.make(game, {'seed': int(fx['slot_seed'][slot])})
         check_slot(fx, slot, FacadeAdapter(env), game + ' (facade)')

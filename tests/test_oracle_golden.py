@@ -3,9 +3,9 @@ import numpy as np
 import pytest
 
 import oracle
-from replay_util import ALL_GAMES, check_slot, have_fixture, load_fixture, slot_records, slot_tape
+from replay_util import ALL_FIXTURES, check_slot, fixture_game, have_fixture, load_fixture, slot_records, slot_tape
 
-GAMES = [g for g in ALL_GAMES if have_fixture(g)]
+GAMES = [g for g in ALL_FIXTURES if have_fixture(g)]
 
 
 @pytest.mark.parametrize('game', GAMES)
@@ -13,7 +13,7 @@ def test_oracle_replays_reference_tape(game):
     fx = load_fixture(game)
     total = 0
     for slot in range(len(fx['slot_seed'])):
-        env = oracle.OracleEnv(game)
+        env = oracle.OracleEnv(fixture_game(game))
         tape = slot_tape(fx, slot)
         env.set_tape(tape)
         total += check_slot(fx, slot, env, game)
@@ -28,7 +28,7 @@ def test_oracle_mt19937_reproduces_reference_from_seed(game):
     from the seed alone equal the draws the reference's RandomState made."""
     fx = load_fixture(game)
     for slot in range(len(fx['slot_seed'])):
-        env = oracle.OracleEnv(game)
+        env = oracle.OracleEnv(fixture_game(game))
         env.seed(int(fx['slot_seed'][slot]))
         env.record()
         check_slot(fx, slot, env, game + ' (mt)')
