@@ -126,16 +126,16 @@ struct Doudizhu {
         // candidate id ranges [lo1,hi1) u [lo2,hi2) (+ rocket, handled as part of range 2 when adjacent)
         int lo1 = 0, hi1 = kDdzPass, lo2 = 0, hi2 = 0;
         if (!lead) {
-            const int tt = tab.type[greater_action], tw = tab.weight[greater_action];
+            const int tt = __ldg(tab.type + (greater_action)), tw = __ldg(tab.weight + (greater_action));
             if (tt == kDdzTypeRocket) { lo1 = hi1 = 0; }
-            else if (tt == kDdzTypeBomb) { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = kDdzRocket + 1; }   // larger bombs + rocket
-            else { lo1 = (int)tab.tw_start[tt * 17 + tw + 1]; hi1 = (int)tab.tw_start[tt * 17 + 16]; lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
+            else if (tt == kDdzTypeBomb) { lo1 = (int)__ldg(tab.tw_start + (tt * 17 + tw + 1)); hi1 = kDdzRocket + 1; }   // larger bombs + rocket
+            else { lo1 = (int)__ldg(tab.tw_start + (tt * 17 + tw + 1)); hi1 = (int)__ldg(tab.tw_start + (tt * 17 + 16)); lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
         }
         // level 0: one lane per batch of 32 mask words (1024 ids): in range and its nibble-wise minimum contained?
         bool blive = false;
         if (lane < (MASK_WORDS + 31) / 32) {
             const int a0 = 1024 * lane, a1 = a0 + 1024;
-            blive = ((a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2)) && ddz_contains(H, tab.need[864 + lane]);
+            blive = ((a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2)) && ddz_contains(H, __ldg(tab.need + (864 + lane)));
         }
         uint32_t lb = __ballot_sync(kFull, blive);
         int cnt = 0, nl = 0;
@@ -146,14 +146,14 @@ struct Doudizhu {
             if (j < MASK_WORDS) {
                 const int a0 = 32 * j, a1 = a0 + 32;
                 const bool overlap = (a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2);
-                live = overlap && ddz_contains(H, tab.need[j]);
+                live = overlap && ddz_contains(H, __ldg(tab.need + (j)));
             }
             uint32_t lw = __ballot_sync(kFull, live);
             while (lw) {                                                       // level 2: expand the live words
                 const int b = __ffs(lw) - 1; lw &= lw - 1;
                 const int jj = wb * 32 + b, id = 32 * jj + lane;
                 const bool cand = (id >= lo1 && id < hi1) || (id >= lo2 && id < hi2);
-                const bool ok = cand && ddz_contains(H, tab.rows[id]);
+                const bool ok = cand && ddz_contains(H, __ldg(tab.rows + (id)));
                 const uint32_t word = __ballot_sync(kFull, ok);
                 if (word) {
                     if (lane == 0) { smask[jj] = word; slist[nl] = (uint32_t)jj | ((uint32_t)cnt << 10); }
@@ -193,7 +193,7 @@ struct Doudizhu {
         }
         const int p = cur;
         if (id != kDdzPass) {
-            const uint64_t c = tab.rows[id];
+            const uint64_t c = __ldg(tab.rows + (id));
             put3(hand, p, sel3(hand, p) - c);
             put3(played, p, sel3(played, p) + c);
             greater = p; greater_action = (uint32_t)id;
@@ -219,7 +219,7 @@ struct Doudizhu {
             dst[lane + 32] = (T)v;
         }
     }
-    __device__ __forceinline__ uint64_t action_counts(uint32_t id) const { return tab.rows[id]; }
+    __device__ __forceinline__ uint64_t action_counts(uint32_t id) const { return __ldg(tab.rows + (id)); }
     template <class T> __device__ __forceinline__ void one_hot(T *dst, int n, int size, int lane) const {   // :169-173 (Q-DDZ1)
         if (lane == 0) dst[n >= 1 ? n - 1 : size - 1] = (T)1;
     }
