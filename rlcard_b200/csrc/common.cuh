@@ -155,13 +155,25 @@ __device__ __forceinline__ void shuffle_tail_u8(Ch &ch, uint8_t *x, int n, int t
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bf_get(uint32_t w, int pos, int len) { return (w >> pos) & ((1u << len) - 1u); }
 
+// position of the n-th (0-based) set bit of m, n < popc(m): five popc halvings, branch free
+// (the __fns intrinsic expands to ~50 instructions; this is ~30 and has no sign / offset handling)
+__device__ __forceinline__ int nth_set_bit32(uint32_t m, int n) {
+    int pos = 0, c;
+    c = __popc(m & 0xffffu);          if (n >= c) { n -= c; pos += 16; }
+    c = __popc((m >> pos) & 0xffu);   if (n >= c) { n -= c; pos += 8; }
+    c = __popc((m >> pos) & 0xfu);    if (n >= c) { n -= c; pos += 4; }
+    c = __popc((m >> pos) & 0x3u);    if (n >= c) { n -= c; pos += 2; }
+    c = (int)((m >> pos) & 1u);       if (n >= c) { pos += 1; }
+    return pos;
+}
+
 // k-th (0-based) set bit of a multi-word mask
 template <int WORDS>
 __device__ __forceinline__ int kth_set_bit(const uint32_t (&m)[WORDS], int k) {
 #pragma unroll
     for (int w = 0; w < WORDS; w++) {
         const int c = __popc(m[w]);
-        if (k < c) return 32 * w + (int)__fns(m[w], 0, k + 1);
+        if (k < c) return 32 * w + nth_set_bit32(m[w], k);
         k -= c;
     }
     return -1;

@@ -55,10 +55,10 @@ struct Blackjack {
         deck_len--;
         if constexpr (Ch::kKind == 0) {                          // idx-th remaining card of the id-ordered deck
             const int nlo = __popc(mlo);
-            int c;
-            if (idx < nlo) { c = (int)__fns(mlo, 0, idx + 1); mlo &= ~(1u << c); }
-            else { const int b = (int)__fns(mhi, 0, idx - nlo + 1); mhi &= ~(1u << b); c = 32 + b; }
-            return c;
+            const bool hi = idx >= nlo;
+            const int b = nth_set_bit32(hi ? mhi : mlo, hi ? idx - nlo : idx);
+            mlo &= hi ? 0xffffffffu : ~(1u << b); mhi &= hi ? ~(1u << b) : 0xffffffffu;
+            return b + (hi ? 32 : 0);
         } else {
             const int c = deck[idx];
             for (int k = idx; k < deck_len; k++) deck[k] = deck[k + 1];

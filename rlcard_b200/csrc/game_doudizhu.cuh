@@ -182,7 +182,7 @@ struct Doudizhu {
         }
         const uint32_t ee = slist[c - 1];
         const int jj = (int)(ee & 1023u);
-        return 32 * jj + (int)__fns(smask[jj], 0, k - (int)(ee >> 10) + 1);
+        return 32 * jj + nth_set_bit32(smask[jj], k - (int)(ee >> 10));
     }
     // env.py:65-86, game.py:53-81, round.py:52-79, player.py:78-108, judger.py:335-348
     template <class WCh> __device__ void step(int id, WCh &, const uint32_t *smask, uint8_t *scratch, int lane, int &err) {

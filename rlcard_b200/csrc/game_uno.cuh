@@ -95,7 +95,7 @@ struct UnoT {
             const int c = (r >= n0) + (r >= n1) + (r >= n2);
             const uint32_t u = c == 0 ? u0 : (c == 1 ? u1 : (c == 2 ? u2 : u3));
             r -= c == 0 ? 0 : (c == 1 ? n0 : (c == 2 ? n1 : n2));
-            const int t = (int)__fns(u, 0, r + 1) >> 1;
+            const int t = nth_set_bit32(u, r) >> 1;
             const uint32_t dec = 1u << (2 * t);
             dk[0] -= c == 0 ? dec : 0u; dk[1] -= c == 1 ? dec : 0u; dk[2] -= c == 2 ? dec : 0u; dk[3] -= c == 3 ? dec : 0u;
             return 15 * c + t;
