@@ -23,8 +23,17 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_ENVS = {'blackjack': 65536, 'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384,
                 'doudizhu': 8192, 'scout': 8192, 'no-limit-holdem': 16384}
+# the reference's own Python loop (env.run with RandomAgents, 8 spawned processes) as measured in the build container
+# (it cannot travel to the GPU box).  Context for the CPU arm, which is a multi-threaded C port.
+PY_REFERENCE_STEPS_PER_S = {'blackjack': 74843, 'leduc-holdem': 173633, 'limit-holdem': 119464, 'uno': 160893,
+                            'doudizhu': 6689, 'scout': 6492}
 METRIC = 'env steps/sec (random policy, obs+mask)'
 UNIT = 'env-steps/s'
+
+
+def workload_name(game, envs, obs_dtype, obs_stride, num_actions):
+    return '%s, %d envs per GPU, obs %s[%d] + legal mask u8[%d] + action/player/done/payoffs per env-step' % (
+        game, envs, obs_dtype, obs_stride, num_actions)
 
 
 def algorithmic_bytes_per_env_step(info, obs_elem, T):
@@ -136,8 +145,14 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * args.envs * T / value, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-            'config': {'workload': '%s, %d envs per GPU, %d env-steps per launch' % (args.game, args.envs, T)},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'config': {'workload': workload_name(args.game, args.envs, 'float32' if args.game == 'scout' else 'uint8',
+                                                 912 if args.game == 'doudizhu' else max(oracle.info(args.game)[2]),
+                                                 oracle.info(args.game)[1]),
+                       'envs_per_gpu': args.envs, 'env_steps_per_launch_per_env': T,
+                       'sample': 'the CPU arm runs %d of the %d envs per pass' % (min(args.envs, 8192), args.envs)},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
+                             'python_reference_build_container': {'value': PY_REFERENCE_STEPS_PER_S.get(args.game), 'unit': UNIT,
+                                                                  'what': 'rlcard env.run + RandomAgent, 8 processes (BASELINE.md 2)'}},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'wall_s': time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
@@ -366,8 +381,7 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if odt == torch.float32 else 'u8', 'data': 'synthetic',
-        'config': {'workload': '%s, %d envs per GPU, obs %s[%d] + legal mask u8[%d] + action/player/done/payoffs per '
-                               'env-step' % (args.game, E, args.obs_dtype, info.obs_stride, info.num_actions),
+        'config': {'workload': workload_name(args.game, E, args.obs_dtype, info.obs_stride, info.num_actions),
                    'envs_per_gpu': E, 'env_steps_per_launch_per_env': T, 'policy': 'uniform-random legal (Philox, on device)',
                    'chance': 'Philox4x32-10 keyed (seed, global env id, env-step index)', 'auto_reset': True,
                    'l2': 'trajectory written per launch = %.0f MB > 126 MB L2' % (E * T * per_step / 1e6)},
@@ -389,6 +403,8 @@ def main():
         threads = os.cpu_count() or 1
         v, dt, steps, n = cpu_port_run(args.game, E, T, args.seed, threads)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'python_reference_build_container': {'value': PY_REFERENCE_STEPS_PER_S.get(args.game), 'unit': UNIT,
+                                                                     'what': 'rlcard env.run + RandomAgent, 8 processes (BASELINE.md 2)'},
                                 'sample': '%d env-steps in %.1f s: %d envs x %d-step launches of the C oracle, same Philox '
                                           'chance + policy, obs f32 + mask to host RAM' % (steps, dt, n, T)}
     print(json.dumps(line), flush=True)
