@@ -119,7 +119,7 @@ def cpu_port_run(game, envs, T, seed, threads, budget_s=12.0):
     while True:
         steps += L.orc_envs_rollout(*args)
         dt = time.perf_counter() - t0
-        if dt > budget_s or steps >= 400_000_000:
+        if dt > budget_s or steps >= 40_000_000_000:
             break
     return steps / dt, dt, steps, n
 
