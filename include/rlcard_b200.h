@@ -49,7 +49,7 @@ enum rlc_status {
 
 /* where the engines' bounded random draws come from (replaces game.np_random, env.py:228-231) */
 enum rlc_chance {
-    RLC_CHANCE_PHILOX = 0,   /* throughput: Philox4x32-10 keyed (seed, global env id, episode) */
+    RLC_CHANCE_PHILOX = 0,   /* throughput: Philox4x32-10 keyed (seed, global env id, env-step index) */
     RLC_CHANCE_TAPE = 1,     /* replay: recorded np.random draws, uint8 tape per env          */
     RLC_CHANCE_MT19937 = 2   /* replay from a seed: np.random.RandomState on device           */
 };

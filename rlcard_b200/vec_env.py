@@ -50,7 +50,7 @@ def seed_words(seed):
 class VecEnv:
     """``num_envs`` environments of one game on one GPU.
 
-    mode 'throughput': Philox4x32-10 chance keyed by (seed, env_id_base + i, episode).
+    mode 'throughput': Philox4x32-10 chance keyed by (seed, env_id_base + i, env-step index).
     mode 'replay':     chance draws come from a uint8 tape per env (``set_tape``), i.e. the
                        reference's recorded np.random outcomes.
     mode 'mt19937':    np.random.RandomState on device, seeded per env like ``rlcard.make(seed=...)``.
