@@ -291,12 +291,8 @@ def main():
         Ke = args.e2e_step_api_steps
         env2 = rlcard_b200.VecEnv(args.game, E, device=dev, seed=args.seed + 2, env_id_base=rank * E, obs_dtype=odt)
         h_act = torch.zeros(E, dtype=torch.int32).pin_memory()
-        h_obs = torch.zeros((E, info.obs_stride), dtype=odt).pin_memory()
-        h_mask = torch.zeros((E, 4), dtype=torch.uint8).pin_memory()
-        h_cur = torch.zeros(E, dtype=torch.int32).pin_memory()
-        h_done = torch.zeros(E, dtype=torch.uint8).pin_memory()
-        h_pay = torch.zeros((E, info.num_players), dtype=torch.float32).pin_memory()
-        d_act = torch.zeros(E, dtype=torch.int32, device=dev)
+        h_buf, hv = env2.alloc_host_step()
+        h_mask = hv['mask']
         # k-th legal action LUT: code = 4 mask bits, r uniform in [0,12) (12 = lcm(1..4)) -> exact uniform
         lut = np.zeros((16, 12), np.int32)
         for code in range(1, 16):
@@ -310,12 +306,7 @@ def main():
         def host_step(i):
             code = ((m32.astype(np.uint64) * np.uint64(0x01020408)) >> np.uint64(24)) & np.uint64(15)
             np.take(lut.reshape(-1), code.astype(np.int64) * 12 + rnd[i], out=h_act.numpy())
-            d_act.copy_(h_act, non_blocking=True)
-            env2.step(d_act)
-            h_obs.copy_(env2.obs, non_blocking=True); h_mask.copy_(env2.mask, non_blocking=True)
-            h_cur.copy_(env2.cur_player, non_blocking=True); h_done.copy_(env2.done, non_blocking=True)
-            h_pay.copy_(env2.payoffs, non_blocking=True)
-            torch.cuda.synchronize(dev)
+            env2.step_host(h_act, h_buf)
 
         env2.reset()
         h_mask.copy_(env2.mask); torch.cuda.synchronize(dev)
@@ -329,11 +320,11 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        d2h = sum(x.numel() * x.element_size() for x in (h_obs, h_mask, h_cur, h_done, h_pay))
+        d2h = h_buf.numel()
         e2e_step = {'value': world * E * Ke / float(dt.item()), 'unit': UNIT, 'h2d_bytes_per_step': h_act.numel() * 4,
                     'd2h_bytes_per_step': d2h, 'steps': Ke,
-                    'what': 'VecEnv.step per env-step: numpy uniform-legal policy on host -> H2D actions (pinned) -> '
-                            'rlc_step -> D2H obs+mask+player+done+payoffs (pinned), synchronous round trip'}
+                    'what': 'VecEnv.step_host per env-step: numpy uniform-legal policy on host -> H2D actions (pinned) -> '
+                            'rlc_step -> one D2H of obs+mask+player+done+payoffs (pinned), synchronous round trip'}
         env2.check_errors()
 
     # ---- optional: the DMC actor data path (config 5): rollout window + rlc_dmc_collect into per-position pools

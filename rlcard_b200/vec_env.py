@@ -90,14 +90,26 @@ class VecEnv:
         N, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
             self.state = torch.zeros((self.state_words, N), dtype=torch.int32, device=dev)
-            self.obs = torch.zeros((N, self.obs_stride), dtype=obs_dtype, device=dev)
+            # the five per-step outputs are views of ONE device buffer (256-byte aligned sections), so a host
+            # consumer fetches a whole step with a single device-to-host copy (step_host)
+            esz = 4 if obs_dtype == torch.float32 else 1
+            msz = (self.mask_words * 4) if self.mask_bitpacked else self.num_actions
+            sizes = [N * self.obs_stride * esz, N * msz, N * 4, N, N * self.num_players * 4]
+            offs, cur = [], 0
+            for sz in sizes:
+                offs.append(cur)
+                cur += (sz + 255) & ~255
+            self._out = torch.zeros(cur, dtype=torch.uint8, device=dev)
+            sec = lambda k: self._out[offs[k]:offs[k] + sizes[k]]
+            self._sections = (offs, sizes)
+            self.obs = sec(0).view(obs_dtype).view(N, self.obs_stride)
             if self.mask_bitpacked:
-                self.mask = torch.zeros((N, self.mask_words), dtype=torch.int32, device=dev)
+                self.mask = sec(1).view(torch.int32).view(N, self.mask_words)
             else:
-                self.mask = torch.zeros((N, self.num_actions), dtype=torch.uint8, device=dev)
-            self.cur_player = torch.zeros(N, dtype=torch.int32, device=dev)
-            self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
-            self.payoffs = torch.zeros((N, self.num_players), dtype=torch.float32, device=dev)
+                self.mask = sec(1).view(N, self.num_actions)
+            self.cur_player = sec(2).view(torch.int32)
+            self.done = sec(3)
+            self.payoffs = sec(4).view(torch.float32).view(N, self.num_players)
             self.err = torch.zeros(N, dtype=torch.int32, device=dev)
             self.terminal_obs = (torch.zeros((N, self.num_players, self.obs_stride), dtype=obs_dtype, device=dev)
                                  if terminal_obs else None)
@@ -193,6 +205,30 @@ class VecEnv:
         self.launches += 1
         return self.obs, self.mask, self.cur_player, self.done, self.payoffs
 
+    def alloc_host_step(self):
+        """Pinned host mirror of the per-step outputs: (buffer, dict of views obs / mask / cur_player / done / payoffs)."""
+        offs, sizes = self._sections
+        N = self.num_envs
+        buf = torch.zeros(self._out.numel(), dtype=torch.uint8).pin_memory()
+        sec = lambda k: buf[offs[k]:offs[k] + sizes[k]]
+        views = {'obs': sec(0).view(self.obs_dtype).view(N, self.obs_stride),
+                 'mask': sec(1).view(torch.int32).view(N, self.mask_words) if self.mask_bitpacked else sec(1).view(N, self.num_actions),
+                 'cur_player': sec(2).view(torch.int32), 'done': sec(3),
+                 'payoffs': sec(4).view(torch.float32).view(N, self.num_players)}
+        return buf, views
+
+    def step_host(self, host_actions, host_buf, device_actions=None):
+        """Env.step for a HOST agent: actions come from (pinned) host memory, the whole post-step view (obs, mask,
+        cur_player, done, payoffs) lands in ``host_buf`` (alloc_host_step) with one device-to-host copy.  Synchronous."""
+        if device_actions is None:
+            device_actions = getattr(self, '_h_actions', None)
+            if device_actions is None:
+                device_actions = self._h_actions = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        device_actions.copy_(host_actions, non_blocking=True)
+        self.step(device_actions)
+        host_buf.copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def alloc_trajectory(self, T, obs=True, mask=True):
         N, dev = self.num_envs, self.device
         tr = {}
@@ -276,6 +312,30 @@ class VecEnv:
             self._copy_stream.synchronize()
             main.synchronize()
         return host_out
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to resume this VecEnv bit-exactly: the packed env state (it carries the episode / step
+        counters the Philox streams are keyed on), the replay cursors or MT19937 generators, and the error flags."""
+        d = {'env_id': self.name, 'num_envs': self.num_envs, 'seed': self.seed_value, 'env_id_base': self.env_id_base,
+             'chance': self.chance, 'state': self.state.clone(), 'err': self.err.clone()}
+        if self.tape is not None:
+            d['tape'], d['tape_pos'] = self.tape.clone(), self.tape_pos.clone()
+        if self.mt is not None:
+            d['mt'] = self.mt.clone()
+        return d
+
+    def load_state_dict(self, d):
+        if d['env_id'] != self.name or d['num_envs'] != self.num_envs or d['chance'] != self.chance:
+            raise ValueError('checkpoint is for %s x %d (chance %d)' % (d['env_id'], d['num_envs'], d['chance']))
+        self.seed_value, self.env_id_base = int(d['seed']), int(d['env_id_base'])
+        self.state.copy_(d['state']); self.err.copy_(d['err'])
+        if 'tape' in d:
+            self.tape = d['tape'].to(self.device).clone(); self.tape_pos = d['tape_pos'].to(self.device).clone()
+        if 'mt' in d:
+            self.mt = d['mt'].to(self.device).clone()
+        self._buf = None
+        self.get_state(None)                                  # refresh obs / mask / cur_player from the restored state
 
     # ------------------------------------------------------------------ rollout helpers (callers of the path)
     def run(self, policy, num_steps, auto_reset=True):

@@ -310,3 +310,20 @@ def test_illegal_actions_in_every_game_are_flagged():
         obs, mask, cur, done, pay = env.get_state(None)
         m = mask if not env.mask_bitpacked else (mask != 0)
         assert bool(((m != 0).sum(-1) >= 1)[~done.bool()].all()), game
+
+
+@pytest.mark.parametrize('game', ['leduc-holdem', 'uno', 'doudizhu'])
+def test_checkpoint_resume_is_bit_exact(game):
+    """state_dict / load_state_dict: a VecEnv restored into a fresh object continues with the same trajectory."""
+    n, T = 300, 20
+    a = rlcard_b200.VecEnv(game, n, seed=8)
+    a.reset()
+    a.rollout_random(T)
+    ck = a.state_dict()
+    want = a.rollout_random(T)
+    b = rlcard_b200.VecEnv(game, n, seed=12345)                       # seed comes from the checkpoint
+    b.load_state_dict(ck)
+    assert torch.equal(b.obs, want['obs'][0]) and torch.equal(b.cur_player, want['player'][0])
+    got = b.rollout_random(T)
+    for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+        assert torch.equal(got[k], want[k]), (game, k)
