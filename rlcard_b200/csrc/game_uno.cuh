@@ -117,26 +117,26 @@ struct UnoT {
         } else cards[107 - pl] = (uint8_t)code;
         pl++;
     }
-    __device__ __forceinline__ void to_hand(int p, int code) {
+    __device__ __forceinline__ void to_hand(int p, int code) {          // branch free: lanes hold different cards
         const int c = code / 15, t = code - 15 * c;
-        if (t < 13) hc_add(p, c, 1u << (2 * t));
-        else {
-            const int base = t == 13 ? 0 : 11;
-            uint32_t w = hwp(p);
-            const int cnt = (w >> base) & 7;
-            w = (w & ~(3u << (base + 3 + 2 * cnt))) | ((uint32_t)c << (base + 3 + 2 * cnt));
-            set_hw(p, w + (1u << base));
-        }
+        const bool wild = t >= 13;
+        hc_add(p, c, wild ? 0u : 1u << (2 * min(t, 12)));
+        const int base = t == 13 ? 0 : 11;
+        const uint32_t w = hwp(p);
+        const int cnt = (w >> base) & 7;
+        const uint32_t w2 = ((w & ~(3u << (base + 3 + 2 * cnt))) | ((uint32_t)c << (base + 3 + 2 * cnt))) + (1u << base);
+        set_hw(p, wild ? w2 : w);
     }
     // register-friendly accessors (no dynamically indexed arrays -> no local memory)
     __device__ __forceinline__ uint32_t hcp(int p, int c_static) const { return p ? hc[1][c_static] : hc[0][c_static]; }
     __device__ __forceinline__ uint32_t hwp(int p) const { return p ? hw[1] : hw[0]; }
     __device__ __forceinline__ void set_hw(int p, uint32_t v) { hw[0] = p ? hw[0] : v; hw[1] = p ? v : hw[1]; }
     __device__ __forceinline__ void hc_add(int p, int c, uint32_t delta) {
+        const int wi = 4 * p + c;
 #pragma unroll
         for (int q = 0; q < 2; q++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) hc[q][k] += (q == p && k == c) ? delta : 0u;
+            for (int k = 0; k < 4; k++) hc[q][k] += (wi == 4 * q + k) ? delta : 0u;
     }
     __device__ __forceinline__ int wild_count(int p, int t) const { return (hwp(p) >> (t == 13 ? 0 : 11)) & 7; }
     __device__ __forceinline__ int take_first_wild(int p, int t) {        // original colour of the first held wild of trait t
@@ -208,9 +208,10 @@ struct UnoT {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const uint32_t w = hcp(cur, c);
-            uint32_t have = 0;
-#pragma unroll
-            for (int t = 0; t < 13; t++) have |= ((w >> (2 * t)) & 3u) ? (1u << t) : 0u;
+            // bit t of `have` <- 2-bit counter t of w is non-zero: OR the counter halves, then squeeze the even bits
+            uint32_t have = (w | (w >> 1)) & 0x01555555u;
+            have = (have | (have >> 1)) & 0x33333333u; have = (have | (have >> 2)) & 0x0f0f0f0fu;
+            have = (have | (have >> 4)) & 0x00ff00ffu; have = (have | (have >> 8)) & 0x1fffu;
             uint32_t ok = (c == tcolor) ? have : 0u;
             if (!twild) ok |= have & (1u << ttrait);
             bits |= (uint64_t)ok << (15 * c);
