@@ -38,14 +38,14 @@ struct BetRound {
         return m;
     }
     // round.py:53-93; returns chips the actor adds, sets folded flag of the actor
-    __device__ __forceinline__ int proceed(int action, int raise_amount, bool &fold) {
+    __device__ __forceinline__ int proceed(int action, int raise_amount, bool &fold) {   // branch free (lanes act differently)
         const int mx = max(raised0, raised1), mine = pointer ? raised1 : raised0;
-        int diff = 0; fold = false;
-        if (action == kCall) { diff = mx - mine; not_raise_num++; }
-        else if (action == kRaise) { diff = mx - mine + raise_amount; have_raised++; not_raise_num = 1; }
-        else if (action == kFold) fold = true;
-        else not_raise_num++;
-        if (pointer) raised1 += diff; else raised0 += diff;
+        const bool call = action == kCall, raise = action == kRaise;
+        fold = action == kFold;
+        const int diff = call ? mx - mine : (raise ? mx - mine + raise_amount : 0);
+        have_raised += raise ? 1 : 0;
+        not_raise_num = raise ? 1 : (fold ? not_raise_num : not_raise_num + 1);
+        raised1 += pointer ? diff : 0; raised0 += pointer ? 0 : diff;
         pointer ^= 1;     // 2 players: the other seat is never the folded one
         return diff;
     }
@@ -412,12 +412,11 @@ struct NoLimit {
         if (id < 0 || id > 4 || !((m >> id) & 1u)) { id = kFoldA; err |= 4; }   // the reference has no fallback here
         const int p = pointer, pt = pot();
         const int mine = p ? raised1 : raised0, mx = max(raised0, raised1), rem = p ? rem1 : rem0;
-        int nr = mine, amount = 0; bool fold = false;
-        if (id == kCheckCall) { amount = mx - mine; nr = mx; nrn++; }
-        else if (id == kAllIn) { amount = rem; nr = mine + rem; nrn = 1; }
-        else if (id == kPot) { amount = pt; nr = mine + pt; nrn = 1; }
-        else if (id == kHalfPot) { amount = pt >> 1; nr = mine + (pt >> 1); nrn = 1; }
-        else fold = true;
+        const bool fold = id == kFoldA, cc = id == kCheckCall;                  // branch free: lanes act differently
+        const int add = id == kAllIn ? rem : (id == kPot ? pt : (id == kHalfPot ? (pt >> 1) : 0));
+        const int amount = cc ? mx - mine : add;
+        const int nr = cc ? mx : mine + add;
+        nrn = cc ? nrn + 1 : (fold ? nrn : 1);
         if (p) raised1 = nr; else raised0 = nr;
         bet(p, amount);
         int stp = p ? st1 : st0;
