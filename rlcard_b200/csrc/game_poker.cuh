@@ -156,10 +156,16 @@ struct Leduc {
 // 7-card evaluator on rank/suit bit masks (orders hands like games/limitholdem/utils.py
 // compare_hands).  card id = 13*suit + rank (A=0, 2..K = 1..12).
 // ========================================================================================
-__device__ __forceinline__ uint32_t top_bits(uint32_t m, int keep) {   // keep the `keep` highest set bits
-    while (__popc(m) > keep) m &= m - 1;
+// keep the `keep` highest set bits.  Branch free: seven distinct cards leave at most keep + 3 ranks in any mask this is
+// called on (the kickers of a made hand), so three predicated removals of the lowest bit suffice.
+__device__ __forceinline__ uint32_t top_bits(uint32_t m, int keep) {
+    const int r = __popc(m) - keep;
+    m = r > 0 ? m & (m - 1) : m;
+    m = r > 1 ? m & (m - 1) : m;
+    m = r > 2 ? m & (m - 1) : m;
     return m;
 }
+__device__ __forceinline__ uint32_t top_bit(uint32_t m) { return 31u - (uint32_t)__clz(m | 1u); }   // 0 for m == 0
 __device__ __forceinline__ int straight_top(uint32_t m) {   // m bit r = rank (2->0 .. A->12); 0 = none, else top+1
     const uint32_t x = (m << 1) | ((m >> 12) & 1u);          // bit0 = ace playing low
     const uint32_t run = x & (x >> 1) & (x >> 2) & (x >> 3) & (x >> 4);
@@ -179,33 +185,38 @@ __device__ __forceinline__ uint32_t holdem_strength7(const int (&c)[7]) {
     for (int i = 0; i < 7; i++) holdem_add_card(s, c[i]);
     return holdem_strength_masks(s);
 }
-// strength of the seven cards given as four per-suit rank masks
+// strength of the seven cards given as four per-suit rank masks.  Branch free: the 32 lanes of a warp hold hands of
+// different categories, so every category is scored and the best valid one selected (category in bits 26.., then the
+// tie-break ranks in the order games/limitholdem/utils.py compares them).
 __device__ __forceinline__ uint32_t holdem_strength_masks(const uint32_t (&s)[4]) {
     const uint32_t any = s[0] | s[1] | s[2] | s[3];
     uint32_t fl = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (__popc(s[k]) >= 5) fl = s[k];
-    if (fl) { const int t = straight_top(fl); if (t) return (9u << 26) | (uint32_t)t; }
+    for (int k = 0; k < 4; k++) fl = __popc(s[k]) >= 5 ? s[k] : fl;
     const uint32_t x4 = s[0] & s[1] & s[2] & s[3];
     const uint32_t x3 = ((s[0] & s[1] & s[2]) | (s[0] & s[1] & s[3]) | (s[0] & s[2] & s[3]) | (s[1] & s[2] & s[3])) & ~x4;
     const uint32_t x2 = ((s[0] & s[1]) | (s[0] & s[2]) | (s[0] & s[3]) | (s[1] & s[2]) | (s[1] & s[3]) | (s[2] & s[3])) & ~x3 & ~x4;
-    if (x4) {
-        const uint32_t q = 31 - __clz(x4), k = 31 - __clz(any & ~(1u << q));
-        return (8u << 26) | (q << 4) | k;
-    }
-    if (x3 && ((x3 & (x3 - 1)) || x2)) {
-        const uint32_t t = 31 - __clz(x3), rest = (x3 & ~(1u << t)) | x2, p = 31 - __clz(rest);
-        return (7u << 26) | (t << 4) | p;
-    }
-    if (fl) return (6u << 26) | top_bits(fl, 5);
-    { const int t = straight_top(any); if (t) return (5u << 26) | (uint32_t)t; }
-    if (x3) { const uint32_t t = 31 - __clz(x3); return (4u << 26) | (t << 13) | top_bits(any & ~(1u << t), 2); }
-    if (x2 & (x2 - 1)) {
-        const uint32_t hi = 31 - __clz(x2), lo = 31 - __clz(x2 & ~(1u << hi));
-        return (3u << 26) | (hi << 17) | (lo << 13) | top_bits(any & ~(1u << hi) & ~(1u << lo), 1);
-    }
-    if (x2) { const uint32_t p = 31 - __clz(x2); return (2u << 26) | (p << 13) | top_bits(any & ~(1u << p), 3); }
-    return (1u << 26) | top_bits(any, 5);
+    const uint32_t sf = (uint32_t)straight_top(fl), st = (uint32_t)straight_top(any);
+    const uint32_t q = top_bit(x4), t3 = top_bit(x3), p2 = top_bit(x2), p2b = top_bit(x2 & ~(1u << p2));
+    const uint32_t rest3 = (x3 & ~(1u << t3)) | x2;                         // what can fill a full house
+    const uint32_t v9 = (9u << 26) | sf;
+    const uint32_t v8 = (8u << 26) | (q << 4) | top_bit(any & ~(1u << q));
+    const uint32_t v7 = (7u << 26) | (t3 << 4) | top_bit(rest3);
+    const uint32_t v6 = (6u << 26) | top_bits(fl, 5);
+    const uint32_t v5 = (5u << 26) | st;
+    const uint32_t v4 = (4u << 26) | (t3 << 13) | top_bits(any & ~(1u << t3), 2);
+    const uint32_t v3 = (3u << 26) | (p2 << 17) | (p2b << 13) | top_bits(any & ~(1u << p2) & ~(1u << p2b), 1);
+    const uint32_t v2 = (2u << 26) | (p2 << 13) | top_bits(any & ~(1u << p2), 3);
+    uint32_t v = (1u << 26) | top_bits(any, 5);
+    v = x2 ? v2 : v;
+    v = (x2 & (x2 - 1)) ? v3 : v;
+    v = x3 ? v4 : v;
+    v = st ? v5 : v;
+    v = fl ? v6 : v;
+    v = (x3 && rest3) ? v7 : v;
+    v = x4 ? v8 : v;
+    v = sf ? v9 : v;
+    return v;
 }
 
 // ========================================================================================
@@ -293,9 +304,10 @@ struct Limit {
     }
     // game.py:233-243, judger.py:11-108 for two players: winner takes min(chips) from the loser
     __device__ __forceinline__ void payoffs(float *out) const {
-        int w0, w1;
-        if (fold0 + fold1 == 1) { w0 = fold1; w1 = fold0; }
-        else {
+        // random Limit play mostly ends by a fold (a showdown needs eight actions without one), so the evaluator stays
+        // behind a branch that whole warps skip; inside, it is branch free
+        int w0 = fold1, w1 = fold0;
+        if (fold0 + fold1 != 1) {
             uint32_t bd[4] = {0, 0, 0, 0};                           // the five board cards are shared by both hands
 #pragma unroll
             for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
@@ -445,18 +457,15 @@ struct NoLimit {
     }
     // game.py:226-236 + limitholdem/judger.py for two players: the winner takes what the loser can match (chips, not blinds)
     __device__ __forceinline__ void payoffs(float *out) const {
-        int w0, w1;
-        if ((st0 == 1) != (st1 == 1)) { w0 = st1 == 1; w1 = st0 == 1; }
-        else {
-            uint32_t bd[4] = {0, 0, 0, 0};                           // the five board cards are shared by both hands
+        uint32_t bd[4] = {0, 0, 0, 0};                               // always scored, see Limit::payoffs
 #pragma unroll
-            for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
-            uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
-            holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
-            holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
-            const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
-            w0 = s0 >= s1; w1 = s1 >= s0;
-        }
+        for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
+        uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
+        holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
+        holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
+        const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
+        const bool folded = (st0 == 1) != (st1 == 1);
+        const int w0 = folded ? (st1 == 1) : (s0 >= s1), w1 = folded ? (st0 == 1) : (s1 >= s0);
         const int potm = min(in0, in1);
         float p0 = 0.f;
         if (w0 != w1) p0 = w0 ? (float)potm : -(float)potm;
