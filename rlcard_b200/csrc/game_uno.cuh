@@ -221,49 +221,65 @@ struct UnoT {
         if (!bits) bits = 1ull << 60;
         m[0] = (uint32_t)bits; m[1] = (uint32_t)(bits >> 32);
     }
-    // round.py:194-227 (two players)
-    template <class Ch> __device__ void non_number(int code, int color, Ch &ch, int &err) {
-        const int t = code % 15;
-        int current = cur;
-        if (t == 11) dir ^= 1;
-        else if (t == 10) current ^= 1;
-        else if (t == 12 || t == 14) {
-            const int need = t == 12 ? 2 : 4;
-            if (dl < need) replace_deck(ch);
-            deal(current ^ 1, need, ch, err);
-            current ^= 1;
-        }
-        cur = current ^ 1;
-        tcode = code; tcolor = color;
-    }
-    // env.py:65-86, envs/uno.py:39-45, game.py:58-81, round.py:54-94, 162-192
+    // env.py:65-86, envs/uno.py:39-45, game.py:58-81, round.py:54-94 (play), 162-192 (draw), 194-227 (effects).
+    // The lanes of a warp take different actions, so the transition is one mostly branch-free pass over flags; the only
+    // branches left are the ones that make Philox draws (pop a card, colour of an auto-played wild, penalty cards).
     template <class Ch> __device__ void step(int id, Ch &ch, int &err) {
         uint32_t m[2];
         legal(m);
         if (id < 0 || id > 60 || !((m[id >> 5] >> (id & 31)) & 1u)) {   // reference: random legal from the GLOBAL rng
             err |= 4; id = m[0] ? __ffs(m[0]) - 1 : 32 + __ffs(m[1]) - 1;
         }
-        if (id == 60) {                                                 // _perform_draw_action
+        const bool draw = id == 60;
+        int card = 0;
+        if (draw) {                                                     // _perform_draw_action: one card off the pile
             if (dl == 0) replace_deck(ch);
-            const int card = pop_deck(ch, err);
-            if (card < 0) { cur ^= 1; return; }
-            const int c = card / 15, t = card - 15 * c;
-            if (t >= 13) { tcolor = (int)ch.below(4u); tcode = card; push_played(card); cur ^= 1; }
-            else if (c == tcolor) {
-                push_played(card);
-                if (t < 10) { tcode = card; tcolor = c; cur ^= 1; }
-                else non_number(card, c, ch, err);
-            } else { to_hand(cur, card); cur ^= 1; }
-            return;
+            card = pop_deck(ch, err);
         }
-        const int color = id / 15, trait = id - 15 * color;
-        int code = id;
-        if (trait >= 13) code = 15 * take_first_wild(cur, trait) + trait;
-        else hc_add(cur, color, 0u - (1u << (2 * trait)));
-        if (hand_empty(cur)) winner = cur;
-        push_played(code);
-        if (trait < 10) { cur ^= 1; tcode = code; tcolor = color; }
-        else non_number(code, color, ch, err);
+        const bool dead = draw && card < 0;                             // Q-UNO4: nothing left to draw, the turn just passes
+        const int src = draw ? max(card, 0) : id;
+        const int c = src / 15, t = src - 15 * c;                       // play: chosen colour; draw: the card's own colour
+        const bool wild = t >= 13, play = !draw;
+        const bool match = draw && !dead && !wild && c == tcolor;       // drawn card is played at once
+        const bool auto_wild = draw && !dead && wild;                   // drawn wild is played with a random colour
+        const bool keep = draw && !dead && !wild && c != tcolor;        // drawn card joins the hand
+        // hand: played non-wild leaves it, kept card enters it, played wild = the first held one of that trait (Q-UNO2)
+        const uint32_t unit = 1u << (2 * min(t, 12));
+        hc_add(cur, c, (play && !wild) ? 0u - unit : (keep ? unit : 0u));
+        int code = src;
+        {
+            const int base = t == 13 ? 0 : 11;
+            const uint32_t w = hwp(cur), field = (w >> base) & 0x7ffu;
+            const int cnt = field & 7, first = (field >> 3) & 3;
+            const uint32_t rest = ((field >> 5) << 3) | (uint32_t)(cnt - 1);
+            const bool take = play && wild;
+            set_hw(cur, take ? (w & ~(0x7ffu << base)) | ((rest & 0x7ffu) << base) : w);
+            code = take ? 15 * first + t : code;
+        }
+        if (play && hand_empty(cur)) winner = cur;
+        int color = c;
+        if (auto_wild) color = (int)ch.below(4u);
+        const bool to_pile = play || match || auto_wild;
+        {                                                               // push_played, predicated
+            const int pc = code / 15, pt = code - 15 * pc;
+            if constexpr (BAG) {
+                const uint32_t inc = to_pile ? 1u << (2 * pt) : 0u;
+                pk[0] += pc == 0 ? inc : 0u; pk[1] += pc == 1 ? inc : 0u; pk[2] += pc == 2 ? inc : 0u; pk[3] += pc == 3 ? inc : 0u;
+                pl += to_pile ? 1 : 0;
+            } else if (to_pile) push_played(code);
+        }
+        tcode = to_pile ? code : tcode; tcolor = to_pile ? color : tcolor;
+        // effects of a non-number card that was played from the hand or matched on the draw (never of an auto-played wild)
+        const bool effect = (play || match) && t >= 10;
+        const bool penalty = effect && (t == 12 || t == 14);
+        if (penalty) {                                                  // draw_2 / wild_draw_4: the victim draws and is skipped
+            const int need = t == 12 ? 2 : 4;
+            if (dl < need) replace_deck(ch);
+            deal(cur ^ 1, need, ch, err);
+        }
+        dir ^= (effect && t == 11) ? 1 : 0;
+        const bool stay = effect && (t == 10 || penalty);               // two players: skip and penalties return the turn
+        cur ^= stay ? 0 : 1;
     }
     __device__ __forceinline__ void payoffs(float *out) const {          // game.py:108-118
         out[0] = winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f);
