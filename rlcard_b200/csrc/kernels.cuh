@@ -245,8 +245,11 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         }
         __syncwarp();
         if constexpr (kStageMask) {
-            if (ALL || p.t_mask)
-                warp_tile_flush(reinterpret_cast<uint8_t *>(p.t_mask) + (rowi - lane) * (size_t)G::A, mtile, nvalid * G::A, lane);
+            uint8_t *gm = reinterpret_cast<uint8_t *>(p.t_mask) + (rowi - lane) * (size_t)G::A;
+            if constexpr (ALL) {
+                if (full_warp) warp_tile_flush_full<G::A>(gm, mtile, lane);
+                else warp_tile_flush(gm, mtile, nvalid * G::A, lane);
+            } else if (p.t_mask) warp_tile_flush(gm, mtile, nvalid * G::A, lane);
         }
         if constexpr (ALL) {
             if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
@@ -308,7 +311,8 @@ cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
                         (G::A > 4 ? (size_t)(BLOCK / 32) * ((32 * G::A + 15) & ~15) : 0);
     // rollout fast path: every trajectory stream requested and obs rows of a full warp 16-byte aligned
     const bool all = op == kOpRollout && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
-                     ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * G::OBS * sizeof(ObsT))) & 15u) == 0;
+                     ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * G::OBS * sizeof(ObsT))) & 15u) == 0 &&
+                     (G::A <= 4 || ((reinterpret_cast<uintptr_t>(p.t_mask) | (p.n * (size_t)G::A)) & 15u) == 0);
     cudaError_t e = cudaSuccess;
 #define RLC_LAUNCH(KERNEL)                                                                           \
     do {                                                                                             \
