@@ -61,6 +61,7 @@ struct Leduc {
     static constexpr int kGameId = 1, P = 2, A = 4, OBS = 36, GAME_WORDS = 1, MASK_WORDS = 1;
     static constexpr bool kUsesChain = true;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 6;
+    static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 128;   // deal table: x in [0,120) -> hand0 | hand1 << 2 | public << 4
     int hand0, hand1, pub, pub_dealt, chips0, chips1, rc, fold0, fold1;
@@ -231,6 +232,7 @@ struct Limit {
     static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 52;
+    static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
@@ -348,6 +350,7 @@ struct NoLimit {
     static constexpr int kGameId = 6, P = 2, A = 5, OBS = 54, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;
     static constexpr int kMaxResetDraws = 53;
+    static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}

@@ -224,12 +224,16 @@ struct UnoT {
     // env.py:65-86, envs/uno.py:39-45, game.py:58-81, round.py:54-94 (play), 162-192 (draw), 194-227 (effects).
     // The lanes of a warp take different actions, so the transition is one mostly branch-free pass over flags; the only
     // branches left are the ones that make Philox draws (pop a card, colour of an auto-played wild, penalty cards).
+    static constexpr bool kHasApply = true;      // the fused rollout only takes legal ids: it calls apply() directly
     template <class Ch> __device__ void step(int id, Ch &ch, int &err) {
         uint32_t m[2];
         legal(m);
         if (id < 0 || id > 60 || !((m[id >> 5] >> (id & 31)) & 1u)) {   // reference: random legal from the GLOBAL rng
             err |= 4; id = m[0] ? __ffs(m[0]) - 1 : 32 + __ffs(m[1]) - 1;
         }
+        apply(id, ch, err);
+    }
+    template <class Ch> __device__ void apply(int id, Ch &ch, int &err) {
         const bool draw = id == 60;
         int card = 0;
         if (draw) {                                                     // _perform_draw_action: one card off the pile

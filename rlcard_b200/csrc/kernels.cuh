@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             const int a = pick_action<G>(m, word, cnt);
             if constexpr (G::kUsesChain) ch.seed_chain(word, (uint32_t)cnt);
             if (ALL || p.t_action) __stcs(p.t_action + rowi, a);
-            g.step(a, ch, err);
+            if constexpr (G::kHasApply) g.apply(a, ch, err);          // a was picked from the legal set: no re-validation
+            else g.step(a, ch, err);
             h.t++; h.k++;
             const bool over = g.over();
             float pay[G::P];
