@@ -211,11 +211,12 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
     }
 }
 
-// Full-warp fast path: 32 rows of ROW_BYTES (compile time), destination 16-byte aligned -> the trip
+// Full-tile fast path: TILE_BYTES (compile time, a multiple of 16) to a 16-byte aligned destination -> the trip
 // count and every guard are compile-time, 128-bit LDS / STG.cs / STS per chunk.
-template <int ROW_BYTES>
+template <int TILE_BYTES>
 __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *tile, int lane) {
-    constexpr int kChunks = 2 * ROW_BYTES;                    // 32 * ROW_BYTES / 16
+    static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 128-bit chunks");
+    constexpr int kChunks = TILE_BYTES / 16;
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *t4 = reinterpret_cast<uint4 *>(tile), *g4 = reinterpret_cast<uint4 *>(gdst);
 #pragma unroll

@@ -61,6 +61,7 @@ struct Leduc {
     static constexpr int kGameId = 1, P = 2, A = 4, OBS = 36, GAME_WORDS = 1, MASK_WORDS = 1;
     static constexpr bool kUsesChain = true;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 6;
+    static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 128;   // deal table: x in [0,120) -> hand0 | hand1 << 2 | public << 4
@@ -232,6 +233,7 @@ struct Limit {
     static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr int kMaxResetDraws = 52;
+    static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
@@ -350,6 +352,7 @@ struct NoLimit {
     static constexpr int kGameId = 6, P = 2, A = 5, OBS = 54, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;
     static constexpr int kMaxResetDraws = 53;
+    static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;

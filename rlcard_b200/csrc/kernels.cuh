@@ -4,6 +4,7 @@
 // State is SoA uint32 [words][n] (coalesced word loads); obs rows are staged per warp in shared
 // memory and streamed out with 128-bit stores (common.cuh warp_tile_flush).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/rlcard_b200.h"
 
@@ -192,32 +193,37 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
 // warp emits one coalesced obs tile plus mask/action/player/done/payoff rows of the trajectory.
 // ALL = every trajectory pointer is present and the obs rows of a full warp are 16-byte aligned (the
 // bench / DMC case): no per-step null checks, compile-time tile flush.
-template <class G, class Ch, class ObsT, int BLOCK, bool ALL>
+// EPW = envs per warp (32, 16 or 8).  The thread-per-env engines are bound by the latency of one env-step's
+// dependent instruction chain, so a batch that yields fewer warps than the GPU has scheduler slots (16 384 envs
+// = 512 warps for 592 schedulers) runs faster spread over more warps: lanes >= EPW carry no env and only help
+// to flush the tiles; fewer envs per warp also means fewer warp-steps pay for a diverged reset.
+template <class G, class Ch, class ObsT, int BLOCK, bool ALL, int EPW>
 __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
-    constexpr int kTileBytes = BLOCK * kRowBytes;
+    constexpr int kWarps = BLOCK / 32;
+    constexpr int kTileBytes = kWarps * EPW * kRowBytes;
     if constexpr (G::kSharedBytes > 0) {                      // per-block constant tables of the game
         G::fill_shared(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes, threadIdx.x, BLOCK);
         __syncthreads();
     }
-    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
+    const size_t warp_env0 = ((size_t)blockIdx.x * kWarps + wib) * EPW;
     if (warp_env0 >= p.n) return;
     const size_t i = warp_env0 + lane;
-    const bool valid = i < p.n;
-    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
-    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * G::OBS;
-    ObsT *row = tile + lane * G::OBS;
-    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    const bool valid = lane < EPW && i < p.n;
+    const int nvalid = (int)min((size_t)EPW, p.n - warp_env0);
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * EPW * G::OBS;
+    ObsT *row = tile + (lane & (EPW - 1)) * G::OBS;
+    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), EPW * kRowBytes, lane);
     __syncwarp();
 
     G g; EnvHeader h; Ch ch; int err = 0;
     g.bind_shared(reinterpret_cast<const uint8_t *>(smem_raw) + kTileBytes);
-    // dense mask rows wider than one word (UNO: 61 bytes) are staged per warp too: 32 rows are contiguous
+    // dense mask rows wider than one word (UNO: 61 bytes) are staged per warp too: the rows of a warp are contiguous
     // in global memory, byte stores from the lanes would touch 32 different sectors each
     constexpr bool kStageMask = G::A > 4;
-    constexpr int kMaskTile = kStageMask ? ((32 * G::A + 15) & ~15) : 0;
+    constexpr int kMaskTile = kStageMask ? ((EPW * G::A + 15) & ~15) : 0;
     uint8_t *mtile = reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes + ((G::kSharedBytes + 15) & ~15) + wib * kMaskTile;
     if (valid) {
         h.load(p.state, p.n, i);
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     // per-thread output cursors, advanced by one trajectory row (n envs) per step
     uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
     const size_t obs_step = p.n * (size_t)kRowBytes;
-    const bool full_warp = nvalid == 32;                      // ALL: aligned rows were checked by the launcher
+    const bool full_warp = nvalid == EPW;                     // ALL: aligned rows were checked by the launcher
     size_t rowi = i;
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         uint32_t m[G::MASK_WORDS];
@@ -247,12 +253,12 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         if constexpr (kStageMask) {
             uint8_t *gm = reinterpret_cast<uint8_t *>(p.t_mask) + (rowi - lane) * (size_t)G::A;
             if constexpr (ALL) {
-                if (full_warp) warp_tile_flush_full<G::A>(gm, mtile, lane);
+                if (full_warp) warp_tile_flush_full<EPW * G::A>(gm, mtile, lane);
                 else warp_tile_flush(gm, mtile, nvalid * G::A, lane);
             } else if (p.t_mask) warp_tile_flush(gm, mtile, nvalid * G::A, lane);
         }
         if constexpr (ALL) {
-            if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+            if (full_warp) warp_tile_flush_full<EPW * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
             else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         } else {
             if (p.t_obs) warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
@@ -304,16 +310,67 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
 // ---- host-side launcher shared by the per-game translation units ----------------------------
 enum { kOpReset = 0, kOpStep = 1, kOpObserve = 2, kOpRollout = 3 };
 
+// envs per warp of the fused rollout: 32 unless the batch leaves warp schedulers short of kRolloutWarpsPerScheduler
+// warps AND the game gains from fewer envs per warp (G::kRolloutMinEpw; measured on a B200 at 16 384 envs, ms per
+// 128-step launch at 32 / 16 / 8: UNO 0.658 / 0.585 / 0.730, Limit 0.106 / 0.134 / 0.200, no-limit 0.197 / 0.281 / 0.483,
+// Blackjack (65 536 envs) 0.614 / 0.900 / 1.460 -- only UNO, whose warps diverge on resets, wins).  RLC_ROLLOUT_EPW forces
+// a value (tests, tuning).  Only the Philox throughput mode is specialised, replays always run 32 envs per warp.
+constexpr int kRolloutWarpsPerScheduler = 2;
+inline int rollout_envs_per_warp(size_t n, int min_epw) {
+    static int schedulers = 0;
+    if (schedulers == 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        schedulers = 4 * sms;
+    }
+    const char *e = getenv("RLC_ROLLOUT_EPW");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 32 || forced == 16 || forced == 8) return forced;
+    for (int epw = 32; epw > min_epw; epw >>= 1)
+        if (n / (size_t)epw >= (size_t)kRolloutWarpsPerScheduler * schedulers) return epw;
+    return min_epw;
+}
+
+template <class G, class Ch, class ObsT, int EPW>
+cudaError_t launch_rollout(const KParams &p, cudaStream_t stream) {
+    constexpr int BLOCK = 64, kWarps = BLOCK / 32;
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    const unsigned grid = (unsigned)((p.n + kWarps * EPW - 1) / (kWarps * EPW));
+    const size_t smem = (size_t)kWarps * EPW * kRowBytes + ((G::kSharedBytes + 15) & ~15) +
+                        (G::A > 4 ? (size_t)kWarps * ((EPW * G::A + 15) & ~15) : 0);
+    // fast path: every trajectory stream requested and the obs (and staged mask) rows of a full warp 16-byte aligned
+    constexpr bool kTilesAligned = (EPW * kRowBytes) % 16 == 0 && (G::A <= 4 || (EPW * G::A) % 16 == 0);
+    const bool all = kTilesAligned && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
+                     ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * (size_t)kRowBytes)) & 15u) == 0 &&
+                     (G::A <= 4 || ((reinterpret_cast<uintptr_t>(p.t_mask) | (p.n * (size_t)G::A)) & 15u) == 0);
+    cudaError_t e = cudaSuccess;
+    if constexpr (kTilesAligned) {
+        if (all) {
+            auto k = k_rollout<G, Ch, ObsT, BLOCK, true, EPW>;
+            if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) { k<<<grid, BLOCK, smem, stream>>>(p); e = cudaGetLastError(); }
+            return e;
+        }
+    }
+    auto k = k_rollout<G, Ch, ObsT, BLOCK, false, EPW>;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { k<<<grid, BLOCK, smem, stream>>>(p); e = cudaGetLastError(); }
+    return e;
+}
+
 template <class G, class Ch, class ObsT>
 cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
     constexpr int BLOCK = 64;
+    if (op == kOpRollout) {
+        if constexpr (Ch::kKind == 0) {
+            const int epw = rollout_envs_per_warp(p.n, G::kRolloutMinEpw);
+            if (epw == 16) return launch_rollout<G, Ch, ObsT, 16>(p, stream);
+            if (epw == 8) return launch_rollout<G, Ch, ObsT, 8>(p, stream);
+        }
+        return launch_rollout<G, Ch, ObsT, 32>(p, stream);
+    }
     const unsigned grid = (unsigned)((p.n + BLOCK - 1) / BLOCK);
-    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT) + ((G::kSharedBytes + 15) & ~15) +
-                        (G::A > 4 ? (size_t)(BLOCK / 32) * ((32 * G::A + 15) & ~15) : 0);
-    // rollout fast path: every trajectory stream requested and obs rows of a full warp 16-byte aligned
-    const bool all = op == kOpRollout && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
-                     ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * G::OBS * sizeof(ObsT))) & 15u) == 0 &&
-                     (G::A <= 4 || ((reinterpret_cast<uintptr_t>(p.t_mask) | (p.n * (size_t)G::A)) & 15u) == 0);
+    const size_t smem = (size_t)BLOCK * G::OBS * sizeof(ObsT) + ((G::kSharedBytes + 15) & ~15);
     cudaError_t e = cudaSuccess;
 #define RLC_LAUNCH(KERNEL)                                                                           \
     do {                                                                                             \
@@ -324,10 +381,6 @@ cudaError_t launch_op(int op, const KParams &p, cudaStream_t stream) {
     case kOpReset: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeReset, BLOCK>)); break;
     case kOpStep: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeStep, BLOCK>)); break;
     case kOpObserve: RLC_LAUNCH((k_env<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
-    case kOpRollout:
-        if (all) RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK, true>));
-        else RLC_LAUNCH((k_rollout<G, Ch, ObsT, BLOCK, false>));
-        break;
     default: e = cudaErrorInvalidValue;
     }
 #undef RLC_LAUNCH

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
             row[21 + (seat ? c0 : c1)] = (ObsT)1;
         }
         __syncwarp();
-        if (full_warp) warp_tile_flush_full<kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+        if (full_warp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
         else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         __syncwarp();
         if (valid) {

@@ -280,6 +280,30 @@ def test_partial_streams_and_unaligned_batches(game):
     odd.check_errors()
 
 
+THREAD_GAMES = [g for g in GAMES if g not in ('doudizhu', 'scout')]
+
+
+@pytest.mark.parametrize('epw', [32, 16, 8])
+@pytest.mark.parametrize('game', THREAD_GAMES)
+def test_rollout_envs_per_warp_variants_equal_oracle(game, epw, monkeypatch):
+    """The fused rollout of the thread-per-env games runs 32, 16 or 8 envs per warp depending on the batch size
+    (kernels.cuh rollout_envs_per_warp; RLC_ROLLOUT_EPW forces one).  Every variant must give the oracle's trajectory,
+    on a ragged batch (last warp partly filled) and on an aligned one (compile-time tile flush)."""
+    monkeypatch.setenv('RLC_ROLLOUT_EPW', str(epw))
+    T, seed = 30, 424242
+    for n in (203, 512):
+        env = rlcard_b200.VecEnv(game, n, seed=seed)
+        env.reset()
+        tr = env.rollout_random(T)
+        ref = oracle.OracleVec(game, n, seed).rollout(T, nthreads=4)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            got, want = to_np(tr[k]), ref[k]
+            if k == 'obs':
+                got = got[..., :want.shape[-1]]
+            assert np.array_equal(got.astype(np.float64), want.astype(np.float64)), (game, epw, n, k)
+        env.check_errors()
+
+
 def test_reset_mask_and_tape_errors():
     """rlc_reset with a partial mask only deals the selected envs; an exhausted replay tape raises the error flag."""
     env = rlcard_b200.VecEnv('leduc-holdem', 64, seed=1, auto_reset=False)
