@@ -7,16 +7,22 @@ namespace rlc {
 // ==========================================================================================
 // Table-driven Leduc rollout.  Everything about a Leduc state except the three cards is one of < 256
 // "betting states" (round, pointer, raise counters, chips, folds); the transition function over them is
-// tabulated ONCE per device by running the register-level engine (Leduc::step, game_poker.cuh) over every
-// reachable state, so table == engine by construction.  The rollout then costs two shared-memory
-// lookups per env-step instead of the branchy engine.
-//   entry.x = the packed state word (game_poker.cuh layout) with the card bits [0:7) replaced by
-//             legal mask [0:4) | is_over [4]
-//   entry.y = next state id for actions call, raise, fold, check (one byte each)
+// tabulated ONCE per device by running the register-level engine (Leduc::step / legal / payoffs / encode_obs,
+// game_poker.cuh) over every reachable state, so table == engine by construction.  The rollout then costs two
+// 128-bit shared-memory lookups per env-step instead of the branchy engine.  One entry (uint4) per state:
+//   .x  the packed state word (game_poker.cuh layout) with the card bits [0:7) replaced by legal mask [0:4) | is_over [4]
+//   .y  running state: id of the next state after the k-th legal action (k = 0..3 in ascending id order, a byte each)
+//       terminal state: seat 0's payoff in quarter chips (int8) when the cards say seat 0 wins / seat 1 wins / tie
+//       (seat 1 gets the negative: Leduc is zero-sum, checked while tabulating; a fold decides all three alike)
+//   .z  the id of the k-th legal action (a byte each)
+//   .w  where the obs row of the acting seat has its ones (envs/leducholdem.py:41-71): byte 0 = 6 + own chips,
+//       byte 1 = 21 + opponent's chips, byte 2 = bit offset of the own card in `cards`, byte 3 = public card dealt
 // State ids 0 / 1 are the first states of an episode with seat 0 / 1 as small blind.
+// The cards live in one register: hand0 | hand1 << 2 | public << 4 | showdown outcome << 6 (0 seat 0 wins, 1 seat 1
+// wins, 2 tie -- judger.py:12-64 evaluated by Leduc::payoffs when the deal table is filled).
 // ==========================================================================================
 constexpr int kFsmMax = 256;
-static uint2 *g_fsm[64];
+static uint4 *g_fsm[64];
 static std::mutex g_fsm_mu;
 
 __device__ __forceinline__ uint32_t fsm_key(const Leduc &g) {
@@ -29,8 +35,17 @@ __device__ __forceinline__ void fsm_unkey(Leduc &g, uint32_t w) {
     g.r.have_raised = bf_get(w, 23, 2); g.r.not_raise_num = bf_get(w, 25, 2); g.r.pointer = bf_get(w, 27, 1);
     g.rc = bf_get(w, 28, 2); g.fold0 = bf_get(w, 30, 1); g.fold1 = bf_get(w, 31, 1);
 }
+// showdown outcome of a deal (hand0 | hand1 << 2 | public << 4), by the engine's judger on an even pot
+__device__ __forceinline__ uint32_t leduc_showdown_code(uint32_t cards) {
+    Leduc g; fsm_unkey(g, 0);
+    g.hand0 = cards & 3u; g.hand1 = (cards >> 2) & 3u; g.pub = (cards >> 4) & 3u; g.pub_dealt = 1; g.rc = 2;
+    g.chips0 = g.chips1 = 1;
+    float out[2];
+    g.payoffs(out);
+    return out[0] > 0.f ? 0u : (out[0] < 0.f ? 1u : 2u);
+}
 // single thread: breadth-first closure of the two initial states under Leduc::step
-__global__ void k_leduc_build_fsm(uint2 *tab, int *count) {
+__global__ void k_leduc_build_fsm(uint4 *tab, int *count) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     __shared__ uint32_t keys[kFsmMax];
     int n = 0;
@@ -44,8 +59,9 @@ __global__ void k_leduc_build_fsm(uint2 *tab, int *count) {
     for (int i = 0; i < n; i++) {
         Leduc g; fsm_unkey(g, keys[i]);
         uint32_t m[1]; g.legal(m);
-        uint32_t x = keys[i] | (m[0] & 15u) | (g.over() ? 16u : 0u), y = 0;
+        uint32_t x = keys[i] | (m[0] & 15u) | (g.over() ? 16u : 0u), y = 0, z = 0, w = 0;
         if (!g.over()) {
+            int kth = 0;
             for (int a = 0; a < 4; a++) {
                 if (!((m[0] >> a) & 1u)) continue;
                 Leduc h; fsm_unkey(h, keys[i]);
@@ -55,24 +71,46 @@ __global__ void k_leduc_build_fsm(uint2 *tab, int *count) {
                 int j = 0;
                 while (j < n && keys[j] != k2) j++;
                 if (j == n) { if (n >= kFsmMax) { *count = -1; return; } keys[n++] = k2; }
-                y |= (uint32_t)j << (8 * a);
+                y |= (uint32_t)j << (8 * kth);
+                z |= (uint32_t)a << (8 * kth);
+                kth++;
+            }
+            // where encode_obs puts the ones of the acting seat's row: probe it with distinct cards (own 1, other 2, public 0)
+            const int seat = g.player();
+            g.hand0 = seat ? 2 : 1; g.hand1 = seat ? 1 : 2; g.pub = 0; g.pub_dealt = g.rc != 0;
+            uint8_t row[Leduc::OBS];
+            for (int k = 0; k < Leduc::OBS; k++) row[k] = 0;
+            g.encode_obs(seat, false, row);
+            int mine = -1, other = -1;
+            for (int k = 6; k < 21; k++) if (row[k]) mine = k;
+            for (int k = 21; k < 36; k++) if (row[k]) other = k;
+            if (mine < 0 || other < 0 || !row[1] || (row[3] != 0) != (g.rc != 0)) { *count = -2; return; }
+            w = (uint32_t)mine | ((uint32_t)other << 8) | ((uint32_t)(2 * seat) << 16) | ((g.rc != 0 ? 1u : 0u) << 24);
+        } else {
+            for (int code = 0; code < 3; code++) {           // cards that make the judger say: seat 0 / seat 1 / tie
+                g.hand0 = code == 0 ? 1 : 0; g.hand1 = code == 1 ? 1 : 0; g.pub = 1; g.pub_dealt = 1;
+                float out[2];
+                g.payoffs(out);
+                const int q0 = (int)(out[0] * 4.f), q1 = (int)(out[1] * 4.f);
+                if (q0 != -q1 || (float)q0 * 0.25f != out[0]) { *count = -3; return; }
+                y |= ((uint32_t)q0 & 255u) << (8 * code);
             }
         }
-        tab[i] = make_uint2(x, y);
+        tab[i] = make_uint4(x, y, z, w);
     }
     *count = n;
 }
-static cudaError_t leduc_fsm(const uint2 **out) {
+static cudaError_t leduc_fsm(const uint4 **out) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev >= 64) return cudaErrorInvalidValue;
     std::lock_guard<std::mutex> lock(g_fsm_mu);
     if (!g_fsm[dev]) {
-        uint2 *tab = nullptr; int *cnt = nullptr, h = 0;
-        if ((e = cudaMalloc(&tab, sizeof(uint2) * kFsmMax)) != cudaSuccess) return e;
+        uint4 *tab = nullptr; int *cnt = nullptr, h = 0;
+        if ((e = cudaMalloc(&tab, sizeof(uint4) * kFsmMax)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&cnt, sizeof(int))) != cudaSuccess) return e;
-        cudaMemset(tab, 0, sizeof(uint2) * kFsmMax);
+        cudaMemset(tab, 0, sizeof(uint4) * kFsmMax);
         k_leduc_build_fsm<<<1, 32>>>(tab, cnt);
         e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
         cudaFree(cnt);
@@ -84,17 +122,28 @@ static cudaError_t leduc_fsm(const uint2 **out) {
     return cudaSuccess;
 }
 
+// byte k (k < 4) of w, zero extended / sign extended: one PRMT each
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, uint32_t k) { return __byte_perm(w, 0u, 0x4440u | k); }
+__device__ __forceinline__ int sbyte_of(uint32_t w, uint32_t k) {            // prmt's sign-replicate selectors (the
+    uint32_t r;                                                              // __byte_perm intrinsic masks them off)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"(0x8880u | (k * 0x1111u)));
+    return (int)r;
+}
+
 // The Env.run loop with random agents (env.py:120-169) over the tabulated engine: same trajectory, state
-// words and Philox draws as k_rollout<Leduc, ChancePhilox, ObsT, 64, true>.
+// words and Philox draws as k_rollout<Leduc, ChancePhilox, ObsT, 64, true, 32>.
 template <class ObsT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, const uint2 *__restrict__ gtab) {
+__global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, const uint4 *__restrict__ gtab) {
     extern __shared__ uint4 smem_raw[];
     constexpr int kRowBytes = Leduc::OBS * (int)sizeof(ObsT);
     constexpr int kTileBytes = BLOCK * kRowBytes;
-    uint2 *stab = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
+    uint4 *stab = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
     uint8_t *lut = reinterpret_cast<uint8_t *>(stab + kFsmMax);
     for (int j = threadIdx.x; j < kFsmMax; j += BLOCK) stab[j] = gtab[j];
-    Leduc::fill_shared(lut, threadIdx.x, BLOCK);
+    for (int x = threadIdx.x; x < 120; x += BLOCK) {         // deal table with the showdown outcome on top
+        const uint32_t c = Leduc::deal_code((uint32_t)x);
+        lut[x] = (uint8_t)(c | (leduc_showdown_code(c) << 6));
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
@@ -108,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
     __syncwarp();
 
     EnvHeader h; ChancePhilox ch;
-    uint32_t cards = 0, sid = 0;           // hand0 | hand1 << 2 | public << 4 ; betting-state id
+    uint32_t cards = 0, sid = 0;           // hand0 | hand1 << 2 | public << 4 | showdown outcome << 6 ; betting-state id
     if (valid) {
         h.load(p.state, p.n, i);
         ch.init(p.seed, p.env_id_base + (uint32_t)i);
@@ -120,60 +169,44 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
         } else {
             const uint32_t w = p.state[kHeaderWords * p.n + i];
             cards = w & 63u;
+            cards |= leduc_showdown_code(cards) << 6;
             const uint32_t key = w & ~127u;
             for (int j = 0; j < kFsmMax; j++) if ((stab[j].x & ~127u) == key) { sid = (uint32_t)j; break; }
         }
     }
-    uint2 e = stab[sid];
+    uint4 e = stab[sid];
     uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
     const size_t obs_step = p.n * (size_t)kRowBytes;
     const bool full_warp = nvalid == 32;
     size_t rowi = i;
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
-        const uint32_t legal = e.x & 15u, seat = (e.x >> 27) & 1u, rc = (e.x >> 28) & 3u;
-        const uint32_t c0 = (e.x >> 7) & 15u, c1 = (e.x >> 11) & 15u;
-        if (valid) {                       // envs/leducholdem.py:41-71
-            row[(cards >> (2 * seat)) & 3u] = (ObsT)1;
-            if (rc) row[3 + ((cards >> 4) & 3u)] = (ObsT)1;
-            row[6 + (seat ? c1 : c0)] = (ObsT)1;
-            row[21 + (seat ? c0 : c1)] = (ObsT)1;
+        const uint32_t legal = e.x & 15u;
+        if (valid) {                       // envs/leducholdem.py:41-71, positions tabulated from Leduc::encode_obs
+            row[(cards >> byte_of(e.w, 2)) & 3u] = (ObsT)1;
+            if (e.w >> 24) row[3 + ((cards >> 4) & 3u)] = (ObsT)1;
+            row[byte_of(e.w, 0)] = (ObsT)1;
+            row[byte_of(e.w, 1)] = (ObsT)1;
         }
         __syncwarp();
         if (full_warp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
         else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         __syncwarp();
         if (valid) {
-            __stcs(reinterpret_cast<uint32_t *>(p.t_mask) + rowi,
-                   (legal & 1u) | ((legal & 2u) << 7) | ((legal & 4u) << 14) | ((legal & 8u) << 21));
-            __stcs(p.t_player + rowi, (int)seat);
+            __stcs(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
+            __stcs(p.t_player + rowi, (int)((e.x >> 27) & 1u));
             const uint32_t word = ch.begin_step(h.k);
             const uint32_t cnt = (uint32_t)__popc(legal);
-            const int kth = (int)__umulhi(word, cnt);
+            const uint32_t kth = __umulhi(word, cnt);        // uniform over the legal ids, ascending
             ch.seed_chain(word, cnt);
-            uint32_t mm = legal;
-            if (kth > 0) mm &= mm - 1;
-            if (kth > 1) mm &= mm - 1;
-            if (kth > 2) mm &= mm - 1;
-            const int a = __ffs(mm) - 1;
-            __stcs(p.t_action + rowi, a);
-            sid = (e.y >> (8 * a)) & 255u;
+            __stcs(p.t_action + rowi, (int)byte_of(e.z, kth));
+            sid = byte_of(e.y, kth);
             e = stab[sid];
             h.t++; h.k++;
             const bool over = (e.x >> 4) & 1u;
             float2 pay = make_float2(0.f, 0.f);
-            if (over) {                    // judger.py:12-64 in quarter-chip integers (see Leduc::payoffs)
-                const int f0 = (e.x >> 30) & 1u, f1 = e.x >> 31, ch0 = (e.x >> 7) & 15u, ch1 = (e.x >> 11) & 15u;
-                const int h0 = cards & 3u, h1 = (cards >> 2) & 3u, pb = (cards >> 4) & 3u;
-                const bool dealt = ((e.x >> 28) & 3u) != 0u;
-                int w0, w1;
-                if (f0 + f1 == 1) { w0 = f1; w1 = f0; }
-                else if (dealt && h0 == pb) { w0 = 1; w1 = 0; }
-                else if (dealt && h1 == pb) { w0 = 0; w1 = 1; }
-                else { w0 = h0 >= h1; w1 = h1 >= h0; }
-                const int tie = w0 & w1;
-                const int q0 = tie ? ch1 - ch0 : (w0 ? 2 * ch1 : -2 * ch0);
-                const int q1 = tie ? ch0 - ch1 : (w1 ? 2 * ch0 : -2 * ch1);
-                pay = make_float2((float)q0 * 0.25f, (float)q1 * 0.25f);
+            if (over) {                    // judger.py:12-64 through the tabulated quarter-chip payoffs
+                const float q0 = (float)sbyte_of(e.y, cards >> 6) * 0.25f;
+                pay = make_float2(q0, -q0);
                 cards = lut[ch.chain(120u)];                 // game.py:46-95: the next episode, same step's draws
                 sid = ch.chain(2u);
                 e = stab[sid];
@@ -186,17 +219,17 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
     if (valid) {
         h.store(p.state, p.n, i);
         const uint32_t rc = (e.x >> 28) & 3u;
-        p.state[kHeaderWords * p.n + i] = (e.x & ~127u) | cards | (rc ? 64u : 0u);
+        p.state[kHeaderWords * p.n + i] = (e.x & ~127u) | (cards & 63u) | (rc ? 64u : 0u);
     }
 }
 
 template <class ObsT>
 static cudaError_t launch_leduc_fsm(const KParams &p, cudaStream_t s) {
-    const uint2 *tab = nullptr;
+    const uint4 *tab = nullptr;
     cudaError_t e = leduc_fsm(&tab);
     if (e != cudaSuccess) return e;
     constexpr int BLOCK = 64;
-    const size_t smem = (size_t)BLOCK * Leduc::OBS * sizeof(ObsT) + sizeof(uint2) * kFsmMax + 128;
+    const size_t smem = (size_t)BLOCK * Leduc::OBS * sizeof(ObsT) + sizeof(uint4) * kFsmMax + 128;
     k_rollout_leduc_fsm<ObsT, BLOCK><<<(unsigned)((p.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(p, tab);
     return cudaGetLastError();
 }
