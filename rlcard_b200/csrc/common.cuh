@@ -212,20 +212,32 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
 }
 
 // Full-tile fast path: TILE_BYTES (compile time, a multiple of 16) to a 16-byte aligned destination -> the trip
-// count and every guard are compile-time, 128-bit LDS / STG.cs / STS per chunk.
+// count and every guard are compile-time.  Chunks move in batches of up to four per lane: all 128-bit LDS of a batch
+// first, then the zeroing STS, then the STG.cs -- distinct registers per chunk, so no load waits for a store to
+// release its source registers and the shared-memory latency is paid once per batch.
 template <int TILE_BYTES>
 __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *tile, int lane) {
     static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 128-bit chunks");
-    constexpr int kChunks = TILE_BYTES / 16;
+    constexpr int kChunks = TILE_BYTES / 16, kBatch = 4;
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *t4 = reinterpret_cast<uint4 *>(tile), *g4 = reinterpret_cast<uint4 *>(gdst);
 #pragma unroll
-    for (int c0 = 0; c0 < kChunks; c0 += kWarp) {
-        const int c = c0 + lane;
-        if (c0 + kWarp <= kChunks || c < kChunks) {
-            const uint4 v = t4[c];
-            __stcs(g4 + c, v);
-            t4[c] = z;
+    for (int b0 = 0; b0 < kChunks; b0 += kBatch * kWarp) {
+        uint4 v[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; q++) {
+            const int c0 = b0 + q * kWarp, c = c0 + lane;
+            if (c0 < kChunks && (c0 + kWarp <= kChunks || c < kChunks)) v[q] = t4[c];
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; q++) {
+            const int c0 = b0 + q * kWarp, c = c0 + lane;
+            if (c0 < kChunks && (c0 + kWarp <= kChunks || c < kChunks)) t4[c] = z;
+        }
+#pragma unroll
+        for (int q = 0; q < kBatch; q++) {
+            const int c0 = b0 + q * kWarp, c = c0 + lane;
+            if (c0 < kChunks && (c0 + kWarp <= kChunks || c < kChunks)) __stcs(g4 + c, v[q]);
         }
     }
 }

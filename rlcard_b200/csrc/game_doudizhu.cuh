@@ -25,8 +25,8 @@ namespace rlc {
 
 struct DdzTables {
     const uint64_t *rows;      // [27472] nibble-packed rank counts ('pass' = 0)
-    const uint64_t *need;      // [864]   nibble-wise min over the 32 rows of each mask word; [864 + b] = min over
-                               //         batch b of 32 mask words (1024 ids), b < 27
+    const ulonglong2 *need;    // [864 + 32] per mask word j: .x = nibble-wise min over its 32 rows, .y = bit t set when an id of
+                               //         the word has type t; entry 864 + b describes batch b of 32 mask words (1024 ids), b < 27
     const uint8_t *type;       // [27472]
     const uint8_t *weight;     // [27472]
     const uint32_t *tw_start;  // [39][17] first id of type t with weight >= w; [t][16] = end of type t
@@ -35,6 +35,25 @@ constexpr int kDdzPass = 27471, kDdzRocket = 27470, kDdzBomb0 = 27457, kDdzTypeB
 constexpr uint64_t kNibHi = 0x8888888888888888ull;
 
 __device__ __forceinline__ bool ddz_contains(uint64_t hand, uint64_t row) { return (((hand | kNibHi) - row) & kNibHi) == kNibHi; }
+// Type prefilter.  Whatever its kickers, every action of a type contains `len` consecutive ranks (within 3..A when
+// len > 1) of at least `mult` cards each (doudizhu_table.py type_requirements, checked against all 27 472 rows by the
+// CPU tests); the rocket is both jokers.  A hand that lacks that core holds no action of the type, so whole id ranges
+// are skipped before any table row is fetched -- on a lead this leaves a handful of the ~48 mask words whose
+// nibble-wise minimum alone cannot rule them out (four_two_* / trio_* words mix many ranks, their minimum is zero).
+// Type ids: 0 solo 1 pair 2 trio 3 trio_solo 4 trio_pair | 5..12 solo_chain_5..12 | 13..20 pair_chain_3..10 |
+// 21..25 trio_chain_2..6 | 26..29 trio_solo_chain_2..5 | 30..32 trio_pair_chain_2..4 | 33 four_two_solo
+// 34 four_two_pair 35 bomb | 36 rocket | 37 pass.
+__device__ __forceinline__ bool ddz_type_ok(uint64_t hand, int t) {
+    if (t >= 36) return t == 36 && ((hand >> 52) & 15u) != 0u && ((hand >> 56) & 15u) != 0u;
+    const int mult = t < 5 ? min(t + 1, 3) : (t < 13 ? 1 : (t < 21 ? 2 : (t < 33 ? 3 : 4)));
+    const int len = t < 5 ? 1 : (t < 13 ? t : (t < 21 ? t - 10 : (t < 26 ? t - 19 : (t < 30 ? t - 24 : (t < 33 ? t - 28 : 1)))));
+    uint64_t g = ((hand | kNibHi) - (uint64_t)mult * 0x1111111111111111ull) & kNibHi;     // bit 3 of nibble r: count_r >= mult
+    if (len > 1) {
+        g &= 0x0000888888888888ull;                                                        // chains live on ranks 3..A
+        for (int i = 1; i < len; i++) g &= g >> 4;
+    }
+    return g != 0;
+}
 __device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of cards = sum of nibbles
     c = (c & 0x0f0f0f0f0f0f0f0full) + ((c >> 4) & 0x0f0f0f0f0f0f0f0full);
     return (int)((c * 0x0101010101010101ull) >> 56);
@@ -44,7 +63,8 @@ struct Doudizhu {
     static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 859;
     static constexpr bool kMaskBitpacked = true;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for
-    static constexpr int kScratchBytes = 64 + 4 * 864;   // reset: 54-card deck | legal(): list of non-empty mask words
+    static constexpr int kScratchBytes = 64 + 4 * 864 + 128;   // reset: 54-card deck | legal(): list of non-empty mask words | encode_obs: 16 count words
+    static constexpr int kObsScratch = 64 + 4 * 864;
     int n_legal, n_live; bool has_pass;                  // summary of the last legal() (warp-uniform)
     DdzTables tab;
     uint64_t hand[3], played[3];
@@ -59,7 +79,7 @@ struct Doudizhu {
         return (w >> (16 * (k & 1))) & 0xffffu;
     }
     __device__ __forceinline__ void bind(const KParams &p) {
-        tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const uint64_t *>(p.tab[1]);
+        tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const ulonglong2 *>(p.tab[1]);
         tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
         tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);
     }
@@ -124,18 +144,32 @@ struct Doudizhu {
         const uint64_t H = sel3(hand, cur);
         const bool lead = greater == 3 || greater == cur;
         // candidate id ranges [lo1,hi1) u [lo2,hi2) (+ rocket, handled as part of range 2 when adjacent)
-        int lo1 = 0, hi1 = kDdzPass, lo2 = 0, hi2 = 0;
+        int lo1 = 0, hi1 = kDdzPass, lo2 = 0, hi2 = 0, tt_follow = kDdzTypeRocket;
         if (!lead) {
             const int tt = __ldg(tab.type + (greater_action)), tw = __ldg(tab.weight + (greater_action));
+            tt_follow = tt;
             if (tt == kDdzTypeRocket) { lo1 = hi1 = 0; }
             else if (tt == kDdzTypeBomb) { lo1 = (int)__ldg(tab.tw_start + (tt * 17 + tw + 1)); hi1 = kDdzRocket + 1; }   // larger bombs + rocket
             else { lo1 = (int)__ldg(tab.tw_start + (tt * 17 + tw + 1)); hi1 = (int)__ldg(tab.tw_start + (tt * 17 + 16)); lo2 = kDdzBomb0; hi2 = kDdzRocket + 1; }
         }
-        // level 0: one lane per batch of 32 mask words (1024 ids): in range and its nibble-wise minimum contained?
+        // which types the hand can play at all (bit t); a follow only asks about the target's type, bombs and the rocket
+        uint64_t F;
+        {
+            const uint64_t quad = ddz_type_ok(H, 35) ? 1ull : 0ull, rocket = ddz_type_ok(H, kDdzTypeRocket) ? 1ull : 0ull;
+            if (lead) {
+                F = (uint64_t)__ballot_sync(kFull, ddz_type_ok(H, lane)) | ((ddz_type_ok(H, 32) ? 1ull : 0ull) << 32) |
+                    (quad * 7ull << 33) | (rocket << 36);
+            } else {
+                F = (quad << 35) | (rocket << 36);
+                if (tt_follow < kDdzTypeBomb) F |= (ddz_type_ok(H, tt_follow) ? 1ull : 0ull) << tt_follow;
+            }
+        }
+        // level 0: one lane per batch of 32 mask words (1024 ids): in range, a playable type in it, nibble-wise minimum contained?
         bool blive = false;
         if (lane < (MASK_WORDS + 31) / 32) {
             const int a0 = 1024 * lane, a1 = a0 + 1024;
-            blive = ((a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2)) && ddz_contains(H, __ldg(tab.need + (864 + lane)));
+            const ulonglong2 nd = __ldg(tab.need + (864 + lane));
+            blive = ((a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2)) && (nd.y & F) != 0 && ddz_contains(H, nd.x);
         }
         uint32_t lb = __ballot_sync(kFull, blive);
         int cnt = 0, nl = 0;
@@ -146,7 +180,8 @@ struct Doudizhu {
             if (j < MASK_WORDS) {
                 const int a0 = 32 * j, a1 = a0 + 32;
                 const bool overlap = (a0 < hi1 && a1 > lo1) || (a0 < hi2 && a1 > lo2);
-                live = overlap && ddz_contains(H, __ldg(tab.need + (j)));
+                const ulonglong2 nd = __ldg(tab.need + (j));
+                live = overlap && (nd.y & F) != 0 && ddz_contains(H, nd.x);
             }
             uint32_t lw = __ballot_sync(kFull, live);
             while (lw) {                                                       // level 2: expand the live words
@@ -224,25 +259,70 @@ struct Doudizhu {
         if (lane == 0) dst[n >= 1 ? n - 1 : size - 1] = (T)1;
     }
     // envs/doudizhu.py:26-91 (row pre-zeroed; 790 used for the landlord, 901 for peasants, stride 912)
-    template <class T> __device__ void encode_obs(int seat, bool, T *row, int lane) const {
-        const int up = seat == 2 ? 0 : seat + 1, down = seat == 0 ? 2 : seat - 1;
-        put54(row, sel3(hand, seat), lane);
-        put54(row + 54, sel3(hand, up) + sel3(hand, down), lane);
-        const uint32_t newest = trace_at(8), prev = trace_at(7);
-        put54(row + 108, action_counts(newest != (uint32_t)kDdzPass ? newest : prev), lane);
+    template <class T> __device__ void encode_obs(int seat, bool, T *row, uint8_t *scratch, int lane) const {
+        const int up = seat == 2 ? 0 : seat + 1, down = seat == 0 ? 2 : seat - 1, mate = 3 - seat;
+        if constexpr (sizeof(T) == 1) {
+            // byte rows: the 14 (landlord) / 16 (peasant) 54-d blocks are built together.  Lane b computes the rank
+            // counts of block b (action blocks fetch their table row, all in flight at once) and parks them in
+            // shared memory; then lane (r, parity) writes the 4-byte thermometer of rank r (r = 13: the two joker
+            // bytes) of every second block -- 8 rounds of one LDS and two 16-bit STS (blocks are 2-byte aligned).
+            uint64_t *cw = reinterpret_cast<uint64_t *>(scratch + kObsScratch);
+            if (lane < 16) {
+                const int b = lane;
+                const uint32_t newest = trace_at(8), prev = trace_at(7);
+                uint32_t id = (uint32_t)kDdzPass;                               // table row of 'pass' = no cards
+                if (b == 2) id = newest != (uint32_t)kDdzPass ? newest : prev;
+                else if (b >= 3 && b <= 11) id = trace_at(b - 3);
+                else if (b == 14) id = last_by[0];
+                else if (b == 15) id = mate == 1 ? last_by[1] : last_by[2];
+                uint64_t v = action_counts(id);
+                if (b == 0) v = sel3(hand, seat);
+                else if (b == 1) v = sel3(hand, up) + sel3(hand, down);
+                else if (b == 12) v = seat == 0 ? played[2] : played[0];
+                else if (b == 13) v = seat == 0 ? played[1] : sel3(played, mate);
+                cw[b] = v;
+            }
+            __syncwarp();
+            const int r = lane & 15, nb = seat == 0 ? 14 : 16;
+            if (r < 14) {
+                uint8_t *dst = reinterpret_cast<uint8_t *>(row) + 54 * (lane >> 4) + 4 * r;
 #pragma unroll
-        for (int k = 0; k < 9; k++) put54(row + 162 + 54 * k, action_counts(trace_at(k)), lane);
+                for (int b = lane >> 4; b < 16; b += 2, dst += 108) {
+                    if (b < nb) {
+                        const uint64_t c = cw[b];
+                        if (r < 13) {
+                            const uint32_t k = (uint32_t)(c >> (4 * r)) & 15u;                     // 0..4 copies of rank r
+                            const uint32_t w = k ? 0x01010101u >> (32u - 8u * k) : 0u;               // thermometer bytes
+                            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)w;
+                            *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(w >> 16);
+                        } else {
+                            const uint32_t hi = (uint32_t)(c >> 32);
+                            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)((((hi >> 20) & 15u) ? 1u : 0u) | (((hi >> 24) & 15u) ? 0x100u : 0u));
+                        }
+                    }
+                }
+            }
+        } else {
+            put54(row, sel3(hand, seat), lane);
+            put54(row + 54, sel3(hand, up) + sel3(hand, down), lane);
+            const uint32_t newest = trace_at(8), prev = trace_at(7);
+            put54(row + 108, action_counts(newest != (uint32_t)kDdzPass ? newest : prev), lane);
+#pragma unroll
+            for (int k = 0; k < 9; k++) put54(row + 162 + 54 * k, action_counts(trace_at(k)), lane);
+            if (seat == 0) {
+                put54(row + 648, played[2], lane);
+                put54(row + 702, played[1], lane);
+            } else {
+                put54(row + 648, played[0], lane);
+                put54(row + 702, sel3(played, mate), lane);
+                put54(row + 756, action_counts(last_by[0]), lane);
+                put54(row + 810, action_counts(mate == 1 ? last_by[1] : last_by[2]), lane);
+            }
+        }
         if (seat == 0) {
-            put54(row + 648, played[2], lane);
-            put54(row + 702, played[1], lane);
             one_hot(row + 756, ddz_cards(hand[2]), 17, lane);
             one_hot(row + 773, ddz_cards(hand[1]), 17, lane);
         } else {
-            const int mate = 3 - seat;
-            put54(row + 648, played[0], lane);
-            put54(row + 702, sel3(played, mate), lane);
-            put54(row + 756, action_counts(last_by[0]), lane);
-            put54(row + 810, action_counts(mate == 1 ? last_by[1] : last_by[2]), lane);
             one_hot(row + 864, ddz_cards(hand[0]), 20, lane);
             one_hot(row + 884, ddz_cards(sel3(hand, mate)), 17, lane);
         }

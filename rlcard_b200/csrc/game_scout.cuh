@@ -215,7 +215,7 @@ struct Scout {
         for (int p = 0; p < 4; p++) out[p] = (float)(score[p] - hl[p]);
     }
     // envs/scout.py:171-235 (row pre-zeroed).  Scalars are float32(python float64 expression).
-    template <class T> __device__ void encode_obs(int seat, bool, T *row, int lane) const {
+    template <class T> __device__ void encode_obs(int seat, bool, T *row, uint8_t *, int lane) const {
         if (lane < 16) {
             const int s = lane;
             if (s < seli(hl, seat)) {

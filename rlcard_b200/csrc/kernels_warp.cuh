@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
                     g.legal(smask, scratch, lane);
                     __syncwarp();
                     for (int s = 0; s < G::P; s++) {
-                        g.encode_obs(s, false, srow, lane);
+                        g.encode_obs(s, false, srow, scratch, lane);
                         __syncwarp();
                         warp_flush_row<G, ObsT>(p.terminal_obs, env * G::P + s, srow, lane);
                         __syncwarp();
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
     __syncwarp();
     const int seat = (MODE == kModeObserve && p.seat) ? p.seat[env] : g.player();
     if (p.obs) {
-        g.encode_obs(seat, MODE != kModeObserve && h.t == 0, srow, lane);
+        g.encode_obs(seat, MODE != kModeObserve && h.t == 0, srow, scratch, lane);
         __syncwarp();
         warp_flush_row<G, ObsT>(p.obs, env, srow, lane);
     }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     size_t rowi = env;
     for (int t = 0; t < p.T; t++, rowi += p.n) {
         if (p.t_obs) {
-            g.encode_obs(g.player(), h.t == 0, srow, lane);
+            g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
             __syncwarp();
             warp_flush_row<G, ObsT>(p.t_obs, rowi, srow, lane);
         }

@@ -18,7 +18,7 @@ const uint64_t *doudizhu_rows_on_device(int device) {
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     if (device < 0 || device >= 64 || !blob || nbytes < sizeof(DdzBlobHeader)) return cudaErrorInvalidValue;
     DdzBlobHeader h; memcpy(&h, blob, sizeof h);
-    if (memcmp(h.magic, "DDZ1", 4) != 0 || h.n_actions != 27472 || h.n_words_padded != 896 || h.total != nbytes || h.n_types != 38) return cudaErrorInvalidValue;
+    if (memcmp(h.magic, "DDZ2", 4) != 0 || h.n_actions != 27472 || h.n_words_padded != 896 || h.total != nbytes || h.n_types != 38) return cudaErrorInvalidValue;
     int prev = 0; cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
@@ -28,7 +28,7 @@ cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     if (e == cudaSuccess) {
         const char *b = reinterpret_cast<const char *>(g_dev_blob[device]);
         g_tab[device].rows = reinterpret_cast<const uint64_t *>(b + h.off_rows);
-        g_tab[device].need = reinterpret_cast<const uint64_t *>(b + h.off_need);
+        g_tab[device].need = reinterpret_cast<const ulonglong2 *>(b + h.off_need);
         g_tab[device].type = reinterpret_cast<const uint8_t *>(b + h.off_type);
         g_tab[device].weight = reinterpret_cast<const uint8_t *>(b + h.off_weight);
         g_tab[device].tw_start = reinterpret_cast<const uint32_t *>(b + h.off_tw);

@@ -154,11 +154,54 @@ def action_strings():
     return [counts_to_str(unpack_counts(x)) for x in load()['counts']]
 
 
+# what every action of a type contains, whatever its kickers: `length` consecutive ranks (within 3..A when length > 1)
+# holding at least `mult` cards each; the rocket is both jokers.  (mult, length) per type id; pass: never a candidate.
+def type_requirements():
+    req = []
+    for name in TYPE_NAMES:
+        if name in ('solo', 'pair', 'trio'):
+            req.append(({'solo': 1, 'pair': 2, 'trio': 3}[name], 1))
+        elif name in ('trio_solo', 'trio_pair'):
+            req.append((3, 1))
+        elif name.startswith('solo_chain_'):
+            req.append((1, int(name.rsplit('_', 1)[1])))
+        elif name.startswith('pair_chain_'):
+            req.append((2, int(name.rsplit('_', 1)[1])))
+        elif name.startswith(('trio_chain_', 'trio_solo_chain_', 'trio_pair_chain_')):
+            req.append((3, int(name.rsplit('_', 1)[1])))
+        elif name in ('four_two_solo', 'four_two_pair', 'bomb'):
+            req.append((4, 1))
+        elif name == 'rocket':
+            req.append((0, 2))
+        else:
+            req.append((0, 0))
+    return req
+
+
+def type_feasible(counts, t):
+    """The device prefilter (game_doudizhu.cuh type_feasibility) on a list of 15 rank counts."""
+    mult, length = type_requirements()[t]
+    if TYPE_NAMES[t] == 'rocket':
+        return counts[13] >= 1 and counts[14] >= 1
+    if TYPE_NAMES[t] == 'pass':
+        return False
+    ok = [c >= mult for c in counts]
+    if length == 1:
+        return any(ok)
+    run = 0
+    for r in range(12):                                  # chains live on ranks 3..A
+        run = run + 1 if ok[r] else 0
+        if run >= length:
+            return True
+    return False
+
+
 def build_blob():
     """Device table blob for rlc_upload_tables(RLC_DOUDIZHU, ...) (layout: csrc/tu_doudizhu.cu DdzBlobHeader):
-    rows u64[27472] | need u64[864 + 32] (nibble-wise min of the 32 rows of each mask word; entries 864.. =
-    nibble-wise min of each batch of 32 mask words = 1024 ids) | type u8[27472] |
-    weight u8[27472] | tw_start u32[38][17] (first id of type t with weight >= w; [t][16] = end of type t)."""
+    rows u64[27472] | need u64[2 * (864 + 32)] | type u8[27472] | weight u8[27472] |
+    tw_start u32[38][17] (first id of type t with weight >= w; [t][16] = end of type t).
+    need holds one pair per mask word j (32 ids): [2j] = nibble-wise min of the 32 rows, [2j+1] = bit t set when some id
+    of the word has type t; pairs 864.. describe the batches of 32 mask words (1024 ids) the same way."""
     import struct
     tab = load()
     rows = tab['counts'].astype(np.uint64)
@@ -166,11 +209,15 @@ def build_blob():
     nib = np.stack([(rows >> np.uint64(4 * r)) & np.uint64(15) for r in range(15)], axis=1).astype(np.uint8)   # [A, 15]
     pad = np.full((n_words * 32 - NUM_ACTIONS, 15), 15, np.uint8)
     mins = np.concatenate([nib, pad]).reshape(n_words, 32, 15).min(axis=1)
-    need = np.zeros(864 + 32, np.uint64)
+    need = np.zeros(2 * (864 + 32), np.uint64)
     bmins = np.concatenate([mins, np.full((864 - n_words, 15), 15, np.uint8)]).reshape(27, 32, 15).min(axis=1)
     for r in range(15):
-        need[:n_words] |= mins[:, r].astype(np.uint64) << np.uint64(4 * r)
-        need[864:864 + 27] |= bmins[:, r].astype(np.uint64) << np.uint64(4 * r)
+        need[0:2 * n_words:2] |= mins[:, r].astype(np.uint64) << np.uint64(4 * r)
+        need[2 * 864:2 * (864 + 27):2] |= bmins[:, r].astype(np.uint64) << np.uint64(4 * r)
+    tbit = np.uint64(1) << tab['type'].astype(np.uint64)
+    for i in range(NUM_ACTIONS):
+        need[2 * (i >> 5) + 1] |= tbit[i]
+        need[2 * (864 + (i >> 10)) + 1] |= tbit[i]
     ntypes = len(TYPE_NAMES)
     tw = np.zeros((ntypes, 17), np.uint32)
     types, weights = tab['type'].astype(np.int64), tab['weight'].astype(np.int64)
@@ -191,7 +238,7 @@ def build_blob():
         offs.append(cur)
         cur += len(b)
     total = (cur + 15) & ~15
-    hdr = struct.pack('<4sIII6Q', b'DDZ1', NUM_ACTIONS, 864 + 32, ntypes, *offs, total)
+    hdr = struct.pack('<4sIII6Q', b'DDZ2', NUM_ACTIONS, 864 + 32, ntypes, *offs, total)
     blob = bytearray(total)
     blob[:len(hdr)] = hdr
     for o, b in zip(offs, parts):

@@ -56,3 +56,30 @@ def test_seed_words():
         w = oracle.seed_words(seed)
         lo, hi = struct.unpack('2I', hashlib.sha512(str(seed).encode()).digest()[:8])
         assert w == ([lo, hi] if hi else [lo])
+
+
+def test_doudizhu_type_prefilter_is_sound():
+    """The device legal-set generator skips whole action types the hand cannot play (game_doudizhu.cuh ddz_type_ok ==
+    doudizhu_table.type_feasible).  Sound iff every table row passes the requirement of its own type: a hand that
+    contains the row then passes it too (the requirement is monotone in the rank counts).  Also pins the blob layout
+    the library parses (need pairs: nibble-wise minimum | type bits per mask word and per batch of 32 words)."""
+    import struct
+    import numpy as np
+    from rlcard_b200 import doudizhu_table as dt
+    tab = dt.load()
+    for i, x in enumerate(tab['counts']):
+        if i != dt.PASS_ID:
+            assert dt.type_feasible(dt.unpack_counts(x), int(tab['type'][i])), (i, dt.TYPE_NAMES[tab['type'][i]])
+    for t, name in enumerate(dt.TYPE_NAMES):                       # the empty hand plays nothing
+        assert not dt.type_feasible([0] * 15, t), name
+    blob = dt.build_blob()
+    magic, n_actions, n_words, n_types, off_rows, off_need, off_type, off_weight, off_tw, total = struct.unpack_from('<4sIII6Q', blob)
+    assert magic == b'DDZ2' and n_actions == 27472 and n_words == 896 and n_types == 38 and total == len(blob)
+    need = np.frombuffer(blob, np.uint64, 2 * 896, off_need).reshape(896, 2)
+    types = tab['type'].astype(np.int64)
+    for j in (0, 1, 400, 858):
+        want = 0
+        for i in range(32 * j, min(32 * j + 32, dt.NUM_ACTIONS)):
+            want |= 1 << int(types[i])
+        assert int(need[j, 1]) == want
+    assert int(need[864 + 26, 1]) & (1 << dt.T_PASS) and not int(need[864, 1]) & (1 << dt.T_PASS)
