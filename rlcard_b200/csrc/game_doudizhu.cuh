@@ -82,6 +82,8 @@ struct Doudizhu {
         tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const ulonglong2 *>(p.tab[1]);
         tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
         tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);
+        n_legal = 0; n_live = 0; has_pass = false;           // legal() relies on these describing the (zeroed) smask; writing the
+                                                             // mask row as zero words + listed words on top measured 14 % slower
     }
     __device__ void load(const uint32_t *w, int) {
 #pragma unroll
@@ -137,7 +139,10 @@ struct Doudizhu {
     // number of legal ids before each (word index | prefix << 10), so the policy never rescans the mask.
     __device__ int legal(uint32_t *smask, uint8_t *scratch, int lane) {
         uint32_t *slist = reinterpret_cast<uint32_t *>(scratch + 64);
-        for (int j = lane; j < MASK_WORDS; j += 32) smask[j] = 0;
+        // smask is all zero outside the words the previous legal() listed (kernels zero it once, bind() starts the list
+        // empty): clear those instead of all 859 words
+        for (int idx = lane; idx < n_live; idx += 32) smask[slist[idx] & 1023u] = 0;
+        if (has_pass && lane == 0) smask[kDdzPass >> 5] = 0;
         __syncwarp();
         n_legal = 0; n_live = 0; has_pass = false;
         if (winner != 3) return 0;                                             // terminal: actions = []
@@ -286,19 +291,16 @@ struct Doudizhu {
             const int r = lane & 15, nb = seat == 0 ? 14 : 16;
             if (r < 14) {
                 uint8_t *dst = reinterpret_cast<uint8_t *>(row) + 54 * (lane >> 4) + 4 * r;
+                const uint32_t *half = reinterpret_cast<const uint32_t *>(cw) + 2 * (lane >> 4) + (r >> 3);   // the word holding rank r
+                const int sh = 4 * (r & 7);
 #pragma unroll
-                for (int b = lane >> 4; b < 16; b += 2, dst += 108) {
+                for (int b = lane >> 4; b < 16; b += 2, dst += 108, half += 4) {
                     if (b < nb) {
-                        const uint64_t c = cw[b];
-                        if (r < 13) {
-                            const uint32_t k = (uint32_t)(c >> (4 * r)) & 15u;                     // 0..4 copies of rank r
-                            const uint32_t w = k ? 0x01010101u >> (32u - 8u * k) : 0u;               // thermometer bytes
-                            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)w;
-                            *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(w >> 16);
-                        } else {
-                            const uint32_t hi = (uint32_t)(c >> 32);
-                            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)((((hi >> 20) & 15u) ? 1u : 0u) | (((hi >> 24) & 15u) ? 0x100u : 0u));
-                        }
+                        const uint32_t w = *half, k = (w >> sh) & 15u;                                 // 0..4 copies of rank r
+                        uint32_t v = k ? 0x01010101u >> (32u - 8u * k) : 0u;                            // thermometer bytes
+                        if (r == 13) v = (k ? 1u : 0u) | (((w >> 24) & 15u) ? 0x100u : 0u);             // the two joker bytes
+                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+                        if (r < 13) *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(v >> 16);
                     }
                 }
             }

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
     ObsT *srow = reinterpret_cast<ObsT *>(base);
     uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
     uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
-    warp_tile_zero(base, kRowBytes, lane);
+    warp_tile_zero(base, kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15), lane);      // obs row and mask words
     __syncwarp();
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     ObsT *srow = reinterpret_cast<ObsT *>(base);
     uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
     uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
-    warp_tile_zero(base, kRowBytes, lane);
+    warp_tile_zero(base, kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15), lane);      // obs row and mask words
     __syncwarp();
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(128) k_judge_doudizhu(const uint8_t *hands, co
     uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)wib * kWarpBytes;
     uint32_t *smask = reinterpret_cast<uint32_t *>(base);
     uint8_t *scratch = base + ((Doudizhu::MASK_WORDS * 4 + 15) & ~15);
+    for (int w = lane; w < Doudizhu::MASK_WORDS; w += 32) smask[w] = 0;
+    __syncwarp();
     Doudizhu g; g.bind(p);
     uint64_t h = 0;
     for (int r = 0; r < 15; r++) h |= (uint64_t)(hands[(size_t)i * 15 + r] & 15) << (4 * r);
