@@ -13,6 +13,7 @@ typedef struct {
     ucard deck[108], played[108], hand[2][108], target;
     int dl, pl, hl[2];
     int current, direction, is_over, winner, err;
+    int opening;        /* throughput spec: the 15 opening cards are popped in order after a partial Fisher-Yates */
 } uno_t;
 
 #define TRAIT(c) ((c).code % 15)
@@ -41,7 +42,7 @@ static void uno_shuffle(orc_chance *ch, ucard *x, int n) {              /* deale
 }
 static int uno_pop(uno_t *g, orc_chance *ch, ucard *out) {              /* deck.pop(); Q-UNO4: empty -> flag, not emulated */
     if (g->dl <= 0) { g->err |= 8; return 0; }
-    if (ch->kind == ORC_CHANCE_PHILOX) {
+    if (ch->kind == ORC_CHANCE_PHILOX && !g->opening) {
         int cnt[60], r = (int)orc_below(ch, (uint32_t)g->dl), code = 0;
         memset(cnt, 0, sizeof cnt);
         for (int i = 0; i < g->dl; i++) cnt[g->deck[i].code]++;
@@ -70,11 +71,17 @@ static int uno_reset(void *s, orc_chance *ch) {
     uno_t *g = (uno_t *)s;
     memset(g, 0, sizeof *g);
     g->dl = uno_init_deck(g->deck);
-    uno_shuffle(ch, g->deck, g->dl);
+    if (ch->kind == ORC_CHANCE_PHILOX) {
+        /* throughput spec: only the 15 positions the opening deal pops are shuffled (reverse Fisher-Yates steps
+         * i = 107 .. 93 over the deck in utils.py:31-52 order); what stays in the pile is a multiset anyway */
+        for (int i = 107; i >= 93; i--) { uint32_t j = orc_below(ch, (uint32_t)i + 1u); ucard t = g->deck[i]; g->deck[i] = g->deck[j]; g->deck[j] = t; }
+        g->opening = 1;
+    } else uno_shuffle(ch, g->deck, g->dl);
     uno_deal(g, ch, 0, 7); uno_deal(g, ch, 1, 7);
     g->direction = 1; g->current = 0; g->winner = -1;
     ucard top;
     uno_pop(g, ch, &top);
+    g->opening = 0;
     while (TRAIT(top) == 14) { g->deck[g->dl++] = top; uno_shuffle(ch, g->deck, g->dl); uno_pop(g, ch, &top); }
     if (TRAIT(top) == 13) top.color = (uint8_t)orc_below(ch, 4);
     g->target = top; g->played[g->pl++] = top;

@@ -21,6 +21,7 @@ struct Blackjack {
     static constexpr int kMaxResetDraws = 55;
     static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
+    static constexpr bool kWarpDeal = false;
     static constexpr bool kChanceAwareState = true;   // load_k/store_k<chance kind>
     int p_sum, p_aces, d_first, d_vis_sum, d_vis_aces, winner, deck_len;
     uint8_t deck[52];

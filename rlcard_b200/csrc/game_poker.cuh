@@ -63,6 +63,7 @@ struct Leduc {
     static constexpr int kMaxResetDraws = 6;
     static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
+    static constexpr bool kWarpDeal = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 128;   // deal table: x in [0,120) -> hand0 | hand1 << 2 | public << 4
     int hand0, hand1, pub, pub_dealt, chips0, chips1, rc, fold0, fold1;
@@ -235,6 +236,7 @@ struct Limit {
     static constexpr int kMaxResetDraws = 52;
     static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
+    static constexpr bool kWarpDeal = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}
@@ -354,6 +356,7 @@ struct NoLimit {
     static constexpr int kMaxResetDraws = 53;
     static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
+    static constexpr bool kWarpDeal = false;
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
     static __device__ __forceinline__ void fill_shared(uint8_t *, int, int) {}

@@ -27,6 +27,26 @@
 
 namespace rlc {
 
+// Reverse Fisher-Yates over an identity deck of n cards of which only the last K positions are popped: original
+// position of the card that ends at position n-1-s (same traceback as fy_tail_cards in game_poker.cuh).
+template <int K>
+__device__ __forceinline__ void fy_tail_positions(int n, const int (&j)[K], int (&c)[K]) {
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        int pos = j[s];
+#pragma unroll
+        for (int r = s - 1; r >= 0; r--) pos = (pos == j[r]) ? n - 1 - r : pos;
+        c[s] = pos;
+    }
+}
+// physical position in the deck of utils.py:31-52 (27 cards per colour: 0, 1 1 .. 9 9, skip x2, reverse x2, draw_2 x2,
+// wild, wild_draw_4) -> card code 15 * colour + trait
+__device__ __forceinline__ int uno_code_at(int pos) {
+    const int c = pos / 27, r = pos - 27 * c;
+    const int t = r == 0 ? 0 : (r <= 18 ? (r + 1) >> 1 : (r <= 24 ? 10 + ((r - 19) >> 1) : r - 12));
+    return 15 * c + t;
+}
+
 template <bool BAG>
 struct UnoT {
     static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = BAG ? 19 : 38, MASK_WORDS = 2;
@@ -185,10 +205,36 @@ struct UnoT {
         dl = 108; pl = 0;
 #pragma unroll
         for (int p = 0; p < 2; p++) { hc[p][0] = hc[p][1] = hc[p][2] = hc[p][3] = 0; hw[p] = 0; }
-        shuffle_deck(ch);
-        deal(0, 7, ch, err); deal(1, 7, ch, err);
+        int top;
+        if constexpr (BAG) {
+            // throughput spec: the 15 cards of the opening deal come from a partial Fisher-Yates over the 108 physical
+            // positions of the deck (15 draws and a traceback); what stays in the pile is a multiset anyway.  The fused
+            // rollout deals with the whole warp instead (warp_deal below, same draws, same result).
+            int j[15], pos[15];
+#pragma unroll
+            for (int q = 0; q < 15; q++) j[q] = (int)ch.below((uint32_t)(108 - q));
+            fy_tail_positions<15>(108, j, pos);
+            top = 0;
+#pragma unroll
+            for (int q = 0; q < 15; q++) {
+                const int code = uno_code_at(pos[q]), c = code / 15, t = code - 15 * c;
+                const uint32_t dec = 1u << (2 * t);
+                dk[0] -= c == 0 ? dec : 0u; dk[1] -= c == 1 ? dec : 0u; dk[2] -= c == 2 ? dec : 0u; dk[3] -= c == 3 ? dec : 0u;
+                if (q < 14) to_hand(q < 7 ? 0 : 1, code);
+                else top = code;
+            }
+            dl = 93;
+        } else {
+            shuffle_deck(ch);
+            deal(0, 7, ch, err); deal(1, 7, ch, err);
+            top = pop_deck(ch, err);
+        }
+        open_round(ch, top, err);
+    }
+    // the rest of init_game once both hands and the first top card are dealt: dealer.py:28-39 (a wild_draw_4 goes back),
+    // round.py:24-52 (colour of a wild top, opening effects)
+    template <class Ch> __device__ void open_round(Ch &ch, int top, int &err) {
         dir = 0; cur = 0; winner = -1;
-        int top = pop_deck(ch, err);
         while (top % 15 == 14) { unpop_deck(top); shuffle_deck(ch); top = pop_deck(ch, err); }
         tcode = top; tcolor = top / 15;
         if (top % 15 == 13) tcolor = (int)ch.below(4u);
@@ -197,6 +243,63 @@ struct UnoT {
         if (t == 10) cur = 1;
         else if (t == 11) { dir = 1; cur = 1; }
         else if (t == 12) deal(0, 2, ch, err);
+    }
+    // Opening deal of the fused rollout, by the whole warp: for every lane whose env starts an episode, lane q draws
+    // swap partner q of the partial Fisher-Yates from that env's Philox stream, traces its card back through the
+    // earlier swaps (14 shuffles), and the hands / pile counters are summed with warp reductions -- ~200 warp
+    // instructions per deal instead of ~1900 executed by one lane while the other 31 wait.  Same draws and result as
+    // reset() above.
+    static constexpr bool kWarpDeal = BAG;
+    __device__ void warp_deal(ChancePhilox &ch, bool starts, int lane) {
+        uint32_t need = __ballot_sync(0xffffffffu, starts);
+        while (need) {
+            const int L = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t env = __shfl_sync(0xffffffffu, ch.env, L), kk = __shfl_sync(0xffffffffu, ch.k, L);
+            const uint32_t dom = __shfl_sync(0xffffffffu, ch.dom, L), d0 = __shfl_sync(0xffffffffu, ch.d, L);
+            const uint32_t k0 = __shfl_sync(0xffffffffu, ch.k0, L), k1 = __shfl_sync(0xffffffffu, ch.k1, L);
+            const uint32_t idx = d0 + (uint32_t)lane;
+            uint32_t o0, o1, o2, o3;
+            philox4x32_10(kk, idx >> 2, env, dom, k0, k1, o0, o1, o2, o3);
+            const int j = (int)__umulhi(sel4(o0, o1, o2, o3, idx & 3u), (uint32_t)(108 - min(lane, 14)));
+            int pos = j;
+#pragma unroll
+            for (int r = 13; r >= 0; r--) {
+                const int jr = __shfl_sync(0xffffffffu, j, r);
+                pos = (r < lane && pos == jr) ? 107 - r : pos;
+            }
+            const int code = uno_code_at(pos), c = code / 15, t = code - 15 * c;
+            const bool in0 = lane < 7, in1 = lane >= 7 && lane < 14, dealt = lane < 15;
+            const uint32_t unit = 1u << (2 * t);
+            uint32_t ndk[4], nh0[4], nh1[4], nhw[2] = {0u, 0u};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ndk[q] = __reduce_add_sync(0xffffffffu, (dealt && c == q) ? unit : 0u);
+                nh0[q] = __reduce_add_sync(0xffffffffu, (in0 && c == q && t < 13) ? unit : 0u);
+                nh1[q] = __reduce_add_sync(0xffffffffu, (in1 && c == q && t < 13) ? unit : 0u);
+            }
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int tr = 13; tr < 15; tr++) {                     // held wilds: count + original colours in deal order
+                    const bool mine = (p ? in1 : in0) && t == tr;
+                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                    const int my = __popc(m & ((1u << lane) - 1u));
+                    const uint32_t field = (uint32_t)__popc(m) | __reduce_or_sync(0xffffffffu, mine ? (uint32_t)c << (3 + 2 * my) : 0u);
+                    nhw[p] |= field << (tr == 13 ? 0 : 11);
+                }
+            const int top = __shfl_sync(0xffffffffu, code, 14);
+            if (lane == L) {
+                int err = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) { dk[q] = 0x16AAAAA9u - ndk[q]; pk[q] = 0; hc[0][q] = nh0[q]; hc[1][q] = nh1[q]; }
+                hw[0] = nhw[0]; hw[1] = nhw[1];
+                dl = 93; pl = 0;
+                ch.d = d0 + 15u;
+                open_round(ch, top, err);
+                ch.err |= err;
+            }
+        }
     }
     __device__ __forceinline__ int player() const { return cur; }
     __device__ __forceinline__ bool over() const { return winner >= 0; }   // game.py:154-160
@@ -225,7 +328,7 @@ struct UnoT {
     // The lanes of a warp take different actions, so the transition is one mostly branch-free pass over flags; the only
     // branches left are the ones that make Philox draws (pop a card, colour of an auto-played wild, penalty cards).
     // smallest envs-per-warp the fused rollout may use on batches too small to fill the schedulers (measured: UNO gains
-    // 12 % at 16 because half as many warp-steps pay for some lane's reset; 8 loses it again to idle lanes)
+    // 3-12 % at 16 because half as many warp-steps pay for some lane's draw or reset; 8 loses it again to idle lanes)
     static constexpr int kRolloutMinEpw = 16;
     static constexpr bool kHasApply = true;      // the fused rollout only takes legal ids: it calls apply() directly
     template <class Ch> __device__ void step(int id, Ch &ch, int &err) {

@@ -225,12 +225,19 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     constexpr bool kStageMask = G::A > 4;
     constexpr int kMaskTile = kStageMask ? ((EPW * G::A + 15) & ~15) : 0;
     uint8_t *mtile = reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes + ((G::kSharedBytes + 15) & ~15) + wib * kMaskTile;
+    constexpr bool kWarpDeal = G::kWarpDeal && Ch::kKind == 0;   // episodes are dealt by the whole warp (UNO, throughput mode)
+    bool starts = false;                                         // this lane's env begins an episode at this point
     if (valid) {
         h.load(p.state, p.n, i);
         game_load<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         ChanceIO<Ch>::open(ch, p, i);
-        if (h.episode == 0) { ch.begin_reset(h.k); new_episode(g, ch, h); }
+        if (h.episode == 0) {
+            ch.begin_reset(h.k);
+            if constexpr (kWarpDeal) { h.episode++; h.t = 0; starts = true; }
+            else new_episode(g, ch, h);
+        }
     }
+    if constexpr (kWarpDeal) g.warp_deal(ch, starts, lane);
     // per-thread output cursors, advanced by one trajectory row (n envs) per step
     uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
     const size_t obs_step = p.n * (size_t)kRowBytes;
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     size_t rowi = i;
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         uint32_t m[G::MASK_WORDS];
+        starts = false;
         if (valid) {
             if (ALL || p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
             g.legal(m);
@@ -285,7 +293,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             for (int q = 0; q < G::P; q++) pay[q] = 0.f;
             if (over) {
                 g.payoffs(pay);
-                new_episode(g, ch, h);
+                if constexpr (kWarpDeal) { h.episode++; h.t = 0; starts = true; }
+                else new_episode(g, ch, h);
             }
             if (ALL || p.t_done) p.t_done[rowi] = over ? 1 : 0;
             if (ALL || p.t_payoffs) {
@@ -297,6 +306,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
                 }
             }
         }
+        if constexpr (kWarpDeal) g.warp_deal(ch, starts, lane);
     }
     if (valid) {
         ChanceIO<Ch>::close(ch, p, i);
@@ -312,9 +322,10 @@ enum { kOpReset = 0, kOpStep = 1, kOpObserve = 2, kOpRollout = 3 };
 
 // envs per warp of the fused rollout: 32 unless the batch leaves warp schedulers short of kRolloutWarpsPerScheduler
 // warps AND the game gains from fewer envs per warp (G::kRolloutMinEpw; measured on a B200 at 16 384 envs, ms per
-// 128-step launch at 32 / 16 / 8: UNO 0.658 / 0.585 / 0.730, Limit 0.106 / 0.134 / 0.200, no-limit 0.197 / 0.281 / 0.483,
-// Blackjack (65 536 envs) 0.614 / 0.900 / 1.460 -- only UNO, whose warps diverge on resets, wins).  RLC_ROLLOUT_EPW forces
-// a value (tests, tuning).  Only the Philox throughput mode is specialised, replays always run 32 envs per warp.
+// 128-step launch at 32 / 16 / 8: UNO 0.405 / 0.392 / 0.587 (0.658 / 0.585 / 0.730 before the warp-cooperative deal),
+// Limit 0.106 / 0.134 / 0.200, no-limit 0.197 / 0.281 / 0.483, Blackjack (65 536 envs) 0.614 / 0.900 / 1.460 -- only
+// UNO, whose warps diverge on draws and resets, wins).  RLC_ROLLOUT_EPW forces a value (tests, tuning).  Only the
+// Philox throughput mode is specialised, replays always run 32 envs per warp.
 constexpr int kRolloutWarpsPerScheduler = 2;
 inline int rollout_envs_per_warp(size_t n, int min_epw) {
     static int schedulers = 0;
