@@ -186,6 +186,24 @@ __device__ __forceinline__ int popc_words(const uint32_t (&m)[WORDS]) {
     return c;
 }
 
+// Trajectory / obs / mask rows are written once and never re-read by the kernels: streaming stores.  RLC_STORE_POLICY
+// selects the cache operator for tuning runs (0 = st.global.cs, the default; 1 = plain; 2 = .wt; 3 = .cg).
+#ifndef RLC_STORE_POLICY
+#define RLC_STORE_POLICY 0
+#endif
+template <class T>
+__device__ __forceinline__ void st_stream(T *p, T v) {
+#if RLC_STORE_POLICY == 0
+    __stcs(p, v);
+#elif RLC_STORE_POLICY == 1
+    *p = v;
+#elif RLC_STORE_POLICY == 2
+    __stwt(p, v);
+#else
+    __stcg(p, v);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // Warp-cooperative row writer.  Each lane fills its own row of a per-warp shared-memory tile
 // (rows of ROW_BYTES, one env per lane); the 32 rows are contiguous in global memory, so the
@@ -203,7 +221,7 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (int c = lane; c < (nbytes >> 4); c += kWarp) {
             const uint4 v = reinterpret_cast<uint4 *>(tile)[c];
-            __stcs(reinterpret_cast<uint4 *>(gdst) + c, v);
+            st_stream(reinterpret_cast<uint4 *>(gdst) + c, v);
             reinterpret_cast<uint4 *>(tile)[c] = z;
         }
     } else {
@@ -237,7 +255,7 @@ __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *til
 #pragma unroll
         for (int q = 0; q < kBatch; q++) {
             const int c0 = b0 + q * kWarp, c = c0 + lane;
-            if (c0 < kChunks && (c0 + kWarp <= kChunks || c < kChunks)) __stcs(g4 + c, v[q]);
+            if (c0 < kChunks && (c0 + kWarp <= kChunks || c < kChunks)) st_stream(g4 + c, v[q]);
         }
     }
 }

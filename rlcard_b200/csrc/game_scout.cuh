@@ -4,9 +4,9 @@
 //
 // Hands and the table set are ordered lists of (top, bottom) cards with values 1..10, kept as two
 // 16-nibble words each (slot k = bits [4k, 4k+4)), so that slicing, inserting and the group/run tests
-// are a handful of 64-bit operations.  The whole state is replicated in every lane's registers; the 32
-// lanes split the 204 candidate action ids (lane = id mod 32) and each __ballot_sync yields one word of
-// the legal mask (round.py:225-260).
+// are a handful of 64-bit operations.  The whole state is replicated in every lane's registers; for the
+// legal mask (round.py:225-260) lane s owns the plays that start at hand position s -- one contiguous id
+// range per start -- and the mask words are warp OR-reductions of those ranges.
 //
 // Game words (23): [0..7] hand tops p0..p3 (lo,hi)  [8..15] hand bottoms  [16,17] table tops
 //   [18,19] table bottoms  [20] hl0..3 (5 bits each) | tl [20:25) | owner [25:28) (4 = none) |
@@ -31,7 +31,6 @@ struct Scout {
     uint64_t ht[4], hb[4], tt, tb;
     int hl[4], score[4], tl, owner, consec, cur, over_;
     bool forced;           // current_player_forced_scout: recomputed by every legal() (round.py:246)
-    uint64_t segtab;       // per lane: (start | (end-1) << 4) of play ids lane, lane+32, ... (utils.py:186-200)
 
     __device__ __forceinline__ uint64_t sel(const uint64_t (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
     __device__ __forceinline__ int seli(const int (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
@@ -52,15 +51,6 @@ struct Scout {
         tl = (m >> 20) & 31; owner = (m >> 25) & 7; consec = (m >> 28) & 3; cur = (m >> 30) & 3;
         score[0] = s0 & 0xffff; score[1] = s0 >> 16; score[2] = s1 & 0xffff; score[3] = (s1 >> 16) & 0x7fff; over_ = s1 >> 31;
         forced = false; lm_valid = false;
-        // play ids of this lane: id = lane + 32 r, r = 0..4 -> (start, end) of the s-major enumeration
-        segtab = 0;
-        int s = 0, base = 0;
-        for (int r = 0; r < 5; r++) {
-            const int id = lane + 32 * r;
-            while (s < 16 && id >= base + (16 - s)) { base += 16 - s; s++; }
-            const int e = s + (id - base) + 1;
-            if (id < 136) segtab |= (uint64_t)(s | ((e - 1) << 4)) << (8 * r);
-        }
     }
     __device__ void store(uint32_t *w, int lane) const {
         if (lane != 0) return;
@@ -86,42 +76,50 @@ struct Scout {
         return len == 1 || group || asc || desc;
     }
     // round.py:225-260: 204-bit legal set of the current player, identical in all lanes.
-    // Valid play segments (utils/utils.py:17-67) are read off three adjacency masks of the hand (bit i: card i+1
-    // equals / is one above / is one below card i, built with one ballot each): slice [s, s+len) is a group, an
-    // ascending or a descending run iff the mask has len-1 consecutive ones from bit s.
+    // Play ids are enumerated start-major (utils.py:186-200): start s owns the contiguous ids base(s) + len - 1,
+    // base(s) = 16 s - s (s - 1) / 2.  From s the valid lengths are a prefix 1 .. 1 + max(#equal, #ascending, #descending
+    // adjacent steps) (utils.py:17-67), cut at the hand's end; against a table set of tl cards the longer ones always
+    // beat it and length tl does iff its (type, rank) is higher (round.py:262-295) -- so each start contributes ONE id
+    // range.  Lane s works out its range from three adjacency ballots and the five mask words are OR-reductions of the
+    // lanes' ranges; the scout ids 136 + 4 ins + {front, front flipped, back, back flipped} are a closed-form pattern.
     __device__ void legal_words(uint32_t (&m)[7], int lane) {
         const uint64_t T = sel(ht, cur);
         const int n = seli(hl, cur);
         int ttype = 0, trank = 0;
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
-        const bool can_scout = tl > 0 && n < 16;
         const int a = nib(T, lane & 15), b = nib(T, (lane + 1) & 15);
         const bool adj = lane < 15 && lane + 1 < n;
         const uint32_t eqm = __ballot_sync(kFull, adj && b == a);
         const uint32_t upm = __ballot_sync(kFull, adj && b == a + 1);
         const uint32_t dnm = __ballot_sync(kFull, adj && b == a - 1);
-#pragma unroll
-        for (int r = 0; r < 7; r++) {
-            const int id = lane + 32 * r;
-            bool ok = false;
-            if (r < 5 && id < 136) {
-                const int code = (int)((segtab >> (8 * r)) & 255ull), s = code & 15, e = (code >> 4) + 1, len = e - s;
-                const int first = nib(T, s);
-                const int req = __ffs((int)~(eqm >> s)) - 1, rup = __ffs((int)~(upm >> s)) - 1, rdn = __ffs((int)~(dnm >> s)) - 1;
-                const bool group = len - 1 <= req, asc = len - 1 <= rup, desc = len - 1 <= rdn;
-                const bool valid = len == 1 || group || asc || desc;
-                const int type = len == 1 ? 0 : (group ? 2 : 1);
-                const int rank = (len > 1 && !group) ? (asc ? first + len - 1 : first) : first;       // run: max(first, last)
-                const bool stronger = tl == 0 || len > tl || (len == tl && (type > ttype || (type == ttype && rank > trank)));   // round.py:262-295
-                ok = e <= n && valid && stronger;
+        int lo_id = 1, hi_id = 0;                                          // empty
+        if (lane < n && lane < 16) {
+            const int s = lane;
+            const int req = __ffs((int)~(eqm >> s)) - 1, rup = __ffs((int)~(upm >> s)) - 1, rdn = __ffs((int)~(dnm >> s)) - 1;
+            const int hi_len = min(max(req, max(rup, rdn)) + 1, n - s);
+            int lo_len = 1;
+            if (tl > 0) {                                                  // a set of exactly tl cards: stronger than the table?
+                const bool group = tl - 1 <= req, asc = tl - 1 <= rup;
+                const int type = tl == 1 ? 0 : (group ? 2 : 1);
+                const int rank = (tl > 1 && !group) ? (asc ? a + tl - 1 : a) : a;          // run: max(first, last)
+                lo_len = (type > ttype || (type == ttype && rank > trank)) ? tl : tl + 1;   // validity of length tl: tl <= hi_len
             }
-            if (id >= 136 && id < 204) {
-                const int k = id - 136, ins = k >> 2;
-                ok = can_scout && ins <= n && ((k & 3) < 2 || tl > 1);
-            }
-            m[r] = __ballot_sync(kFull, ok);
+            const int base = 16 * s - ((s * (s - 1)) >> 1);
+            lo_id = base + lo_len - 1; hi_id = base + hi_len - 1;
         }
-        forced = (m[0] | m[1] | m[2] | m[3] | (m[4] & 0xffu)) == 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
+            const uint32_t bits = x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
+            m[r] = __reduce_or_sync(kFull, bits);
+        }
+        forced = (m[0] | m[1] | m[2] | m[3] | m[4]) == 0;
+        m[5] = m[6] = 0;
+        if (tl > 0 && n < 16) {                                            // scout: insert position <= n; back variants need tl > 1
+            const int nb = 4 * n + 4;
+            const uint64_t S = (nb >= 64 ? ~0ull : (1ull << nb) - 1ull) & (tl > 1 ? ~0ull : 0x3333333333333333ull);
+            m[4] |= (uint32_t)(S << 8); m[5] = (uint32_t)(S >> 24); m[6] = (uint32_t)(S >> 56);
+        }
     }
     uint32_t lm[7];        // the last legal() set, identical in all lanes
     bool lm_valid;         // lm / forced already describe the current state (step() computed them)

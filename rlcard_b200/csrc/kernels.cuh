@@ -76,7 +76,7 @@ template <class G>
 __device__ __forceinline__ void write_mask_row(uint8_t *gmask, size_t env, const uint32_t (&m)[G::MASK_WORDS]) {
     if constexpr (G::A == 4) {
         const uint32_t w = (m[0] & 1u) | ((m[0] & 2u) << 7) | ((m[0] & 4u) << 14) | ((m[0] & 8u) << 21);
-        __stcs(reinterpret_cast<uint32_t *>(gmask) + env, w);
+        st_stream(reinterpret_cast<uint32_t *>(gmask) + env, w);
     } else if constexpr (G::A == 2) {
         reinterpret_cast<uint16_t *>(gmask)[env] = (uint16_t)((m[0] & 1u) | ((m[0] & 2u) << 7));
     } else {
@@ -276,14 +276,14 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             if constexpr (!kStageMask) {
                 if (ALL || p.t_mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
             }
-            if (ALL || p.t_player) __stcs(p.t_player + rowi, g.player());
+            if (ALL || p.t_player) st_stream(p.t_player + rowi, g.player());
             uint32_t word;
             if constexpr (Ch::kKind == 0) word = ch.begin_step(h.k);
             else word = policy_word_only(p, i, h.k);
             int cnt;
             const int a = pick_action<G>(m, word, cnt);
             if constexpr (G::kUsesChain) ch.seed_chain(word, (uint32_t)cnt);
-            if (ALL || p.t_action) __stcs(p.t_action + rowi, a);
+            if (ALL || p.t_action) st_stream(p.t_action + rowi, a);
             if constexpr (G::kHasApply) g.apply(a, ch, err);          // a was picked from the legal set: no re-validation
             else g.step(a, ch, err);
             h.t++; h.k++;
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             }
             if (ALL || p.t_done) p.t_done[rowi] = over ? 1 : 0;
             if (ALL || p.t_payoffs) {
-                if constexpr (G::P == 2) __stcs(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
-                else if constexpr (G::P == 4) __stcs(reinterpret_cast<float4 *>(p.t_payoffs) + rowi, make_float4(pay[0], pay[1], pay[2], pay[3]));
+                if constexpr (G::P == 2) st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
+                else if constexpr (G::P == 4) st_stream(reinterpret_cast<float4 *>(p.t_payoffs) + rowi, make_float4(pay[0], pay[1], pay[2], pay[3]));
                 else {
 #pragma unroll
                     for (int q = 0; q < G::P; q++) p.t_payoffs[rowi * G::P + q] = pay[q];

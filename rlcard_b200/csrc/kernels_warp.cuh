@@ -54,13 +54,13 @@ template <class G>
 __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const uint32_t *sm, int lane) {
     if constexpr (G::kMaskBitpacked) {
         uint32_t *dst = reinterpret_cast<uint32_t *>(gmask) + row * (size_t)G::MASK_WORDS;
-        for (int wi = lane; wi < G::MASK_WORDS; wi += 32) __stcs(dst + wi, sm[wi]);
+        for (int wi = lane; wi < G::MASK_WORDS; wi += 32) st_stream(dst + wi, sm[wi]);
     } else {
         static_assert(G::A % 4 == 0, "dense mask rows are written as 32-bit words");
         uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gmask) + row * (size_t)G::A);
         for (int q = lane; q < G::A / 4; q += 32) {
             const uint32_t b = (sm[q >> 3] >> ((q & 7) * 4)) & 15u;
-            __stcs(dst + q, (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
+            st_stream(dst + q, (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
         }
     }
 }
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
         cnt = g.legal(smask, scratch, lane);                      // legal set of the state the next iteration emits
         __syncwarp();
         if (lane == 0) {
-            if (p.t_player) __stcs(p.t_player + rowi, pl);
-            if (p.t_action) __stcs(p.t_action + rowi, a);
+            if (p.t_player) st_stream(p.t_player + rowi, pl);
+            if (p.t_action) st_stream(p.t_action + rowi, a);
             if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
         }
         if (p.t_payoffs && lane < G::P) {

@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
         else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         __syncwarp();
         if (valid) {
-            __stcs(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
-            __stcs(p.t_player + rowi, (int)((e.x >> 27) & 1u));
+            st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
+            st_stream(p.t_player + rowi, (int)((e.x >> 27) & 1u));
             const uint32_t word = ch.begin_step(h.k);
             const uint32_t cnt = (uint32_t)__popc(legal);
             const uint32_t kth = __umulhi(word, cnt);        // uniform over the legal ids, ascending
             ch.seed_chain(word, cnt);
-            __stcs(p.t_action + rowi, (int)byte_of(e.z, kth));
+            st_stream(p.t_action + rowi, (int)byte_of(e.z, kth));
             sid = byte_of(e.y, kth);
             e = stab[sid];
             h.t++; h.k++;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
                 h.episode++; h.t = 0;
             }
             p.t_done[rowi] = over ? 1 : 0;
-            __stcs(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+            st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
         }
     }
     if (valid) {
