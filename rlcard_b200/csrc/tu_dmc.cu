@@ -26,10 +26,20 @@ struct DmcParams {
     int32_t *out_count; int cap; int32_t *overflow;
 };
 
-// warp copy of one obs row (obs_stride bytes, a multiple of 4)
+// warp copy of one obs row (obs_stride bytes, a multiple of 4): 128-bit chunks in batches of four per lane, every load
+// of a batch in flight before the first store (a row is read once from the trajectory and written once to a pool)
 __device__ __forceinline__ void copy_row(uint8_t *dst, const uint8_t *src, int nbytes, int lane) {
     if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 15u) == 0) {
-        for (int c = lane; c < (nbytes >> 4); c += 32) reinterpret_cast<uint4 *>(dst)[c] = reinterpret_cast<const uint4 *>(src)[c];
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        const int nchunks = nbytes >> 4;
+        for (int c0 = 0; c0 < nchunks; c0 += 128) {
+            uint4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int c = c0 + 32 * q + lane; if (c < nchunks) v[q] = __ldcs(s4 + c); }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int c = c0 + 32 * q + lane; if (c < nchunks) __stcs(d4 + c, v[q]); }
+        }
     } else {
         for (int c = lane; c < nbytes; c += 32) dst[c] = src[c];
     }
@@ -83,11 +93,21 @@ __global__ void __launch_bounds__(128) k_dmc_collect(const DmcParams q) {
             if (lane == 0 && cnt[p] > 0) b = atomicAdd(q.out_count + p, cnt[p]);
             base[p] = __shfl_sync(0xffffffffu, b, 0);
         }
+        int pl_next = 0, act_next = 0;                        // (player, action) of row r + 1 load while row r is copied
+        if (total > 0) {
+            const size_t w0 = (size_t)(t_start - len0) * q.n + env;
+            pl_next = len0 > 0 ? (int)opl[0] : q.t_player[w0];
+            act_next = len0 > 0 ? oact[0] : q.t_action[w0];
+        }
         for (int r = 0; r < total; r++) {                     // emit in episode order
             const bool from_open = r < len0;
             const size_t wrow = (size_t)(t_start + r - len0) * q.n + env;
-            const int pl = from_open ? (int)opl[r] : q.t_player[wrow];
-            const int act = from_open ? oact[r] : q.t_action[wrow];
+            const int pl = pl_next, act = act_next;
+            if (r + 1 < total) {
+                const size_t wn = (size_t)(t_start + r + 1 - len0) * q.n + env;
+                pl_next = r + 1 < len0 ? (int)opl[r + 1] : q.t_player[wn];
+                act_next = r + 1 < len0 ? oact[r + 1] : q.t_action[wn];
+            }
             int b = 0, c = 0, s = 0; float py = 0.f;
 #pragma unroll
             for (int p = 0; p < RLC_MAX_PLAYERS; p++) if (pl == p) { b = base[p]; c = cnt[p]; s = seen[p]; py = pay[p]; seen[p]++; }
