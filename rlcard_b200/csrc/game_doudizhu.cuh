@@ -65,6 +65,7 @@ struct Doudizhu {
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for
     static constexpr int kScratchBytes = 64 + 4 * 864 + 128;   // reset: 54-card deck | legal(): list of non-empty mask words | encode_obs: 16 count words
     static constexpr int kObsScratch = 64 + 4 * 864;
+    static constexpr bool kRowFlushFull = false;  // the batched flush spills at the 72-register cap (measured 2 % slower)
     int n_legal, n_live; bool has_pass;                  // summary of the last legal() (warp-uniform)
     DdzTables tab;
     uint64_t hand[3], played[3];

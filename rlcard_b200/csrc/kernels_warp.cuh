@@ -68,7 +68,11 @@ __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const u
 template <class G, class ObsT>
 __device__ __forceinline__ void warp_flush_row(void *gobs, size_t row, ObsT *srow, int lane) {
     constexpr int kBytes = G::OBS * (int)sizeof(ObsT);
-    warp_tile_flush(reinterpret_cast<uint8_t *>(gobs) + row * (size_t)kBytes, reinterpret_cast<uint8_t *>(srow), kBytes, lane);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(gobs) + row * (size_t)kBytes;
+    if constexpr (G::kRowFlushFull && kBytes % 16 == 0) {      // compile-time batched flush (costs registers: per game)
+        if ((reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) { warp_tile_flush_full<kBytes>(dst, reinterpret_cast<uint8_t *>(srow), lane); return; }
+    }
+    warp_tile_flush(dst, reinterpret_cast<uint8_t *>(srow), kBytes, lane);
 }
 
 template <class G, class Ch, class ObsT, int MODE, int BLOCK>
