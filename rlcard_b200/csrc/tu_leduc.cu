@@ -2,6 +2,7 @@
 #include "game_poker.cuh"
 #include "kernels.cuh"
 #include <mutex>
+#include <type_traits>
 namespace rlc {
 
 // ==========================================================================================
@@ -179,19 +180,25 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
     const size_t obs_step = p.n * (size_t)kRowBytes;
     const bool full_warp = nvalid == 32;
     size_t rowi = i;
+    // the step loop is instantiated twice (full warp: compile-time tile flush without a branch, so that the flush and the
+    // transition form one straight-line region the scheduler can interleave; ragged last warp: generic flush)
+    auto run = [&](auto full_c) {
+    constexpr bool kFull = decltype(full_c)::value;
+    const bool live = kFull || valid;                      // a full warp has no idle lane: no branch around the step
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         const uint32_t legal = e.x & 15u;
-        if (valid) {                       // envs/leducholdem.py:41-71, positions tabulated from Leduc::encode_obs
+        if (live) {                        // envs/leducholdem.py:41-71, positions tabulated from Leduc::encode_obs
             row[(cards >> byte_of(e.w, 2)) & 3u] = (ObsT)1;
             if (e.w >> 24) row[3 + ((cards >> 4) & 3u)] = (ObsT)1;
             row[byte_of(e.w, 0)] = (ObsT)1;
             row[byte_of(e.w, 1)] = (ObsT)1;
         }
         __syncwarp();
-        if (full_warp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+        if constexpr (kFull) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
         else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
-        __syncwarp();
-        if (valid) {
+        // no barrier here: the transition below does not touch the tile, so its table look-ups overlap the flush; the
+        // barrier that orders the flush's zeroing before the next row is written sits at the end of the step
+        if (live) {
             st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
             st_stream(p.t_player + rowi, (int)((e.x >> 27) & 1u));
             const uint32_t word = ch.begin_step(h.k);
@@ -215,7 +222,10 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
             p.t_done[rowi] = over ? 1 : 0;
             st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
         }
+        __syncwarp();
     }
+    };
+    if (full_warp) run(std::true_type{}); else run(std::false_type{});
     if (valid) {
         h.store(p.state, p.n, i);
         const uint32_t rc = (e.x >> 28) & 3u;
