@@ -130,7 +130,9 @@ int rlc_observe(int game_id, const rlc_buffers *b, const int32_t *seat, int n, v
 
 /* The Env.run loop with RandomAgents (env.py:120-169, agents/random_agent.py:17-27) fused on
  * device: k_steps env-steps per env, uniform-random legal actions from the Philox policy stream,
- * auto reset.  Trajectory rows as documented above. */
+ * auto reset.  Trajectory rows as documented above.  Results depend only on (seed, global env id, step
+ * index), never on the launch geometry: the thread-per-env games run 32 / 16 / 8 envs per warp depending
+ * on the game and n (environment variable RLC_ROLLOUT_EPW forces one, for tuning and tests). */
 int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *traj, int n, int k_steps,
                        void *stream);
 
