@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     constexpr bool kStageMask = G::A > 4;
     constexpr int kMaskTile = kStageMask ? ((EPW * G::A + 15) & ~15) : 0;
     uint8_t *mtile = reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes + ((G::kSharedBytes + 15) & ~15) + wib * kMaskTile;
+    if constexpr (kStageMask) { warp_tile_zero(mtile, kMaskTile, lane); __syncwarp(); }   // rows OR their edge words into the tile
     constexpr bool kWarpDeal = G::kWarpDeal && Ch::kKind == 0;   // episodes are dealt by the whole warp (UNO, throughput mode)
     bool starts = false;                                         // this lane's env begins an episode at this point
     if (valid) {
@@ -251,9 +252,28 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             g.legal(m);
             if constexpr (kStageMask) {
                 if (ALL || p.t_mask) {
-                    uint8_t *mr = mtile + lane * G::A;
+                    if constexpr (G::MASK_WORDS == 2 && G::A <= 61 && (EPW * G::A) % 4 == 0) {
+                        // 4 mask bits -> 4 bytes per 32-bit store instead of one byte store per action: the row starts at byte
+                        // lane * A, o = (lane * A) & 3 bytes past a word boundary, so the bits are shifted up by o and expanded
+                        // on the word grid; the first and the last word are shared with the neighbouring rows and OR-ed in
+                        // (the tile is zero between steps), the words in between are this lane's alone
+                        const int o = (lane * G::A) & 3;
+                        const uint64_t mm = ((uint64_t)m[0] | ((uint64_t)m[1] << 32)) << o;
+                        const uint32_t lo = (uint32_t)mm, hi = (uint32_t)(mm >> 32);
+                        uint32_t *w = reinterpret_cast<uint32_t *>(mtile + lane * G::A - o);
+                        constexpr int kW = (G::A + 3 + 3) / 4;
 #pragma unroll
-                    for (int a = 0; a < G::A; a++) mr[a] = (m[a >> 5] >> (a & 31)) & 1u;
+                        for (int j = 0; j < kW; j++) {
+                            const uint32_t nibble = ((j < 8 ? lo : hi) >> (4 * (j & 7))) & 15u;
+                            const uint32_t v = (nibble * 0x00204081u) & 0x01010101u;          // bit a -> byte a
+                            if (j == 0 || j == kW - 1) atomicOr(w + j, v);
+                            else w[j] = v;
+                        }
+                    } else {
+                        uint8_t *mr = mtile + lane * G::A;
+#pragma unroll
+                        for (int a = 0; a < G::A; a++) mr[a] = (m[a >> 5] >> (a & 31)) & 1u;
+                    }
                 }
             }
         }
