@@ -242,6 +242,27 @@ def test_full_size_properties(game):
         assert torch.equal(tr[k][:, n // 2:], tr2[k]), k
 
 
+@pytest.mark.parametrize('game', GAMES)
+def test_rollout_does_not_depend_on_stale_shared_memory(game):
+    """Two identical rollouts with other kernels in between (which leave their own bytes in shared memory) must agree:
+    tiles that rows are OR-ed into are zeroed by the kernel itself, never assumed clean."""
+    n, T, seed = 4096, 32, 31337
+    a = rlcard_b200.VecEnv(game, n, seed=seed)
+    a.reset()
+    ta = a.rollout_random(T)
+    for other in GAMES:                                            # dirty every SM's shared memory with other layouts
+        if other != game:
+            o = rlcard_b200.VecEnv(other, 8192, seed=1)
+            o.reset()
+            o.rollout_random(4)
+    b = rlcard_b200.VecEnv(game, n, seed=seed)
+    b.reset()
+    tb = b.rollout_random(T)
+    for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+        assert torch.equal(ta[k], tb[k]), (game, k)
+    assert torch.equal(a.state, b.state)
+
+
 def test_illegal_action_fallback_and_noop():
     env = rlcard_b200.VecEnv('leduc-holdem', 64, seed=3, auto_reset=False)
     obs, mask, cur = env.reset()
