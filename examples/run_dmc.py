@@ -1,9 +1,12 @@
 """The data side of examples/run_dmc.py on the B200 simulator: actors with (random-init) DMC-style nets drive a
 VecEnv, rlc_dmc_collect fills the per-position pools, get_batch hands [T, B] batches to a learner step."""
 import argparse
+import os
+import sys
 
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere in the checkout
 import rlcard_b200
 from rlcard_b200.dmc import DMCCollector, DMCPolicy
 

@@ -1,12 +1,15 @@
 """examples/run_random.py of the reference on the B200 simulator: one seeded episode through the single-env
 facade (same trajectory as rlcard.make(env, {'seed': 42}) would deal), then the same loop for 65 536 envs at once."""
 import argparse
+import os
+import sys
 import pprint
 import time
 
 import numpy as np
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere in the checkout
 import rlcard_b200
 from rlcard_b200 import RandomAgent
 

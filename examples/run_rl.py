@@ -1,9 +1,12 @@
 """The data side of examples/run_rl.py on the B200 simulator: a Q-network plays seat 0 epsilon-greedily, the other seats
 play randomly, TransitionCollector yields (state, action, reward, next_state, next legal mask, done) for a DQN update."""
 import argparse
+import os
+import sys
 
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from anywhere in the checkout
 import rlcard_b200
 from rlcard_b200.rl import TransitionCollector
 
