@@ -79,7 +79,7 @@ struct Doudizhu {
         const uint32_t w = k < 2 ? tr[0] : (k < 4 ? tr[1] : (k < 6 ? tr[2] : (k < 8 ? tr[3] : tr[4])));
         return (w >> (16 * (k & 1))) & 0xffffu;
     }
-    __device__ __forceinline__ void bind(const KParams &p) {
+    __device__ __forceinline__ void bind(const KParams &p, uint8_t * = nullptr) {
         tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const ulonglong2 *>(p.tab[1]);
         tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
         tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);

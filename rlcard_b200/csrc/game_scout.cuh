@@ -26,24 +26,28 @@ __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * 
 struct Scout {
     static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
     static constexpr bool kMaskBitpacked = false;
-    static constexpr int kMinBlocks = 5;          // resident 128-thread blocks per SM the rollout kernel is compiled for
-    static constexpr int kScratchBytes = 48;
+    static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for (71 registers, no spills;
+                                                  // measured 5 / 6 / 7 / 8 blocks: 1.175 / 1.139 / 1.050 / 1.043 ms, 8 spills)
+    static constexpr int kScratchBytes = 48 + 64;   // reset: 45-card deck | the four hands (tops, bottoms)
     static constexpr bool kRowFlushFull = true;   // 2752-byte rows: batched compile-time flush (1.235 -> 1.212 ms)
-    uint64_t ht[4], hb[4], tt, tb;
+    uint64_t *hands;       // shared memory of the warp: [0..3] hand tops p0..p3, [4..7] hand bottoms.  Every lane writes the
+                           // same values (the state is replicated), so no barrier is needed around these accesses; keeping
+                           // them out of the registers drops the 64-bit four-way select chains and 16 registers per thread
+    uint64_t tt, tb;
     int hl[4], score[4], tl, owner, consec, cur, over_;
     bool forced;           // current_player_forced_scout: recomputed by every legal() (round.py:246)
 
-    __device__ __forceinline__ uint64_t sel(const uint64_t (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
+    __device__ __forceinline__ uint64_t top_of(int p) const { return hands[p]; }
+    __device__ __forceinline__ uint64_t bot_of(int p) const { return hands[4 + p]; }
     __device__ __forceinline__ int seli(const int (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
-    __device__ __forceinline__ void put(uint64_t (&a)[4], int p, uint64_t v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
     __device__ __forceinline__ void puti(int (&a)[4], int p, int v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
 
-    __device__ __forceinline__ void bind(const KParams &) {}
+    __device__ __forceinline__ void bind(const KParams &, uint8_t *scratch) { hands = reinterpret_cast<uint64_t *>(scratch + 48); }
     __device__ void load(const uint32_t *w, int lane) {
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            ht[p] = (uint64_t)w[2 * p] | ((uint64_t)w[2 * p + 1] << 32);
-            hb[p] = (uint64_t)w[8 + 2 * p] | ((uint64_t)w[9 + 2 * p] << 32);
+            hands[p] = (uint64_t)w[2 * p] | ((uint64_t)w[2 * p + 1] << 32);
+            hands[4 + p] = (uint64_t)w[8 + 2 * p] | ((uint64_t)w[9 + 2 * p] << 32);
         }
         tt = (uint64_t)w[16] | ((uint64_t)w[17] << 32); tb = (uint64_t)w[18] | ((uint64_t)w[19] << 32);
         const uint32_t m = w[20], s0 = w[21], s1 = w[22];
@@ -57,8 +61,8 @@ struct Scout {
         if (lane != 0) return;
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            w[2 * p] = (uint32_t)ht[p]; w[2 * p + 1] = (uint32_t)(ht[p] >> 32);
-            w[8 + 2 * p] = (uint32_t)hb[p]; w[9 + 2 * p] = (uint32_t)(hb[p] >> 32);
+            w[2 * p] = (uint32_t)hands[p]; w[2 * p + 1] = (uint32_t)(hands[p] >> 32);
+            w[8 + 2 * p] = (uint32_t)hands[4 + p]; w[9 + 2 * p] = (uint32_t)(hands[4 + p] >> 32);
         }
         w[16] = (uint32_t)tt; w[17] = (uint32_t)(tt >> 32); w[18] = (uint32_t)tb; w[19] = (uint32_t)(tb >> 32);
         w[20] = hl[0] | (hl[1] << 5) | (hl[2] << 10) | (hl[3] << 15) | (tl << 20) | (owner << 25) | (consec << 28) | ((uint32_t)cur << 30);
@@ -84,7 +88,7 @@ struct Scout {
     // range.  Lane s works out its range from three adjacency ballots and the five mask words are OR-reductions of the
     // lanes' ranges; the scout ids 136 + 4 ins + {front, front flipped, back, back flipped} are a closed-form pattern.
     __device__ void legal_words(uint32_t (&m)[7], int lane) {
-        const uint64_t T = sel(ht, cur);
+        const uint64_t T = top_of(cur);
         const int n = seli(hl, cur);
         int ttype = 0, trank = 0;
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
@@ -148,14 +152,15 @@ struct Scout {
                 if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
             }
         __syncwarp();
+        uint64_t nt[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int p = 0; p < 4; p++) { ht[p] = hb[p] = 0; hl[p] = 0; score[p] = 0; }
         for (int k = 0; k < 45; k++) {                   // deck.pop() = position 44-k -> player k%4, slot k/4
-            const int c = deck[44 - k], p = k & 3, slot = k >> 2;
-            put(ht, p, sel(ht, p) | ((uint64_t)(c >> 4) << (4 * slot)));
-            put(hb, p, sel(hb, p) | ((uint64_t)(c & 15) << (4 * slot)));
-            puti(hl, p, slot + 1);
+            const int c = deck[44 - k];
+            nt[k & 3] |= (uint64_t)(c >> 4) << (4 * (k >> 2));
+            nb[k & 3] |= (uint64_t)(c & 15) << (4 * (k >> 2));
         }
+#pragma unroll
+        for (int p = 0; p < 4; p++) { hands[p] = nt[p]; hands[4 + p] = nb[p]; hl[p] = p == 0 ? 12 : 11; score[p] = 0; }
         __syncwarp();
         tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
         cur = (int)ch.below(4u);
@@ -172,7 +177,7 @@ struct Scout {
         }
         const int p = cur;
         const bool was_forced = forced;
-        uint64_t T = sel(ht, p), B = sel(hb, p);
+        uint64_t T = top_of(p), B = bot_of(p);
         int n = seli(hl, p);
         if (id < 136) {
             int s = 0, k = id;
@@ -203,7 +208,9 @@ struct Scout {
             if (tl == 0) { owner = 4; consec = 0; }
             if (consec == 3 && owner < 4) over_ = 1;
         }
-        put(ht, p, T); put(hb, p, B); puti(hl, p, n);
+        __syncwarp();                                                       // every lane has read the old hand
+        hands[p] = T; hands[4 + p] = B; puti(hl, p, n);
+        __syncwarp();
         cur = (p + 1) & 3;
         legal_words(lm, lane);                                              // next player cannot move -> round ends
         lm_valid = true;
@@ -218,8 +225,8 @@ struct Scout {
         if (lane < 16) {
             const int s = lane;
             if (s < seli(hl, seat)) {
-                row[s * 10 + nib(sel(ht, seat), s) - 1] = (T)1;
-                row[160 + s * 10 + nib(sel(hb, seat), s) - 1] = (T)1;
+                row[s * 10 + nib(top_of(seat), s) - 1] = (T)1;
+                row[160 + s * 10 + nib(bot_of(seat), s) - 1] = (T)1;
                 row[640 + s] = (T)1;
             }
         } else {

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
     EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
-    G g; g.bind(p); g.load(row + kHeaderWords, lane);
+    G g; g.bind(p, scratch); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0; bool done = false;
     float pay[G::P];
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
     EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
-    G g; g.bind(p); g.load(row + kHeaderWords, lane);
+    G g; g.bind(p, scratch); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0;
     if (h.episode == 0) { ch.begin_reset(h.k); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
