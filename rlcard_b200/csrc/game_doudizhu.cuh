@@ -63,23 +63,25 @@ struct Doudizhu {
     static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 859;
     static constexpr bool kMaskBitpacked = true;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for
-    static constexpr int kScratchBytes = 64 + 4 * 864 + 128;   // reset: 54-card deck | legal(): list of non-empty mask words | encode_obs: 16 count words
+    static constexpr int kScratchBytes = 64 + 4 * 864 + 128 + 48;   // reset: 54-card deck | legal(): list of non-empty mask words | encode_obs: 16 count words | hands, played piles
     static constexpr int kObsScratch = 64 + 4 * 864;
     static constexpr bool kRowFlushFull = false;  // the batched flush spills at the 72-register cap (measured 2 % slower)
     int n_legal, n_live; bool has_pass;                  // summary of the last legal() (warp-uniform)
     DdzTables tab;
-    uint64_t hand[3], played[3];
+    uint64_t *hand, *played;   // [3] each, in the warp's shared memory: every lane writes the same values (replicated state),
+                               // dynamic seat index = one LDS instead of a 64-bit select chain, 12 registers fewer
     uint32_t tr[5];            // nine 16-bit action ids, entry k in tr[k/2] >> (16*(k&1)), k = 8 is the newest
     uint32_t last_by[3], greater_action;
     int greater, cur, winner;
 
-    __device__ __forceinline__ uint64_t sel3(const uint64_t (&a)[3], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : a[2]); }
-    __device__ __forceinline__ void put3(uint64_t (&a)[3], int p, uint64_t v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; }
+    __device__ __forceinline__ uint64_t sel3(const uint64_t *a, int p) const { return a[p]; }
+    __device__ __forceinline__ void put3(uint64_t *a, int p, uint64_t v) { a[p] = v; }
     __device__ __forceinline__ uint32_t trace_at(int k) const {
         const uint32_t w = k < 2 ? tr[0] : (k < 4 ? tr[1] : (k < 6 ? tr[2] : (k < 8 ? tr[3] : tr[4])));
         return (w >> (16 * (k & 1))) & 0xffffu;
     }
-    __device__ __forceinline__ void bind(const KParams &p, uint8_t * = nullptr) {
+    __device__ __forceinline__ void bind(const KParams &p, uint8_t *scratch) {
+        hand = reinterpret_cast<uint64_t *>(scratch + kObsScratch + 128); played = hand + 3;
         tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const ulonglong2 *>(p.tab[1]);
         tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
         tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);
@@ -121,11 +123,11 @@ struct Doudizhu {
             if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
         }
         __syncwarp();
-        hand[0] = hand[1] = hand[2] = 0; played[0] = played[1] = played[2] = 0;
-        for (int k = 0; k < 54; k++) {
-            const int p = k < 51 ? k / 17 : 0;
-            put3(hand, p, sel3(hand, p) + (1ull << (4 * deck[k])));
-        }
+        uint64_t nh[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 54; k++) nh[k < 51 ? k / 17 : 0] += 1ull << (4 * deck[k]);
+#pragma unroll
+        for (int q = 0; q < 3; q++) { hand[q] = nh[q]; played[q] = 0; }
         __syncwarp();
         const uint32_t pp = (uint32_t)kDdzPass | ((uint32_t)kDdzPass << 16);
         tr[0] = tr[1] = tr[2] = tr[3] = tr[4] = pp;
@@ -235,8 +237,11 @@ struct Doudizhu {
         const int p = cur;
         if (id != kDdzPass) {
             const uint64_t c = __ldg(tab.rows + (id));
-            put3(hand, p, sel3(hand, p) - c);
-            put3(played, p, sel3(played, p) + c);
+            const uint64_t nhand = sel3(hand, p) - c, nplayed = sel3(played, p) + c;
+            __syncwarp();                                                     // every lane has read the old piles
+            put3(hand, p, nhand);
+            put3(played, p, nplayed);
+            __syncwarp();
             greater = p; greater_action = (uint32_t)id;
         }
         tr[0] = (tr[0] >> 16) | (tr[1] << 16); tr[1] = (tr[1] >> 16) | (tr[2] << 16);

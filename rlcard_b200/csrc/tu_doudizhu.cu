@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) k_judge_doudizhu(const uint8_t *hands, co
     uint8_t *scratch = base + ((Doudizhu::MASK_WORDS * 4 + 15) & ~15);
     for (int w = lane; w < Doudizhu::MASK_WORDS; w += 32) smask[w] = 0;
     __syncwarp();
-    Doudizhu g; g.bind(p);
+    Doudizhu g; g.bind(p, scratch);
     uint64_t h = 0;
     for (int r = 0; r < 15; r++) h |= (uint64_t)(hands[(size_t)i * 15 + r] & 15) << (4 * r);
     g.hand[0] = h; g.hand[1] = g.hand[2] = 0; g.played[0] = g.played[1] = g.played[2] = 0;
