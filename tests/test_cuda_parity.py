@@ -243,6 +243,30 @@ def test_full_size_properties(game):
 
 
 @pytest.mark.parametrize('game', GAMES)
+def test_long_horizon_rollout_equals_oracle(game):
+    """1024 env-steps per env over four launches (hundreds of episodes per env for the short games, UNO reshuffles,
+    Philox step counters far past the first blocks): actions, players, dones and payoffs of every step and the obs /
+    mask rows of the last launch equal the CPU twin."""
+    n, T, launches, seed, base = 512, 256, 4, 20261018, 123457
+    env = rlcard_b200.VecEnv(game, n, seed=seed, env_id_base=base)
+    orc = oracle.OracleVec(game, n, seed, env0=base)
+    env.reset()
+    for launch in range(launches):
+        last = launch == launches - 1
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, want_obs=last, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs') + (('mask', 'obs') if last else ()):
+            got, want = to_np(tr[k]), ref[k]
+            if k == 'mask' and env.mask_bitpacked:
+                want = np.packbits(want, axis=-1, bitorder='little')
+                got = got.view(np.uint8)[..., :want.shape[-1]]
+            if k == 'obs':
+                got = got[..., :want.shape[-1]]
+            assert np.array_equal(got.astype(np.float64), want.astype(np.float64)), '%s launch %d %s' % (game, launch, k)
+    env.check_errors()
+
+
+@pytest.mark.parametrize('game', GAMES)
 def test_rollout_does_not_depend_on_stale_shared_memory(game):
     """Two identical rollouts with other kernels in between (which leave their own bytes in shared memory) must agree:
     tiles that rows are OR-ed into are zeroed by the kernel itself, never assumed clean."""
