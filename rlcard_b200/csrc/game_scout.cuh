@@ -4,7 +4,8 @@
 //
 // Hands and the table set are ordered lists of (top, bottom) cards with values 1..10, kept as two
 // 16-nibble words each (slot k = bits [4k, 4k+4)), so that slicing, inserting and the group/run tests
-// are a handful of 64-bit operations.  The whole state is replicated in every lane's registers; for the
+// are a handful of 64-bit operations.  The state is replicated across the lanes (hands in the warp's
+// shared memory, the rest in registers, see kernels_warp.cuh); for the
 // legal mask (round.py:225-260) lane s owns the plays that start at hand position s -- one contiguous id
 // range per start -- and the mask words are warp OR-reductions of those ranges.
 //
