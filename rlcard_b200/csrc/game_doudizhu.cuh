@@ -299,12 +299,13 @@ struct Doudizhu {
                 uint8_t *dst = reinterpret_cast<uint8_t *>(row) + 54 * (lane >> 4) + 4 * r;
                 const uint32_t *half = reinterpret_cast<const uint32_t *>(cw) + 2 * (lane >> 4) + (r >> 3);   // the word holding rank r
                 const int sh = 4 * (r & 7);
+                const uint32_t joker_bit = r == 13 ? 0x100u : 0u;      // r = 13 writes the two joker bytes (B in the low byte, R above)
 #pragma unroll
                 for (int b = lane >> 4; b < 16; b += 2, dst += 108, half += 4) {
-                    if (b < nb) {
+                    if (b < nb) {                                       // branch free inside: every lane of the half-warp stores
                         const uint32_t w = *half, k = (w >> sh) & 15u;                                 // 0..4 copies of rank r
-                        uint32_t v = k ? 0x01010101u >> (32u - 8u * k) : 0u;                            // thermometer bytes
-                        if (r == 13) v = (k ? 1u : 0u) | (((w >> 24) & 15u) ? 0x100u : 0u);             // the two joker bytes
+                        uint32_t v = __funnelshift_lc(0x01010101u, 0u, 8u * k);                         // k thermometer bytes
+                        v |= (w >> 16) & joker_bit;                                                     // red joker: nibble 14 -> byte 1
                         *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
                         if (r < 13) *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(v >> 16);
                     }
