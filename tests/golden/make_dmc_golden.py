@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 from make_golden import REF, TapeRecorder, import_reference  # noqa: E402
 
-GAMES = {'doudizhu': (12, 3), 'leduc-holdem': (10, 4), 'uno': (16, 3), 'limit-holdem': (8, 3)}   # game: (T, K buffers per position)
+GAMES = {'doudizhu': (12, 3), 'leduc-holdem': (10, 4), 'uno': (16, 3), 'limit-holdem': (8, 3), 'scout': (16, 3)}   # game: (T, K buffers per position)
 
 
 class StopActor(KeyboardInterrupt):

@@ -6,7 +6,8 @@ import torch
 
 import oracle
 import rlcard_b200
-from replay_util import ALL_FIXTURES, ALL_GAMES, check_slot, fixture_game, have_fixture, load_fixture, slot_records, slot_tape
+from replay_util import (ALL_FIXTURES, ALL_GAMES, DEEP_GAMES, check_record_deep, check_slot, deep_slot_records, fixture_game,
+                         have_fixture, load_deep, load_fixture, slot_records, slot_tape)
 
 pytestmark = pytest.mark.gpu
 
@@ -93,6 +94,79 @@ def test_replay_reference_tapes_vectorised(game, obs_dtype, chance):
         pos = to_np(env.tape_pos)
         for s in range(S):
             assert pos[s] == len(slot_tape(fx, s))      # and consumed exactly
+
+
+@pytest.mark.parametrize('chance', ['replay', 'mt19937'])
+@pytest.mark.parametrize('game', [g for g in DEEP_GAMES if built(g)])
+def test_replay_deep_reference_fixture(game, chance):
+    """The deep fixtures (tests/golden/deep_<game>.npz: >= 11 000 reference episodes for the short games, 1 000+ UNO,
+    500+ DouDizhu / Scout, stratified and crafted slots) replayed on the device, all slots side by side in lock step;
+    obs rows and legal sets are compared through their digests, players / done / payoffs directly.  'replay' runs
+    EVERY slot from its recorded draws; 'mt19937' every 4th seeded slot from the seed alone."""
+    fx = load_deep(game)
+    slots = list(range(len(fx['slot_seed'])))
+    if chance == 'mt19937':
+        slots = [s for s in slots[::4] if fx['slot_seed'][s] >= 0]
+    S = len(slots)
+    recs = [deep_slot_records(fx, s) for s in slots]
+    tapes = [fx['tape'][fx['tape_off'][s]:fx['tape_off'][s + 1]] for s in slots]
+    odt = torch.float32 if rlcard_b200.game_info(game).obs_native_dtype == 1 else torch.uint8
+    env = rlcard_b200.VecEnv(game, S, mode=chance, obs_dtype=odt, auto_reset=False)
+    if chance == 'replay':
+        tape = np.zeros((S, max(len(t) for t in tapes) + 8), np.uint8)
+        for i, t in enumerate(tapes):
+            tape[i, :len(t)] = t
+        env.set_tape(tape)
+    else:
+        env.seed_mt19937([int(fx['slot_seed'][s]) for s in slots])
+    kind_all, arg_all = fx['rec_kind'], fx['rec_arg']
+    checked = 0
+    for tick in range(max(len(r) for r in recs)):
+        live = [i for i in range(S) if tick < len(recs[i])]
+        kinds = {i: int(kind_all[recs[i][tick]]) for i in live}
+        for kind in (0, 1, 2, 3):
+            group = [i for i in live if kinds[i] == kind]
+            if not group:
+                continue
+            if kind == 0:
+                m = torch.zeros(S, dtype=torch.uint8); m[group] = 1
+                env.reset(m.cuda())
+            elif kind == 1:
+                a = torch.full((S,), -1, dtype=torch.int32)
+                a[group] = torch.tensor([int(arg_all[recs[i][tick]]) for i in group], dtype=torch.int32)
+                env.step(a.cuda())
+            elif kind == 2:
+                seat = torch.zeros(S, dtype=torch.int32)
+                seat[group] = torch.tensor([int(arg_all[recs[i][tick]]) for i in group], dtype=torch.int32)
+                env.get_state(seat.cuda())
+            else:
+                env.get_state(None)
+            cur, done, pay = (to_np(x) for x in (env.cur_player, env.done, env.payoffs))
+            if kind != 3:
+                obs, mask = to_np(env.obs), to_np(env.mask)
+                if env.mask_bitpacked:
+                    mask = np.unpackbits(mask[group].view(np.uint8), axis=1, bitorder='little')[:, :env.num_actions]
+                else:
+                    mask = mask[group]
+            for gi, i in enumerate(group):
+                r = recs[i][tick]
+                tag = '%s deep slot %d rec %d kind %d' % (game, slots[i], r, kind)
+                if kind == 3:
+                    np.testing.assert_array_equal(pay[i].astype(np.float64), fx['rec_payoffs'][r], err_msg=tag)
+                else:
+                    check_record_deep(fx, r, obs[i], mask[gi], tag)
+                assert cur[i] == fx['rec_player'][r], tag
+                assert bool(done[i]) == bool(fx['rec_done'][r]), tag
+                checked += 1
+    assert checked == sum(len(r) for r in recs)
+    err = to_np(env.err)
+    assert not (err & 3).any()
+    if chance == 'replay':
+        pos = to_np(env.tape_pos)
+        for i in range(S):
+            assert pos[i] == len(tapes[i])
+    print('%s deep fixture on the device (%s): %d slots, %d episodes, %d records' % (
+        game, chance, S, int(fx['slot_episodes'][slots].sum()), checked))
 
 
 class FacadeAdapter:
@@ -240,6 +314,33 @@ def test_full_size_properties(game):
     tr2 = env2.rollout_random(T)
     for k in ('obs', 'mask', 'action', 'done', 'payoffs'):
         assert torch.equal(tr[k][:, n // 2:], tr2[k]), k
+
+
+@pytest.mark.parametrize('game', GAMES)
+def test_full_size_rollout_equals_oracle(game):
+    """BASELINE.json's sizes (65 536 / 16 384 / 8 192 envs per GPU), T = 16: every trajectory tensor of the fused
+    rollout equals the CPU twin, after a first launch that scatters the envs over their episodes."""
+    n = {'leduc-holdem': 65536, 'limit-holdem': 16384, 'uno': 16384, 'blackjack': 65536, 'no-limit-holdem': 16384}.get(game, 8192)
+    T, seed = (8 if game == 'doudizhu' else 16), 20261019         # DouDizhu: the oracle's dense mask is 27 472 bytes per row
+    env = rlcard_b200.VecEnv(game, n, seed=seed)
+    orc = oracle.OracleVec(game, n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=16)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            got, want = to_np(tr[k]), ref[k]
+            if k == 'mask' and env.mask_bitpacked:
+                want = np.packbits(want, axis=-1, bitorder='little')
+                got = got.view(np.uint8)[..., :want.shape[-1]]
+            if k == 'obs':
+                assert not got[..., want.shape[-1]:].any()
+                got = got[..., :want.shape[-1]]
+            assert np.array_equal(got, want.astype(got.dtype)) and np.array_equal(want.astype(got.dtype).astype(want.dtype), want), \
+                '%s full size launch %d %s' % (game, launch, k)
+        del tr, ref
+    env.check_errors()
+    print('%s: %d envs x %d steps x 2 launches == oracle' % (game, n, T))
 
 
 @pytest.mark.parametrize('game', GAMES)

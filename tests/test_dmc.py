@@ -9,7 +9,7 @@ import oracle
 from dmc_util import feature_fn, fold_trajectory
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-GAMES = ['doudizhu', 'leduc-holdem', 'uno', 'limit-holdem']
+GAMES = ['doudizhu', 'leduc-holdem', 'uno', 'limit-holdem', 'scout']
 
 
 def load(game):

@@ -83,3 +83,37 @@ def test_doudizhu_type_prefilter_is_sound():
             want |= 1 << int(types[i])
         assert int(need[j, 1]) == want
     assert int(need[864 + 26, 1]) & (1 << dt.T_PASS) and not int(need[864, 1]) & (1 << dt.T_PASS)
+
+
+# ---- deep fixtures: >= 1e4 / 1e3 / 500 reference episodes per game + stratified / crafted slots -------------------
+from replay_util import DEEP_GAMES, check_slot_deep, load_deep  # noqa: E402
+
+
+@pytest.mark.parametrize('game', DEEP_GAMES)
+def test_oracle_replays_deep_reference_fixture(game):
+    fx = load_deep(game)
+    total = 0
+    for slot in range(len(fx['slot_seed'])):
+        env = oracle.OracleEnv(game)
+        tape = fx['tape'][fx['tape_off'][slot]:fx['tape_off'][slot + 1]]
+        env.set_tape(tape)
+        total += check_slot_deep(fx, slot, env, game + ' (deep)')
+        assert env.tape_err() == 0
+        assert env.tape_pos() == len(tape)
+    assert total == len(fx['rec_kind'])
+    print('%s deep fixture: %d slots, %d episodes, %d records (%d env-steps) replayed bit-exact' % (
+        game, len(fx['slot_seed']), int(fx['slot_episodes'].sum()), total, int((fx['rec_kind'] == 1).sum())))
+
+
+@pytest.mark.parametrize('game', DEEP_GAMES)
+def test_oracle_mt19937_regenerates_deep_tapes(game):
+    """every 5th seeded slot: the draws made from the seed alone equal the recorded tape"""
+    fx = load_deep(game)
+    for slot in range(0, len(fx['slot_seed']), 5):
+        if fx['slot_seed'][slot] < 0:
+            continue
+        env = oracle.OracleEnv(game)
+        env.seed(int(fx['slot_seed'][slot]))
+        env.record()
+        check_slot_deep(fx, slot, env, game + ' (deep, mt)')
+        np.testing.assert_array_equal(env.recorded(), fx['tape'][fx['tape_off'][slot]:fx['tape_off'][slot + 1]])
