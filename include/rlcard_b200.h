@@ -11,7 +11,10 @@
  * as void*; NULL = legacy default stream).
  *
  * Layouts (n = number of envs of this call, P players, A actions):
- *   state     uint32 [state_words][n]   struct-of-arrays, opaque (rlc_game_info.state_words)
+ *   state     opaque packed env state, rlc_game_info.state_words uint32 words per env.  Its layout depends on
+ *             rlc_info.threads_per_env: 1 (thread-per-env games) -> struct-of-arrays uint32 [state_words][n];
+ *             32 (warp-per-env games: DouDizhu, Scout) -> one row per env, uint32 [n][state_words].
+ *             rlc_info.state_layout says which (RLC_STATE_SOA / RLC_STATE_ROWS); slice or shard it accordingly.
  *   obs       obs_t  [n][obs_stride]    row = the reference's exact obs layout of the seat's
  *                                       _extract_state, zero padded to obs_stride (max seat dim)
  *   mask      uint8  [n][A]             1 = legal (games with A <= 256)
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RLC_ABI_VERSION 1
+#define RLC_ABI_VERSION 2
 #define RLC_MAX_PLAYERS 4
 
 /* env ids of rlcard/envs/__init__.py:6-54 covered by this library */
@@ -55,6 +58,7 @@ enum rlc_chance {
 };
 
 enum rlc_dtype { RLC_U8 = 0, RLC_F32 = 1 };
+enum rlc_state_layout { RLC_STATE_SOA = 0, RLC_STATE_ROWS = 1 };
 
 enum rlc_step_flags {
     RLC_AUTO_RESET = 1,      /* deal the next episode inside the step that ends one          */
@@ -71,11 +75,12 @@ typedef struct rlc_info {
     int32_t state_words;                /* uint32 words per env                               */
     int32_t max_tape_draws_reset;       /* draws a reset can consume (tape sizing aid)        */
     int32_t threads_per_env;            /* 1 (thread per env) or 32 (warp per env)            */
-    int32_t reserved[4];
+    int32_t state_layout;               /* RLC_STATE_SOA [state_words][n] or RLC_STATE_ROWS [n][state_words] */
+    int32_t reserved[3];
 } rlc_info;
 
 typedef struct rlc_buffers {
-    uint32_t *state;          /* [state_words][n]                                             */
+    uint32_t *state;          /* [state_words][n] or [n][state_words], see rlc_info.state_layout */
     /* chance source */
     int32_t chance;           /* rlc_chance                                                   */
     uint64_t seed;            /* PHILOX key                                                   */
@@ -93,7 +98,8 @@ typedef struct rlc_buffers {
     float *payoffs;           /* [n][P]                                                       */
     void *terminal_obs;       /* [n][P][obs_stride], written for done envs when RLC_TERMINAL_OBS */
     int32_t *err;             /* [n] sticky bit flags: 1 tape exhausted, 2 tape value out of range,
-                                 4 illegal action replaced by the reference's fallback         */
+                                 4 illegal action replaced by the reference's fallback,
+                                 8 terminal-state pool of the fused rollout was full            */
 } rlc_buffers;
 
 /* trajectory buffers of rlc_rollout_random: [T][n][...], any pointer may be NULL */
@@ -104,6 +110,22 @@ typedef struct rlc_trajectory {
     int32_t *player;          /* [T][n] acting player                                         */
     uint8_t *done;            /* [T][n] episode ended with this action                        */
     float *payoffs;           /* [T][n][P] payoffs when done else 0                           */
+    /* ---- ABI 2 (all optional, NULL / 0 = off) ----
+     * forced_actions: replay of recorded action sequences through the fused loop (the action half of the replay
+     * mode: pair it with RLC_CHANCE_TAPE / RLC_CHANCE_MT19937 for the chance half).  Cell [t][i] is applied with
+     * Env.step semantics (illegal ids take the env's fallback and raise err flag 4); a negative id leaves env i
+     * untouched for that cell (its row is still written, action = the negative id, done = 0).
+     * terminal_*: Env.run appends get_state(p) of EVERY seat after the last step of an episode (env.py:161-164).
+     * The fused loop writes those per-seat terminal views into a pool, one row group per finished episode, and
+     * terminal_row[t][i] = pool row of the episode that ended in cell [t][i] (-1: no episode ended there).  Rows are
+     * handed out with atomicAdd on *terminal_count (in/out, device; zero it to recycle the pool); when the pool is
+     * full the row is -1 and err flag 8 is raised. */
+    const int32_t *forced_actions;   /* [T][n]                                                               */
+    void *terminal_obs;              /* [terminal_capacity][P][obs_stride], obs_dtype                        */
+    void *terminal_mask;             /* [terminal_capacity][A] or [terminal_capacity][mask_words]            */
+    int32_t *terminal_row;           /* [T][n]                                                               */
+    int32_t *terminal_count;         /* [1]                                                                  */
+    int32_t terminal_capacity;
 } rlc_trajectory;
 
 int rlc_abi_version(void);
@@ -213,6 +235,19 @@ typedef struct rlc_rl_buffers {
 
 int rlc_rl_feed(int game_id, int phase, const rlc_buffers *env, const int32_t *actions, int n, const rlc_rl_buffers *b,
                 void *stream);
+
+/* reorganize (rlcard/utils/utils.py:153-179) over a FUSED rollout window: traj = the [T][n] rows written by
+ * rlc_rollout_random with the terminal_* pool enabled (obs, mask, action, player, done, payoffs, terminal_obs,
+ * terminal_mask, terminal_row are all required).  Emits the same per-seat transition rows as rlc_rl_feed into the same
+ * rlc_rl_buffers; decisions whose next state lies in a later window wait in pend_* (so consecutive windows of one
+ * VecEnv chain exactly).  Cells with a negative action id (idle envs of a forced-action replay) are skipped. */
+int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_rl_buffers *b,
+                   void *stream);
+
+/* np.random.RandomState seeding on device (rlcard/utils/seeding.py:33-41 -> RandomState.seed(list) = MT19937
+ * init_by_array): key_words uint32 [n][2] (the 1-2 words of sha512(str(seed))[:8], computed by the caller),
+ * key_len int32 [n] -> mt uint32 [625][n] in the layout of rlc_buffers.mt (624 state words + index). */
+int rlc_seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt, void *stream);
 
 /* number of kernels this library has launched in this process (bench bookkeeping) */
 int64_t rlc_launch_count(void);

@@ -15,6 +15,8 @@ GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'dou
 CHANCE_PHILOX, CHANCE_TAPE, CHANCE_MT19937 = 0, 1, 2
 DTYPE_U8, DTYPE_F32 = 0, 1
 AUTO_RESET, TERMINAL_OBS = 1, 2
+STATE_SOA, STATE_ROWS = 0, 1
+ABI_VERSION = 2
 
 
 class RlcInfo(C.Structure):
@@ -22,7 +24,7 @@ class RlcInfo(C.Structure):
                 ('obs_dim', C.c_int32 * RLC_MAX_PLAYERS), ('obs_stride', C.c_int32),
                 ('obs_native_dtype', C.c_int32), ('mask_bitpacked', C.c_int32), ('mask_words', C.c_int32),
                 ('state_words', C.c_int32), ('max_tape_draws_reset', C.c_int32), ('threads_per_env', C.c_int32),
-                ('reserved', C.c_int32 * 4)]
+                ('state_layout', C.c_int32), ('reserved', C.c_int32 * 3)]
 
 
 class RlcBuffers(C.Structure):
@@ -34,7 +36,9 @@ class RlcBuffers(C.Structure):
 
 class RlcTrajectory(C.Structure):
     _fields_ = [('obs', C.c_void_p), ('mask', C.c_void_p), ('action', C.c_void_p), ('player', C.c_void_p),
-                ('done', C.c_void_p), ('payoffs', C.c_void_p)]
+                ('done', C.c_void_p), ('payoffs', C.c_void_p),
+                ('forced_actions', C.c_void_p), ('terminal_obs', C.c_void_p), ('terminal_mask', C.c_void_p),
+                ('terminal_row', C.c_void_p), ('terminal_count', C.c_void_p), ('terminal_capacity', C.c_int32)]
 
 
 class RlcDmcBuffers(C.Structure):
@@ -56,7 +60,8 @@ class RlcRlBuffers(C.Structure):
 
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
            'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
-           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed', 'rlc_legal_ids', 'rlc_action_features']
+           'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed', 'rlc_legal_ids', 'rlc_action_features',
+           'rlc_reorganize', 'rlc_seed_mt19937']
 
 _LIB = None
 
@@ -91,6 +96,11 @@ def lib():
         L.rlc_action_features.argtypes = [i32, vp, i32, vp, vp]
         L.rlc_rl_feed.argtypes = [i32, i32, C.POINTER(RlcBuffers), vp, i32, C.POINTER(RlcRlBuffers), vp]
         L.rlc_dmc_collect.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcDmcBuffers), vp]
+        L.rlc_reorganize.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcRlBuffers), vp]
+        L.rlc_seed_mt19937.argtypes = [vp, vp, i32, vp, vp]
+        if L.rlc_abi_version() != ABI_VERSION:
+            raise RlcError('%s has ABI %d, the Python side expects %d: rebuild (__graft_entry__.build())'
+                           % (SO_PATH, L.rlc_abi_version(), ABI_VERSION))
         _LIB = L
     return _LIB
 

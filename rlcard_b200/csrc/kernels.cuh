@@ -17,10 +17,15 @@ struct KParams {
     void *obs; void *mask; int32_t *cur_player; uint8_t *done; float *payoffs; void *terminal_obs; int32_t *err;
     const int32_t *actions; const uint8_t *reset_mask; const int32_t *seat; int flags;
     void *t_obs; void *t_mask; int32_t *t_action; int32_t *t_player; uint8_t *t_done; float *t_payoffs; int T;
+    // fused-rollout extensions (rlc_trajectory, ABI 2): recorded action ids to apply instead of the random policy, and the
+    // pool of per-seat terminal states (env.py:161-164) with the row index per trajectory cell
+    const int32_t *t_forced; void *tm_obs; void *tm_mask; int32_t *tm_row; int32_t *tm_count; int tm_cap;
     const void *tables; const void *tab[5];      // per-game constant tables (device pointers), see Game::bind
 };
 
 enum { kModeReset = 0, kModeStep = 1, kModeObserve = 2 };
+enum { kFlagNoFsm = 0x100 };         // internal launch flag: extensions present -> generic kernels only
+enum { kErrTerminalPoolFull = 8 };
 
 // ---- chance source plumbing -------------------------------------------------------------
 template <class Ch> struct ChanceIO;
@@ -301,16 +306,50 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             if constexpr (Ch::kKind == 0) word = ch.begin_step(h.k);
             else word = policy_word_only(p, i, h.k);
             int cnt;
-            const int a = pick_action<G>(m, word, cnt);
+            int a = pick_action<G>(m, word, cnt);
             if constexpr (G::kUsesChain) ch.seed_chain(word, (uint32_t)cnt);
+            bool idle = false;
+            if constexpr (!ALL) {
+                if (p.t_forced) { a = p.t_forced[rowi]; idle = a < 0; }   // replay of a recorded action sequence
+            }
             if (ALL || p.t_action) st_stream(p.t_action + rowi, a);
-            if constexpr (G::kHasApply) g.apply(a, ch, err);          // a was picked from the legal set: no re-validation
-            else g.step(a, ch, err);
-            h.t++; h.k++;
-            const bool over = g.over();
+            bool over = false;
             float pay[G::P];
 #pragma unroll
             for (int q = 0; q < G::P; q++) pay[q] = 0.f;
+            if (!idle) {
+                if constexpr (G::kHasApply) {
+                    if (ALL || !p.t_forced) g.apply(a, ch, err);      // a was picked from the legal set: no re-validation
+                    else g.step(a, ch, err);
+                } else g.step(a, ch, err);
+                h.t++; h.k++;
+                over = g.over();
+            }
+            if constexpr (!ALL) {
+                if (p.tm_row) {                                       // per-seat terminal states into the pool
+                    int r = -1;
+                    if (over) {
+                        r = atomicAdd(p.tm_count, 1);
+                        if (r >= p.tm_cap) { r = -1; err |= kErrTerminalPoolFull; }
+                    }
+                    p.tm_row[rowi] = r;
+                    if (r >= 0) {
+                        if (p.tm_obs) {                               // this lane's tile row is zero here (flushed above)
+                            ObsT *dst = reinterpret_cast<ObsT *>(p.tm_obs) + (size_t)r * (G::P * G::OBS);
+                            for (int s = 0; s < G::P; s++) {
+                                g.encode_obs(s, false, row);
+                                for (int q = 0; q < G::OBS; q++) { dst[s * G::OBS + q] = row[q]; row[q] = (ObsT)0; }
+                            }
+                        }
+                        if (p.tm_mask) {
+                            uint32_t mt[G::MASK_WORDS];
+                            g.legal(mt);
+                            uint8_t *dm = reinterpret_cast<uint8_t *>(p.tm_mask) + (size_t)r * G::A;
+                            for (int q = 0; q < G::A; q++) dm[q] = (mt[q >> 5] >> (q & 31)) & 1u;
+                        }
+                    }
+                }
+            }
             if (over) {
                 g.payoffs(pay);
                 if constexpr (kWarpDeal) { h.episode++; h.t = 0; starts = true; }
@@ -371,7 +410,8 @@ cudaError_t launch_rollout(const KParams &p, cudaStream_t stream) {
                         (G::A > 4 ? (size_t)kWarps * ((EPW * G::A + 15) & ~15) : 0);
     // fast path: every trajectory stream requested and the obs (and staged mask) rows of a full warp 16-byte aligned
     constexpr bool kTilesAligned = (EPW * kRowBytes) % 16 == 0 && (G::A <= 4 || (EPW * G::A) % 16 == 0);
-    const bool all = kTilesAligned && p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
+    const bool all = kTilesAligned && !p.t_forced && !p.tm_row &&
+                     p.t_obs && p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs &&
                      ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * (size_t)kRowBytes)) & 15u) == 0 &&
                      (G::A <= 4 || ((reinterpret_cast<uintptr_t>(p.t_mask) | (p.n * (size_t)G::A)) & 15u) == 0);
     cudaError_t e = cudaSuccess;

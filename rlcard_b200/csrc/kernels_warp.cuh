@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
     if (err && p.err && lane == 0) p.err[env] |= err;
 }
 
-template <class G, class Ch, class ObsT, int BLOCK>
+// EXT = the rlc_trajectory extensions are in use (recorded actions instead of the random policy, terminal-state pool);
+// the plain instantiation is the throughput kernel and carries none of that code.
+template <class G, class Ch, class ObsT, int BLOCK, bool EXT>
 __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -195,18 +197,47 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
         if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
-        const int a = g.pick(smask, scratch, k, lane);
+        int a;
+        if (EXT && p.t_forced) a = p.t_forced[rowi];              // replay of a recorded action sequence (< 0: env idles)
+        else a = g.pick(smask, scratch, k, lane);
         const int pl = g.player();
         __syncwarp();
-        g.step(a, ch, smask, scratch, lane, err);
-        h.t++; h.k++;
-        const bool over = g.over();
+        bool over = false;
         float pay[G::P];
 #pragma unroll
         for (int q = 0; q < G::P; q++) pay[q] = 0.f;
+        if (!EXT || a >= 0) {
+            g.step(a, ch, smask, scratch, lane, err);
+            h.t++; h.k++;
+            over = g.over();
+        }
+        if (EXT && p.tm_row) {                                    // per-seat terminal states into the pool (env.py:161-164)
+            int r = -1;
+            if (over) {
+                if (lane == 0) r = atomicAdd(p.tm_count, 1);
+                r = __shfl_sync(kFull, r, 0);
+                if (r >= p.tm_cap) { r = -1; err |= kErrTerminalPoolFull; }
+            }
+            if (lane == 0) p.tm_row[rowi] = r;
+            if (r >= 0) {
+                __syncwarp();
+                g.legal(smask, scratch, lane);
+                __syncwarp();
+                if (p.tm_obs) {
+                    for (int s = 0; s < G::P; s++) {
+                        g.encode_obs(s, false, srow, scratch, lane);
+                        __syncwarp();
+                        warp_flush_row<G, ObsT>(p.tm_obs, (size_t)r * G::P + s, srow, lane);
+                        __syncwarp();
+                    }
+                }
+                if (p.tm_mask) warp_write_mask<G>(p.tm_mask, (size_t)r, smask, lane);
+                __syncwarp();
+            }
+        }
         if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
         __syncwarp();
-        cnt = g.legal(smask, scratch, lane);                      // legal set of the state the next iteration emits
+        if (!EXT || a >= 0) cnt = g.legal(smask, scratch, lane);  // legal set of the state the next iteration emits
         __syncwarp();
         if (lane == 0) {
             if (p.t_player) st_stream(p.t_player + rowi, pl);
@@ -243,7 +274,10 @@ cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
     case kOpReset: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeReset, BLOCK>)); break;
     case kOpStep: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeStep, BLOCK>)); break;
     case kOpObserve: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
-    case kOpRollout: RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK>)); break;
+    case kOpRollout:
+        if (p.t_forced || p.tm_row) RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, true>));
+        else RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, false>));
+        break;
     default: e = cudaErrorInvalidValue;
     }
 #undef RLC_WLAUNCH

@@ -32,6 +32,8 @@ cudaError_t dmc_collect(const rlc_info &, const rlc_trajectory *, int, int, int,
 cudaError_t legal_ids(const rlc_info &, const void *, int, int, int32_t *, int32_t *, cudaStream_t);
 cudaError_t action_features(const rlc_info &, const int32_t *, int, int8_t *, cudaStream_t);
 cudaError_t rl_feed(const rlc_info &, int, const rlc_buffers *, int, const int32_t *, int, const rlc_rl_buffers *, cudaStream_t);
+cudaError_t reorganize(const rlc_info &, const rlc_trajectory *, int, int, int, const rlc_rl_buffers *, cudaStream_t);
+cudaError_t seed_mt19937(const uint32_t *, const int32_t *, int, uint32_t *, cudaStream_t);
 #endif
 }  // namespace rlc
 
@@ -44,17 +46,17 @@ static int fail(int code, const char *fmt, ...) {
 }
 
 static const rlc_info kInfo[RLC_NUM_GAMES] = {
-    /* game, P, A, obs_dim[4], stride, native dtype, bitpacked, mask_words, state_words, reset draws, threads/env */
-    { RLC_BLACKJACK, 1, 2, {2, 0, 0, 0}, 2, RLC_U8, 0, 1, rlc::kHeaderWords + 15, 55, 1, {0, 0, 0, 0} },
-    { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, {0, 0, 0, 0} },
-    { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, {0, 0, 0, 0} },
-    { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, {0, 0, 0, 0} },
-    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, {0, 0, 0, 0} },
-    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, {0, 0, 0, 0} },
+    /* game, P, A, obs_dim[4], stride, native dtype, bitpacked, mask_words, state_words, reset draws, threads/env, state layout */
+    { RLC_BLACKJACK, 1, 2, {2, 0, 0, 0}, 2, RLC_U8, 0, 1, rlc::kHeaderWords + 15, 55, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, RLC_STATE_ROWS, {0, 0, 0} },
+    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, RLC_STATE_ROWS, {0, 0, 0} },
 #ifdef RLC_HAVE_NOLIMIT
-    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, {0, 0, 0, 0} },
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, RLC_STATE_SOA, {0, 0, 0} },
 #else
-    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, 0, 53, 1, {0, 0, 0, 0} },
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, 0, 53, 1, RLC_STATE_SOA, {0, 0, 0} },
 #endif
 };
 
@@ -157,6 +159,14 @@ int rlc_rollout_random(int game_id, const rlc_buffers *b, const rlc_trajectory *
     if (traj) {
         p.t_obs = traj->obs; p.t_mask = traj->mask; p.t_action = traj->action; p.t_player = traj->player;
         p.t_done = traj->done; p.t_payoffs = traj->payoffs;
+        p.t_forced = traj->forced_actions;
+        if (traj->terminal_row) {
+            if (!traj->terminal_count || traj->terminal_capacity <= 0)
+                return fail(RLC_EINVAL, "terminal_row needs terminal_count and a positive terminal_capacity");
+            p.tm_obs = traj->terminal_obs; p.tm_mask = traj->terminal_mask; p.tm_row = traj->terminal_row;
+            p.tm_count = traj->terminal_count; p.tm_cap = traj->terminal_capacity;
+        }
+        if (p.t_forced || p.tm_row) p.flags |= rlc::kFlagNoFsm;
     }
     p.T = k_steps;
     return dispatch(game_id, rlc::kOpRollout, b, p, stream);
@@ -250,6 +260,33 @@ int rlc_rl_feed(int game_id, int phase, const rlc_buffers *env, const int32_t *a
     return judged(rlc::rl_feed(kInfo[game_id], phase, env, env->obs_dtype, actions, n, b, reinterpret_cast<cudaStream_t>(stream)));
 #else
     return fail(RLC_ENOTIMPL, "the transition collector is not in this build");
+#endif
+}
+
+int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_rl_buffers *b, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!traj || !b || T <= 0 || n <= 0) return fail(RLC_EINVAL, "null buffers or empty window");
+    if (!traj->obs || !traj->mask || !traj->action || !traj->player || !traj->done || !traj->payoffs ||
+        !traj->terminal_obs || !traj->terminal_mask || !traj->terminal_row)
+        return fail(RLC_EINVAL, "rlc_reorganize needs obs, mask, action, player, done, payoffs and the terminal_* pool of the window");
+    if (!b->pend_obs || !b->pend_action || !b->pend_valid || !b->out_count || !b->overflow || b->out_capacity <= 0)
+        return fail(RLC_EINVAL, "incomplete rlc_rl_buffers");
+    for (int p = 0; p < kInfo[game_id].num_players; p++)
+        if (!b->out_state[p] || !b->out_action[p] || !b->out_reward[p] || !b->out_next_state[p] || !b->out_next_mask[p] || !b->out_done[p])
+            return fail(RLC_EINVAL, "rlc_rl_buffers: seat %d pools missing", p);
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::reorganize(kInfo[game_id], traj, obs_dtype, T, n, b, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "the transition collector is not in this build");
+#endif
+}
+
+int rlc_seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt, void *stream) {
+    if (!key_words || !key_len || !mt || n <= 0) return fail(RLC_EINVAL, "null buffers or n <= 0");
+#ifdef RLC_HAVE_DMC
+    return judged(rlc::seed_mt19937(key_words, key_len, n, mt, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "not in this build");
 #endif
 }
 

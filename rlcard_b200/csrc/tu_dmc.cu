@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128) k_dmc_collect(const DmcParams q) {
     int t_start = 0;
     for (int t = 0; t < q.T; t++) {
         if (!q.t_done[(size_t)t * q.n + env]) continue;
+        if (len0 < 0) { len0 = 0; t_start = t + 1; continue; }   // the episode whose rows overflowed the open store: dropped whole
         // an episode ends at row t: its decisions are open[0, len0) followed by window rows [t_start, t]
         const int nwin = t - t_start + 1, total = len0 + nwin;
         float pay[RLC_MAX_PLAYERS]; int cnt[RLC_MAX_PLAYERS], base[RLC_MAX_PLAYERS], seen[RLC_MAX_PLAYERS];
@@ -123,10 +124,12 @@ __global__ void __launch_bounds__(128) k_dmc_collect(const DmcParams q) {
             if (lane == 0) { tg[slot] = py; er[slot] = last ? py : 0.f; dn[slot] = last ? 1 : 0; }
         }
         len0 = 0; t_start = t + 1;
+        __syncwarp();                                         // the open store was read above and is rewritten below
     }
     // decisions of the episode still running wait in the open store
     const int tail = q.T - t_start;
-    if (len0 + tail > q.Lmax) { if (lane == 0) *q.overflow = 2; }
+    if (len0 < 0) { /* still inside the dropped episode */ }
+    else if (len0 + tail > q.Lmax) { if (lane == 0) *q.overflow = 2; len0 = -1; }   // drop this episode, recover at its end
     else {
         for (int r = 0; r < tail; r++) {
             const size_t wrow = (size_t)(t_start + r) * q.n + env;
@@ -310,6 +313,125 @@ cudaError_t rl_feed(const rlc_info &info, int phase, const rlc_buffers *env, int
     q.count = b->out_count; q.cap = b->out_capacity; q.overflow = b->overflow;
     if (phase == 0) k_rl_feed<0><<<(n + 3) / 4, 128, 0, s>>>(q);
     else k_rl_feed<1><<<(n + 3) / 4, 128, 0, s>>>(q);
+    return cudaGetLastError();
+}
+
+
+// ==========================================================================================
+// reorganize over a fused rollout window (rlc_reorganize): the same transition rows as k_rl_feed, produced from the
+// [T][n] trajectory of rlc_rollout_random plus its terminal-state pool.  One warp per env walks its T cells; the last
+// decision of each seat waits (as a cell index of this window, or in pend_obs when it came from an earlier window).
+// ==========================================================================================
+struct ReorgParams {
+    RlParams q;
+    const uint8_t *t_obs, *t_mask; const int32_t *t_action, *t_player, *t_row; const uint8_t *t_done; const float *t_payoffs;
+    const uint8_t *tm_obs, *tm_mask; int T;
+};
+
+__global__ void __launch_bounds__(128) k_reorganize(const ReorgParams r) {
+    const RlParams &q = r.q;
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (env >= q.n) return;
+    uint8_t *pobs = q.pend_obs + (size_t)env * q.P * q.S;
+    int pend_t[RLC_MAX_PLAYERS], pend_a[RLC_MAX_PLAYERS];          // -2 none, -1 row kept in pend_obs, >= 0 cell of this window
+#pragma unroll
+    for (int p = 0; p < RLC_MAX_PLAYERS; p++) {
+        const bool v = p < q.P && q.pend_valid[env * q.P + p];
+        pend_t[p] = v ? -1 : -2;
+        pend_a[p] = v ? q.pend_action[env * q.P + p] : 0;
+    }
+    for (int t = 0; t < r.T; t++) {
+        const size_t cell = (size_t)t * q.n + env;
+        const int a = r.t_action[cell];
+        if (a < 0) continue;                                          // idle cell of a forced-action replay
+        const int pl = r.t_player[cell];
+        const uint8_t *cur = r.t_obs + cell * q.S, *curmask = r.t_mask + cell * q.M;
+#pragma unroll
+        for (int p = 0; p < RLC_MAX_PLAYERS; p++) {
+            if (p != pl) continue;
+            if (pend_t[p] != -2) {
+                const uint8_t *src = pend_t[p] < 0 ? pobs + (size_t)p * q.S : r.t_obs + ((size_t)pend_t[p] * q.n + env) * q.S;
+                rl_emit(q, p, src, pend_a[p], 0.f, cur, curmask, false, lane);
+            }
+            pend_t[p] = t; pend_a[p] = a;
+        }
+        if (r.t_done[cell]) {
+            const int row = r.t_row[cell];
+            if (row < 0) { if (lane == 0) *q.overflow = 3; }          // the terminal pool was full: transitions lost
+#pragma unroll
+            for (int p = 0; p < RLC_MAX_PLAYERS; p++) {
+                if (p >= q.P || pend_t[p] == -2) continue;
+                if (row >= 0) {
+                    const uint8_t *src = pend_t[p] < 0 ? pobs + (size_t)p * q.S : r.t_obs + ((size_t)pend_t[p] * q.n + env) * q.S;
+                    rl_emit(q, p, src, pend_a[p], r.t_payoffs[cell * q.P + p], r.tm_obs + ((size_t)row * q.P + p) * q.S,
+                            r.tm_mask + (size_t)row * q.M, true, lane);
+                }
+                pend_t[p] = -2;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < RLC_MAX_PLAYERS; p++) {                       // decisions still waiting for their next state
+        if (p >= q.P) continue;
+        if (pend_t[p] >= 0) copy_row(pobs + (size_t)p * q.S, r.t_obs + ((size_t)pend_t[p] * q.n + env) * q.S, q.S, lane);
+        if (lane == 0) { q.pend_valid[env * q.P + p] = pend_t[p] != -2; q.pend_action[env * q.P + p] = pend_a[p]; }
+    }
+}
+
+cudaError_t reorganize(const rlc_info &info, const rlc_trajectory *traj, int obs_dtype, int T, int n, const rlc_rl_buffers *b, cudaStream_t s) {
+    ReorgParams r; memset(&r, 0, sizeof r);
+    RlParams &q = r.q;
+    q.n = n; q.P = info.num_players; q.S = info.obs_stride * (obs_dtype == RLC_F32 ? 4 : 1);
+    q.M = info.mask_bitpacked ? info.mask_words * 4 : info.num_actions;
+    q.pend_obs = reinterpret_cast<uint8_t *>(b->pend_obs); q.pend_action = b->pend_action; q.pend_valid = b->pend_valid;
+    for (int p = 0; p < info.num_players; p++) {
+        q.o_state[p] = reinterpret_cast<uint8_t *>(b->out_state[p]); q.o_next[p] = reinterpret_cast<uint8_t *>(b->out_next_state[p]);
+        q.o_mask[p] = reinterpret_cast<uint8_t *>(b->out_next_mask[p]); q.o_done[p] = b->out_done[p];
+        q.o_action[p] = b->out_action[p]; q.o_reward[p] = b->out_reward[p];
+    }
+    q.count = b->out_count; q.cap = b->out_capacity; q.overflow = b->overflow;
+    r.t_obs = reinterpret_cast<const uint8_t *>(traj->obs); r.t_mask = reinterpret_cast<const uint8_t *>(traj->mask);
+    r.t_action = traj->action; r.t_player = traj->player; r.t_row = traj->terminal_row; r.t_done = traj->done;
+    r.t_payoffs = traj->payoffs; r.tm_obs = reinterpret_cast<const uint8_t *>(traj->terminal_obs);
+    r.tm_mask = reinterpret_cast<const uint8_t *>(traj->terminal_mask); r.T = T;
+    k_reorganize<<<(n + 3) / 4, 128, 0, s>>>(r);
+    return cudaGetLastError();
+}
+
+// ==========================================================================================
+// np.random.RandomState.seed(list of uint32) = MT19937 init_by_array, one generator per env, state column i of
+// mt[625][n] (numpy/random/_mt19937 legacy seeding; the words come from rlcard/utils/seeding.py:33-113 on the host)
+// ==========================================================================================
+__global__ void k_seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t N = (size_t)n;
+    auto w = [&](int j) -> uint32_t & { return mt[(size_t)j * N + i]; };
+    w(0) = 19650218u;
+    for (int j = 1; j < 624; j++) { const uint32_t prev = w(j - 1); w(j) = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)j; }
+    const int len = key_len[i];
+    const uint32_t k0 = key_words[2 * i], k1 = key_words[2 * i + 1];
+    int a = 1, b = 0;
+    for (int k = 624 > len ? 624 : len; k; k--) {
+        const uint32_t prev = w(a - 1);
+        w(a) = (w(a) ^ ((prev ^ (prev >> 30)) * 1664525u)) + (b ? k1 : k0) + (uint32_t)b;
+        a++; b++;
+        if (a >= 624) { w(0) = w(623); a = 1; }
+        if (b >= len) b = 0;
+    }
+    for (int k = 623; k; k--) {
+        const uint32_t prev = w(a - 1);
+        w(a) = (w(a) ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)a;
+        a++;
+        if (a >= 624) { w(0) = w(623); a = 1; }
+    }
+    w(0) = 0x80000000u;
+    w(624) = 624u;                                                   // index: the first draw twists
+}
+cudaError_t seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt, cudaStream_t s) {
+    k_seed_mt19937<<<(n + 127) / 128, 128, 0, s>>>(key_words, key_len, n, mt);
     return cudaGetLastError();
 }
 

@@ -20,17 +20,21 @@ def _stream(dev):
 
 def legal_ids(env, mask=None, max_ids=None):
     """Legal action ids of every env in ascending order: (ids int32 [N, max_ids] padded with -1, count int32 [N]).
-    ``mask`` defaults to the env's current mask; ``max_ids`` to 512 for doudizhu (the widest legal set seen is
-    452) and num_actions otherwise."""
+    ``mask`` defaults to the env's current mask; ``max_ids`` to num_actions, for doudizhu to 1024 (the 20-card hand
+    333444555666 + eight singles has 519 legal leads, the widest set found; tests/golden/deep_doudizhu.npz holds it).
+    Raises if a list was cut: a truncated list would silently hide the highest ids (bombs, rocket) from the policy."""
     mask = env.mask if mask is None else mask
     if max_ids is None:
-        max_ids = 512 if env.name == 'doudizhu' else env.num_actions
+        max_ids = 1024 if env.name == 'doudizhu' else env.num_actions
     n = mask.shape[0]
     ids = torch.empty((n, max_ids), dtype=torch.int32, device=env.device)
     count = torch.empty(n, dtype=torch.int32, device=env.device)
     with torch.cuda.device(env.device):
         check(lib().rlc_legal_ids(env.gid, C.c_void_p(mask.data_ptr()), n, int(max_ids), C.c_void_p(ids.data_ptr()),
                                   C.c_void_p(count.data_ptr()), _stream(env.device)))
+    widest = int(count.max().item()) if n else 0
+    if widest > max_ids:
+        raise ValueError('legal_ids: a state has %d legal actions, more than max_ids=%d' % (widest, max_ids))
     return ids, count
 
 
@@ -134,8 +138,19 @@ class DMCCollector:
     def sizes(self):
         of = int(self.overflow.item())
         if of:
-            raise RuntimeError('DMC pools overflowed (flag %d: 1 = a position pool was full, 2 = open store too small)' % of)
+            # rows beyond a full pool were dropped (their slots were still counted): clamp so that the collector stays
+            # usable after the caller has handled the error (drain with get_batch or clear())
+            self.count.clamp_(max=self.pool_rows)
+            self.overflow.zero_()
+            raise RuntimeError('DMC pools overflowed (flag %d: 1 = a position pool was full, rows dropped; 2 = the open store '
+                               'was too small, that episode was dropped whole)' % of)
         return [int(x) for x in self.count[:self.env.num_players].tolist()]
+
+    def clear(self):
+        """Forget every waiting row and every open episode (the envs keep running; decisions of episodes already under
+        way are dropped until their episode ends)."""
+        self.count.zero_(); self.overflow.zero_()
+        self.open_len.fill_(-1)
 
     def get_batch(self, position, T, B):
         """The learner's batch for one position (dmc_agent/utils.py:33-50): dict of [T, B, ...] tensors with keys

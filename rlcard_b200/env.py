@@ -165,7 +165,7 @@ class Env:
     # -- the per-env helpers the reference's callers and tests touch (envs/<game>.py)
     def _get_legal_actions(self):
         """OrderedDict of the current player's legal action ids (envs/<game>.py _get_legal_actions)."""
-        if self.name == 'blackjack' and self._vec.state[0, 0].item() == 0:      # before the first reset: {0, 1}
+        if self.name == 'blackjack' and self._vec.state.view(-1)[0].item() == 0:   # before the first reset: {0, 1}
             return OrderedDict([(0, None), (1, None)])
         self._vec.get_state(None)
         return self._dict_from(self._vec.obs[0], self._vec.mask[0], self.get_player_id())['legal_actions']
@@ -191,7 +191,8 @@ class Env:
         pid = self.get_player_id()
         legal = [self.actions[a] for a in self._dict_from(self._vec.obs[0], self._vec.mask[0], pid)['legal_actions']]
         info = {'current_player': pid, 'legal_actions': legal}
-        w = [int(x) & 0xffffffff for x in self._vec.state[:, 0].cpu().tolist()][3:]       # game words after the header
+        st = self._vec.state[0] if self._vec.state_rows else self._vec.state[:, 0]
+        w = [int(x) & 0xffffffff for x in st.cpu().tolist()][3:]                       # game words after the header
         if self.name == 'leduc-holdem':
             g = w[0]
             info['chips'] = [(g >> 7) & 15, (g >> 11) & 15]

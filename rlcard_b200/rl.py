@@ -10,15 +10,17 @@ import ctypes as C
 
 import torch
 
-from ._lib import AUTO_RESET, TERMINAL_OBS, RlcRlBuffers, check, lib
+from ._lib import AUTO_RESET, DTYPE_F32, DTYPE_U8, TERMINAL_OBS, RlcRlBuffers, RlcTrajectory, check, lib
 
 
 class TransitionCollector:
-    def __init__(self, env, pool_rows):
-        """env: VecEnv created with ``terminal_obs=True`` (the per-seat terminal views are part of the transitions)."""
-        if env.terminal_obs is None:
+    def __init__(self, env, pool_rows, fused=False):
+        """env: VecEnv created with ``terminal_obs=True`` (the per-seat terminal views are part of the transitions);
+        ``fused=True`` -> only the fused-rollout path (``collect_fused``) is used and any VecEnv will do."""
+        if env.terminal_obs is None and not fused:
             raise ValueError('TransitionCollector needs VecEnv(..., terminal_obs=True)')
         self.env = env
+        self._win = None
         dev, N, P = env.device, env.num_envs, env.num_players
         self.pool_rows = int(pool_rows)
         odt = env.obs_dtype
@@ -70,6 +72,26 @@ class TransitionCollector:
         obs, mask, cur = self.env.obs, self.env.mask, self.env.cur_player
         for _ in range(num_steps):
             obs, mask, cur, _, _ = self.step(policy(obs, mask, cur))
+
+    def collect_fused(self, T, actions=None, terminal_rows=None):
+        """run_rl.py's data path on the FUSED rollout: one rlc_rollout_random launch of T env-steps per env (random
+        agents, or the recorded ids in ``actions`` int32 [T, N]; auto reset) that also writes the per-seat terminal states
+        into a pool, then one rlc_reorganize launch that folds the window into the per-seat transition pools.  Consecutive
+        calls chain: a decision whose next state falls into the next window waits in pend_*.  Returns the window."""
+        env = self.env
+        rows = int(terminal_rows or env.num_envs * T)
+        if self._win is None or self._win['action'].shape[0] != T or self._win['terminal_obs'].shape[0] != rows:
+            self._win = env.alloc_terminal_pool(rows, T, env.alloc_trajectory(T))
+        w = self._win
+        w['terminal_count'].zero_()
+        env.rollout_random(T, out=w, actions=actions)
+        tr = RlcTrajectory()
+        for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs', 'terminal_obs', 'terminal_mask', 'terminal_row'):
+            setattr(tr, k, w[k].data_ptr())
+        with torch.cuda.device(env.device):
+            check(lib().rlc_reorganize(env.gid, C.byref(tr), DTYPE_F32 if env.obs_dtype == torch.float32 else DTYPE_U8, int(T),
+                                       env.num_envs, C.byref(self._b), C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)))
+        return w
 
     def sizes(self):
         if int(self.overflow.item()):

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (AUTO_RESET, CHANCE_MT19937, CHANCE_PHILOX, CHANCE_TAPE, DTYPE_F32, DTYPE_U8, GAME_IDS,
+from ._lib import (AUTO_RESET, CHANCE_MT19937, CHANCE_PHILOX, CHANCE_TAPE, DTYPE_F32, DTYPE_U8, GAME_IDS, STATE_ROWS,
                    TERMINAL_OBS, RlcBuffers, RlcTrajectory, check, game_info, lib)
 
 _MODES = {'throughput': CHANCE_PHILOX, 'philox': CHANCE_PHILOX, 'replay': CHANCE_TAPE, 'tape': CHANCE_TAPE,
@@ -77,6 +77,7 @@ class VecEnv:
         self.mask_bitpacked = bool(info.mask_bitpacked)
         self.mask_words = info.mask_words
         self.state_words = info.state_words
+        self.state_rows = info.state_layout == STATE_ROWS        # [N][state_words] (warp-per-env games) vs [state_words][N]
         self.chance = _MODES[mode]
         self.seed_value = int(seed)
         self.env_id_base = int(env_id_base)
@@ -89,7 +90,8 @@ class VecEnv:
         self.obs_dtype = obs_dtype
         N, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
-            self.state = torch.zeros((self.state_words, N), dtype=torch.int32, device=dev)
+            self.state = torch.zeros((N, self.state_words) if self.state_rows else (self.state_words, N),
+                                     dtype=torch.int32, device=dev)
             # the five per-step outputs are views of ONE device buffer (256-byte aligned sections), so a host
             # consumer fetches a whole step with a single device-to-host copy (step_host)
             esz = 4 if obs_dtype == torch.float32 else 1
@@ -131,16 +133,20 @@ class VecEnv:
         self._buf = None
 
     def seed_mt19937(self, seeds):
-        """Per-env ``rlcard.make(..., {'seed': s})`` seeding (utils/seeding.py:33-41)."""
+        """Per-env ``rlcard.make(..., {'seed': s})`` seeding (utils/seeding.py:33-41): the sha512 word split runs on
+        the host (one digest per env), MT19937 init_by_array on the device (rlc_seed_mt19937)."""
         assert len(seeds) == self.num_envs
-        st = np.zeros((625, self.num_envs), np.uint32)
+        keys = np.zeros((self.num_envs, 2), np.uint32)
+        lens = np.zeros(self.num_envs, np.int32)
         for i, s in enumerate(seeds):
-            rs = np.random.RandomState()
-            rs.seed(seed_words(s))
-            key = rs.get_state()
-            st[:624, i] = key[1]
-            st[624, i] = key[2]
-        self.mt = torch.as_tensor(st.view(np.int32)).to(self.device).contiguous()
+            w = seed_words(s)
+            keys[i, :len(w)] = w
+            lens[i] = len(w)
+        dk = torch.as_tensor(keys.view(np.int32)).to(self.device)
+        dl = torch.as_tensor(lens).to(self.device)
+        self.mt = torch.empty((625, self.num_envs), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.rlc_seed_mt19937(_ptr(dk), _ptr(dl), self.num_envs, _ptr(self.mt), self._stream()))
         self._buf = None
 
     # ------------------------------------------------------------------ plumbing
@@ -244,10 +250,25 @@ class VecEnv:
         tr['payoffs'] = torch.empty((T, N, self.num_players), dtype=torch.float32, device=dev)
         return tr
 
-    def rollout_random(self, T, out=None):
+    def alloc_terminal_pool(self, rows, T, out=None):
+        """Adds the per-seat terminal-state pool of the fused rollout (env.py:161-164) to a trajectory dict:
+        terminal_obs [rows, P, obs_stride], terminal_mask [rows, A | mask_words], terminal_row int32 [T, N] (pool row of
+        the episode that ended in that cell, -1 otherwise), terminal_count int32 [1]."""
+        out = {} if out is None else out
+        N, dev = self.num_envs, self.device
+        out['terminal_obs'] = torch.zeros((rows, self.num_players, self.obs_stride), dtype=self.obs_dtype, device=dev)
+        mshape = (rows, self.mask_words) if self.mask_bitpacked else (rows, self.num_actions)
+        out['terminal_mask'] = torch.zeros(mshape, dtype=torch.int32 if self.mask_bitpacked else torch.uint8, device=dev)
+        out['terminal_row'] = torch.full((T, N), -1, dtype=torch.int32, device=dev)
+        out['terminal_count'] = torch.zeros(1, dtype=torch.int32, device=dev)
+        return out
+
+    def rollout_random(self, T, out=None, actions=None):
         """T env-steps per env with on-device uniform-random agents (the Env.run loop with RandomAgents),
         auto reset.  Returns trajectory tensors [T, N, ...]: obs/mask the acting player saw, action,
-        player, done, payoffs."""
+        player, done, payoffs.  ``actions`` (int32 [T, N], device): apply these recorded ids instead of the random
+        policy (negative = the env idles in that cell) -- the action half of the replay mode.  If ``out`` carries a
+        terminal pool (alloc_terminal_pool) the per-seat terminal states of every finished episode are written too."""
         if out is None:
             out = self.alloc_trajectory(T)
         tr = RlcTrajectory()
@@ -256,6 +277,15 @@ class VecEnv:
             if t is not None:
                 assert t.is_contiguous() and t.shape[0] >= T
                 setattr(tr, k, t.data_ptr())
+        if actions is not None:
+            actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            assert actions.shape[0] >= T and actions.shape[1] == self.num_envs
+            tr.forced_actions = actions.data_ptr()
+        if out.get('terminal_row') is not None:
+            assert out['terminal_row'].shape[0] >= T
+            tr.terminal_obs, tr.terminal_mask = out['terminal_obs'].data_ptr(), out['terminal_mask'].data_ptr()
+            tr.terminal_row, tr.terminal_count = out['terminal_row'].data_ptr(), out['terminal_count'].data_ptr()
+            tr.terminal_capacity = out['terminal_obs'].shape[0]
         with torch.cuda.device(self.device):
             check(self.L.rlc_rollout_random(self.gid, C.byref(self._buffers()), C.byref(tr), self.num_envs, int(T),
                                             self._stream()))
@@ -357,7 +387,7 @@ class VecEnv:
         if e:
             bad = int((self.err != 0).sum().item())
             raise _lib.RlcError('device error flags set on %d envs (OR=%d: 1 tape exhausted, 2 tape value out of '
-                                'range, 4 illegal action replaced by fallback)' % (bad, e))
+                                'range, 4 illegal action replaced by fallback, 8 terminal-state pool full)' % (bad, e))
 
 
 def random_policy(generator=None):

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_info():
     L = rlcard_b200.lib()
-    assert L.rlc_abi_version() == 1
+    assert L.rlc_abi_version() == 2
     # Env.num_players / num_actions / state_shape of the reference (envs/*.py)
     expect = {'blackjack': (1, 2, [2]), 'leduc-holdem': (2, 4, [36, 36]), 'limit-holdem': (2, 4, [72, 72]),
               'uno': (2, 61, [240, 240]), 'doudizhu': (3, 27472, [790, 901, 901]), 'scout': (4, 204, [688] * 4),

@@ -107,3 +107,94 @@ def test_collector_run_with_batched_policy():
         assert bool((t['reward'][~t['done']] == 0).all())
         assert bool(((t['reward'] * 2) == (t['reward'] * 2).round()).all())
         assert bool((t['next_mask'].sum(1) >= 1).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('window', [7, 4096])
+@pytest.mark.parametrize('game', GAMES)
+def test_fused_rollout_reorganize_matches_reference(game, window):
+    """The reference's run_rl.py fixtures replayed through the FUSED path: rlc_rollout_random in replay mode (recorded
+    chance tape + the recorded action ids as forced_actions, auto reset, terminal-state pool) followed by rlc_reorganize,
+    in windows that cut through episodes.  Every transition row equals the reference's reorganize output."""
+    import torch
+    import rlcard_b200
+    from rlcard_b200.rl import TransitionCollector
+    fx = load(game)
+    env = rlcard_b200.VecEnv(game, 1, mode='replay')
+    tape = np.concatenate([fx['tape'], np.zeros(512, np.uint8)])          # the auto reset after the last episode deals once more
+    env.set_tape(tape[None, :])
+    env.reset()
+    col = TransitionCollector(env, pool_rows=4096, fused=True)
+    acts = torch.tensor(fx['actions'], dtype=torch.int32, device='cuda').view(-1, 1)
+    for t0 in range(0, len(acts), window):
+        chunk = acts[t0:t0 + window]
+        pad = torch.full((window - len(chunk), 1), -1, dtype=torch.int32, device='cuda')    # idle cells
+        col.collect_fused(window, actions=torch.cat([chunk, pad]).contiguous())
+    assert not (int(env.err.item()) & ~4)                                  # 4 = the fixtures' deliberate illegal ids
+    assert not bool(col.pend_valid.any())
+    A = env.num_actions
+    for p in range(env.num_players):
+        got = col.pop(p)
+        d = env.obs_dims[p]
+        n = len(fx['action_%d' % p])
+        assert got['action'].shape[0] == n, (game, p)
+        np.testing.assert_array_equal(got['state'].cpu().numpy().astype(np.float64), fx['state_%d' % p][:, :d].astype(np.float64))
+        np.testing.assert_array_equal(got['next_state'].cpu().numpy().astype(np.float64), fx['next_state_%d' % p][:, :d].astype(np.float64))
+        np.testing.assert_array_equal(got['action'].cpu().numpy(), fx['action_%d' % p])
+        np.testing.assert_array_equal(got['reward'].cpu().numpy().astype(np.float64), fx['reward_%d' % p])
+        np.testing.assert_array_equal(got['done'].cpu().numpy().astype(np.uint8), fx['done_%d' % p])
+        m = got['next_mask'].cpu().numpy()
+        if env.mask_bitpacked:
+            m = np.unpackbits(m.view(np.uint8), axis=1, bitorder='little')[:, :A]
+        np.testing.assert_array_equal(m, np.unpackbits(fx['next_legal_%d' % p], axis=1, bitorder='little')[:, :A])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', GAMES)
+def test_fused_reorganize_equals_numpy_restatement(game):
+    """Throughput mode, many envs, three chained windows: the device rows of rlc_reorganize equal a numpy restatement of
+    Env.run + reorganize (env.py:120-169, utils.py:153-179) applied to the same fused trajectory + terminal pool, per
+    seat as multisets (pool order depends on warp scheduling)."""
+    import torch
+    import rlcard_b200
+    from rlcard_b200.rl import TransitionCollector
+    n, T, windows, seed = 64, 20, 3, 31
+    env = rlcard_b200.VecEnv(game, n, seed=seed)
+    env.reset()
+    col = TransitionCollector(env, pool_rows=n * T * windows * 2, fused=True)
+    P = env.num_players
+    want = [[] for _ in range(P)]
+    pend = [[None] * P for _ in range(n)]
+    episodes = 0
+    for _ in range(windows):
+        w = {k: v.cpu().numpy() for k, v in col.collect_fused(T).items()}
+        for i in range(n):
+            for t in range(T):
+                a, p = int(w['action'][t, i]), int(w['player'][t, i])
+                o, m = w['obs'][t, i], w['mask'][t, i]
+                if pend[i][p] is not None:
+                    want[p].append((pend[i][p][0].tobytes(), pend[i][p][1], 0.0, o.tobytes(), m.tobytes(), False))
+                pend[i][p] = (o.copy(), a)
+                if w['done'][t, i]:
+                    episodes += 1
+                    r = int(w['terminal_row'][t, i])
+                    assert r >= 0
+                    for s in range(P):
+                        if pend[i][s] is not None:
+                            want[s].append((pend[i][s][0].tobytes(), pend[i][s][1], float(w['payoffs'][t, i, s]),
+                                            w['terminal_obs'][r, s].tobytes(), w['terminal_mask'][r].tobytes(), True))
+                        pend[i][s] = None
+                else:
+                    assert int(w['terminal_row'][t, i]) == -1
+    env.check_errors()
+    assert episodes > 0 or game in ('scout',)
+    sizes = col.sizes()
+    for p in range(P):
+        assert sizes[p] == len(want[p])
+        st, nx = col.state[p][:sizes[p]].cpu().numpy(), col.next_state[p][:sizes[p]].cpu().numpy()
+        mk, ac = col.next_mask[p][:sizes[p]].cpu().numpy(), col.action[p][:sizes[p]].cpu().numpy()
+        rw, dn = col.reward[p][:sizes[p]].cpu().numpy(), col.done[p][:sizes[p]].cpu().numpy()
+        got = [(st[k].tobytes(), int(ac[k]), float(rw[k]), nx[k].tobytes(), mk[k].tobytes(), bool(dn[k])) for k in range(sizes[p])]
+        assert sorted(got) == sorted(want[p]), (game, p)
+    live = sum(1 for i in range(n) for s in range(P) if pend[i][s] is not None)
+    assert int(col.pend_valid.sum().item()) == live
