@@ -48,7 +48,7 @@ def algorithmic_bytes_per_env_step(info, obs_elem, T):
     O = info.obs_stride * obs_elem
     M = info.mask_words * 4 if info.mask_bitpacked else info.num_actions
     per_step = O + M + 4 + 4 + 1 + 4 * info.num_players
-    state = 2 * 4 * info.state_words
+    state = 2 * 4 * info.state_words_philox      # the words the throughput kernels read + write per env and launch
     return per_step + state / float(T), per_step, state
 
 

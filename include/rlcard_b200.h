@@ -76,7 +76,9 @@ typedef struct rlc_info {
     int32_t max_tape_draws_reset;       /* draws a reset can consume (tape sizing aid)        */
     int32_t threads_per_env;            /* 1 (thread per env) or 32 (warp per env)            */
     int32_t state_layout;               /* RLC_STATE_SOA [state_words][n] or RLC_STATE_ROWS [n][state_words] */
-    int32_t reserved[3];
+    int32_t state_words_philox;         /* words the throughput (Philox) kernels actually read and write per env
+                                           (UNO keeps multiset piles, Blackjack a deck mask: fewer than state_words) */
+    int32_t reserved[2];
 } rlc_info;
 
 typedef struct rlc_buffers {
@@ -100,6 +102,15 @@ typedef struct rlc_buffers {
     int32_t *err;             /* [n] sticky bit flags: 1 tape exhausted, 2 tape value out of range,
                                  4 illegal action replaced by the reference's fallback,
                                  8 terminal-state pool of the fused rollout was full            */
+    /* ABI 2, optional: the legal ids of the state that obs/mask describe, in the INSERTION ORDER of the reference's
+     * state['legal_actions'] OrderedDict (what `np.random.choice(list(legal_actions.keys()))` indexes,
+     * agents/random_agent.py:27): UNO = order of first occurrence in the hand list (envs/uno.py:47-50 over
+     * games/uno/round.py:96-135; replay chance modes only -- the throughput mode keeps hands as multisets and
+     * lists ascending), Scout = multi-card plays, then single cards, then scouts (games/scout/round.py:225-260,
+     * utils/utils.py:70-100), every other game ascending (DouDizhu's lead order is Python set order in the
+     * reference, i.e. undefined).  Rows are -1 padded; written by rlc_reset / rlc_step / rlc_observe. */
+    int32_t *legal_order;     /* [n][legal_order_stride]                                      */
+    int32_t legal_order_stride;
 } rlc_buffers;
 
 /* trajectory buffers of rlc_rollout_random: [T][n][...], any pointer may be NULL */

@@ -24,14 +24,15 @@ class RlcInfo(C.Structure):
                 ('obs_dim', C.c_int32 * RLC_MAX_PLAYERS), ('obs_stride', C.c_int32),
                 ('obs_native_dtype', C.c_int32), ('mask_bitpacked', C.c_int32), ('mask_words', C.c_int32),
                 ('state_words', C.c_int32), ('max_tape_draws_reset', C.c_int32), ('threads_per_env', C.c_int32),
-                ('state_layout', C.c_int32), ('reserved', C.c_int32 * 3)]
+                ('state_layout', C.c_int32), ('state_words_philox', C.c_int32), ('reserved', C.c_int32 * 2)]
 
 
 class RlcBuffers(C.Structure):
     _fields_ = [('state', C.c_void_p), ('chance', C.c_int32), ('seed', C.c_uint64), ('env_id_base', C.c_uint32),
                 ('tape', C.c_void_p), ('tape_stride', C.c_int32), ('tape_pos', C.c_void_p), ('mt', C.c_void_p),
                 ('obs', C.c_void_p), ('obs_dtype', C.c_int32), ('mask', C.c_void_p), ('cur_player', C.c_void_p),
-                ('done', C.c_void_p), ('payoffs', C.c_void_p), ('terminal_obs', C.c_void_p), ('err', C.c_void_p)]
+                ('done', C.c_void_p), ('payoffs', C.c_void_p), ('terminal_obs', C.c_void_p), ('err', C.c_void_p),
+                ('legal_order', C.c_void_p), ('legal_order_stride', C.c_int32)]
 
 
 class RlcTrajectory(C.Structure):

@@ -212,6 +212,16 @@ struct Doudizhu {
         n_live = nl; n_legal = cnt + (has_pass ? 1 : 0);
         return n_legal;
     }
+    // ascending ids (the reference's lead order is the iteration order of a Python set of strings: undefined)
+    __device__ void legal_order(const uint32_t *smask, int32_t *out, int stride, int lane) const {
+        if (lane != 0) return;
+        int n = 0;
+        for (int w = 0; w < 859; w++) {
+            uint32_t v = smask[w];
+            while (v) { const int b = __ffs(v) - 1; v &= v - 1; if (n < stride) out[n] = 32 * w + b; n++; }
+        }
+        for (int k = n; k < stride; k++) out[k] = -1;
+    }
     // k-th legal id in ascending order (0 <= k < n_legal of the last legal()); 'pass' is the largest id
     __device__ int pick(const uint32_t *smask, const uint8_t *scratch, int k, int lane) const {
         if (has_pass && k == n_legal - 1) return kDdzPass;

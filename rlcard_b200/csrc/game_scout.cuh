@@ -140,6 +140,25 @@ struct Scout {
     }
     // k-th legal id in ascending order
     __device__ __forceinline__ int pick(const uint32_t *, const uint8_t *, int k, int) const { return kth_set_bit<7>(lm, k); }
+    // the last legal() set in the order games/scout/round.py:225-260 builds it: plays of two or more cards (start-major,
+    // utils/utils.py:83-95), then the single cards (:97-98), then the scouts by insert position (front, front-flip, back,
+    // back-flip) -- i.e. ascending ids except that the singles (id = first id of their start) come after the longer plays
+    __device__ void legal_order(const uint32_t *, int32_t *out, int stride, int lane) const {
+        if (lane != 0) return;
+        int n = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            int single = 0;                                              // id of play-s-(s+1): 0, 16, 31, 45, ...
+            for (int s = 0; s < 16; s++) {
+                const int lo = pass ? single : single + 1, hi = pass ? single + 1 : single + 16 - s;
+                for (int a = lo; a < hi; a++)
+                    if ((lm[a >> 5] >> (a & 31)) & 1u) { if (n < stride) out[n] = a; n++; }
+                single += 16 - s;
+            }
+        }
+        for (int a = 136; a < 204; a++)
+            if ((lm[a >> 5] >> (a & 31)) & 1u) { if (n < stride) out[n] = a; n++; }
+        for (int k = n; k < stride; k++) out[k] = -1;
+    }
     // games/scout/game.py:37-65, dealer.py:12-22, round.py:22-50: two shuffles (Q-SC1), round-robin deal
     template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
         if (lane == 0) {

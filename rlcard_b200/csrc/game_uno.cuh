@@ -49,7 +49,8 @@ __device__ __forceinline__ int uno_code_at(int pos) {
 
 template <bool BAG>
 struct UnoT {
-    static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = BAG ? 19 : 38, MASK_WORDS = 2;
+    static constexpr int kGameId = 3, P = 2, A = 61, OBS = 240, GAME_WORDS = BAG ? 19 : 66, MASK_WORDS = 2;
+    static constexpr bool kHasLegalOrder = !BAG;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
     static constexpr bool kChanceAwareState = false;
     static constexpr int kSharedBytes = 0;
@@ -57,6 +58,11 @@ struct UnoT {
     __device__ __forceinline__ void bind_shared(const uint8_t *) {}
     static constexpr int kMaxResetDraws = 256;
     uint8_t cards[BAG ? 1 : 108];
+    // replay modes also keep the hands as ARRIVAL-ORDERED card lists (seat 0 upwards from ho[0], seat 1 downwards from
+    // ho[107]; the two hands never hold more than 108 cards): the reference's state['legal_actions'] is ordered by first
+    // occurrence in the hand list (round.py:96-135), which only matters to callers that index it (RandomAgent)
+    uint8_t ho[BAG ? 1 : 108];
+    int hl0, hl1;
     uint32_t dk[4], pk[4];                         // BAG: draw / played pile counters (13 x 2 bits + wild, wd4 per colour)
     uint32_t hc[2][4], hw[2];
     int dl, pl, tcode, tcolor, dir, cur, winner;   // dir: 0 = +1, 1 = -1 ; winner: -1 none
@@ -82,6 +88,15 @@ struct UnoT {
         const uint32_t m = st[(size_t)(kBase + 10) * n + i];
         dl = bf_get(m, 0, 7); pl = bf_get(m, 7, 7); tcode = bf_get(m, 14, 6); tcolor = bf_get(m, 20, 2);
         dir = bf_get(m, 22, 1); cur = bf_get(m, 23, 1); winner = (int)bf_get(m, 24, 2) - 1;
+        if constexpr (!BAG) {
+#pragma unroll
+            for (int k = 0; k < 27; k++) {
+                const uint32_t v = st[(size_t)(38 + k) * n + i];
+                ho[4 * k] = v & 255u; ho[4 * k + 1] = (v >> 8) & 255u; ho[4 * k + 2] = (v >> 16) & 255u; ho[4 * k + 3] = v >> 24;
+            }
+            const uint32_t hl = st[(size_t)65 * n + i];
+            hl0 = (int)(hl & 127u); hl1 = (int)((hl >> 7) & 127u);
+        }
     }
     __device__ void store(uint32_t *st, size_t n, size_t i) const {
         if constexpr (BAG) {
@@ -99,6 +114,12 @@ struct UnoT {
             st[(size_t)(kBase + 4 + 5 * p) * n + i] = hw[p];
         }
         st[(size_t)(kBase + 10) * n + i] = dl | (pl << 7) | (tcode << 14) | (tcolor << 20) | (dir << 22) | (cur << 23) | ((winner + 1) << 24);
+        if constexpr (!BAG) {
+#pragma unroll
+            for (int k = 0; k < 27; k++)
+                st[(size_t)(38 + k) * n + i] = ho[4 * k] | (ho[4 * k + 1] << 8) | (ho[4 * k + 2] << 16) | ((uint32_t)ho[4 * k + 3] << 24);
+            st[(size_t)65 * n + i] = (uint32_t)hl0 | ((uint32_t)hl1 << 7);
+        }
     }
 
     // ---- list primitives
@@ -137,7 +158,24 @@ struct UnoT {
         } else cards[107 - pl] = (uint8_t)code;
         pl++;
     }
+    __device__ __forceinline__ void order_append(int p, int code) {      // hand.append(card)
+        if constexpr (!BAG) {
+            if (p == 0) { if (hl0 + hl1 < 108) ho[hl0++] = (uint8_t)code; }
+            else { if (hl0 + hl1 < 108) ho[107 - hl1++] = (uint8_t)code; }
+        }
+    }
+    __device__ void order_remove_first(int p, int code) {               // hand.pop(index of the first card with this str)
+        if constexpr (!BAG) {
+            const int n = p ? hl1 : hl0;
+            int at = -1;
+            for (int k = 0; k < n && at < 0; k++) if (ho[p ? 107 - k : k] == code) at = k;
+            if (at < 0) return;
+            for (int k = at; k + 1 < n; k++) { if (p) ho[107 - k] = ho[107 - (k + 1)]; else ho[k] = ho[k + 1]; }
+            if (p) hl1--; else hl0--;
+        }
+    }
     __device__ __forceinline__ void to_hand(int p, int code) {          // branch free: lanes hold different cards
+        order_append(p, code);
         const int c = code / 15, t = code - 15 * c;
         const bool wild = t >= 13;
         hc_add(p, c, wild ? 0u : 1u << (2 * min(t, 12)));
@@ -205,6 +243,7 @@ struct UnoT {
         dl = 108; pl = 0;
 #pragma unroll
         for (int p = 0; p < 2; p++) { hc[p][0] = hc[p][1] = hc[p][2] = hc[p][3] = 0; hw[p] = 0; }
+        hl0 = hl1 = 0;
         int top;
         if constexpr (BAG) {
             // throughput spec: the 15 cards of the opening deal come from a partial Fisher-Yates over the 108 physical
@@ -324,6 +363,25 @@ struct UnoT {
         if (!bits) bits = 1ull << 60;
         m[0] = (uint32_t)bits; m[1] = (uint32_t)(bits >> 32);
     }
+    // the same set in the insertion order of envs/uno.py:47-50 over round.py:96-135: cards in hand-list order, the four
+    // colours of 'wild' where the first wild is met, a colour card where its first copy is met; wild_draw_4 only if
+    // nothing else is legal, 'draw' only if nothing at all
+    __device__ int legal_order(const uint32_t (&m)[2], int32_t *out, int stride) const {
+        const uint64_t bits = (uint64_t)m[0] | ((uint64_t)m[1] << 32);
+        uint64_t seen = 0;
+        int n = 0;
+        auto emit = [&](int a) { if (!((seen >> a) & 1ull)) { seen |= 1ull << a; if (n < stride) out[n] = a; n++; } };
+        if constexpr (!BAG) {
+            const int hn = cur ? hl1 : hl0;
+            for (int k = 0; k < hn; k++) {
+                const int code = ho[cur ? 107 - k : k], t = code % 15;
+                if (t == 13) { if ((bits >> 13) & 1ull) { emit(13); emit(28); emit(43); emit(58); } }
+                else if (t < 13 && ((bits >> code) & 1ull)) emit(code);
+            }
+        }
+        for (int a = 0; a < 61; a++) if ((bits >> a) & 1ull) emit(a);     // wild_draw_4 x4 / draw, or ascending (multiset hands)
+        return n;
+    }
     // env.py:65-86, envs/uno.py:39-45, game.py:58-81, round.py:54-94 (play), 162-192 (draw), 194-227 (effects).
     // The lanes of a warp take different actions, so the transition is one mostly branch-free pass over flags; the only
     // branches left are the ones that make Philox draws (pop a card, colour of an auto-played wild, penalty cards).
@@ -365,6 +423,10 @@ struct UnoT {
             const bool take = play && wild;
             set_hw(cur, take ? (w & ~(0x7ffu << base)) | ((rest & 0x7ffu) << base) : w);
             code = take ? 15 * first + t : code;
+        }
+        if constexpr (!BAG) {
+            if (keep) order_append(cur, src);
+            if (play) order_remove_first(cur, code);
         }
         if (play && hand_empty(cur)) winner = cur;
         int color = c;

@@ -5,6 +5,7 @@
 // memory and streamed out with 128-bit stores (common.cuh warp_tile_flush).
 #pragma once
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/rlcard_b200.h"
 
@@ -20,6 +21,7 @@ struct KParams {
     // fused-rollout extensions (rlc_trajectory, ABI 2): recorded action ids to apply instead of the random policy, and the
     // pool of per-seat terminal states (env.py:161-164) with the row index per trajectory cell
     const int32_t *t_forced; void *tm_obs; void *tm_mask; int32_t *tm_row; int32_t *tm_count; int tm_cap;
+    int32_t *order; int order_stride;            // legal ids in the reference's insertion order (rlc_buffers.legal_order)
     const void *tables; const void *tab[5];      // per-game constant tables (device pointers), see Game::bind
 };
 
@@ -107,6 +109,21 @@ __device__ __forceinline__ int pick_action(const uint32_t (&m)[G::MASK_WORDS], u
     }
 }
 
+// legal ids in the insertion order of the reference's state['legal_actions'] (see rlc_buffers.legal_order); games without
+// an order of their own list ascending
+template <class G, class = void> struct HasLegalOrder { static constexpr bool value = false; };
+template <class G> struct HasLegalOrder<G, std::void_t<decltype(G::kHasLegalOrder)>> { static constexpr bool value = G::kHasLegalOrder; };
+template <class G>
+__device__ void write_legal_order(const G &g, const uint32_t (&m)[G::MASK_WORDS], int32_t *out, int stride) {
+    int n = 0;
+    if constexpr (HasLegalOrder<G>::value) n = g.legal_order(m, out, stride);
+    else {
+        for (int a = 0; a < G::A; a++)
+            if ((m[a >> 5] >> (a & 31)) & 1u) { if (n < stride) out[n] = a; n++; }
+    }
+    for (int k = n; k < stride; k++) out[k] = -1;
+}
+
 template <class G, class Ch, class ObsT, int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
     extern __shared__ uint4 smem_raw[];
@@ -174,6 +191,7 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
         uint32_t m[G::MASK_WORDS];
         g.legal(m);
         if (p.mask) write_mask_row<G>(reinterpret_cast<uint8_t *>(p.mask), i, m);
+        if (p.order) write_legal_order<G>(g, m, p.order + i * (size_t)p.order_stride, p.order_stride);
         if (p.cur_player) p.cur_player[i] = g.player();
         if (p.done) p.done[i] = done ? 1 : 0;
         if (p.payoffs) {
@@ -237,7 +255,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         h.load(p.state, p.n, i);
         game_load<G, Ch>(g, p.state + kHeaderWords * p.n, p.n, i);
         ChanceIO<Ch>::open(ch, p, i);
-        if (h.episode == 0) {
+        if (h.episode == 0 || g.over()) {         // never dealt, or a finished episode left by rlc_step without auto reset
             ch.begin_reset(h.k);
             if constexpr (kWarpDeal) { h.episode++; h.t = 0; starts = true; }
             else new_episode(g, ch, h);

@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
         warp_flush_row<G, ObsT>(p.obs, env, srow, lane);
     }
     if (p.mask) warp_write_mask<G>(p.mask, env, smask, lane);
+    if (p.order) {
+        __syncwarp();
+        g.legal_order(smask, p.order + env * (size_t)p.order_stride, p.order_stride, lane);
+    }
     if (lane == 0) {
         if (p.cur_player) p.cur_player[env] = g.player();
         if (p.done) p.done[env] = done ? 1 : 0;
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     G g; g.bind(p, scratch); g.load(row + kHeaderWords, lane);
     WarpChance<Ch> ch; wchance_open(ch, p, env, lane);
     int err = 0;
-    if (h.episode == 0) { ch.begin_reset(h.k); h.episode = 1; h.t = 0; g.reset(ch, scratch, lane); }
+    if (h.episode == 0 || g.over()) { ch.begin_reset(h.k); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
     __syncwarp();
     int cnt = g.legal(smask, scratch, lane);
     __syncwarp();

@@ -9,6 +9,7 @@
 namespace rlc {
 cudaError_t dispatch_blackjack(int, int, int, const KParams &, cudaStream_t);
 cudaError_t dispatch_leduc(int, int, int, const KParams &, cudaStream_t);
+cudaError_t leduc_init(int device);
 cudaError_t dispatch_limit(int, int, int, const KParams &, cudaStream_t);
 cudaError_t judge_holdem(const uint8_t *, int, int, uint8_t *, cudaStream_t);
 cudaError_t judge_leduc(const int32_t *, int, float *, cudaStream_t);
@@ -47,16 +48,16 @@ static int fail(int code, const char *fmt, ...) {
 
 static const rlc_info kInfo[RLC_NUM_GAMES] = {
     /* game, P, A, obs_dim[4], stride, native dtype, bitpacked, mask_words, state_words, reset draws, threads/env, state layout */
-    { RLC_BLACKJACK, 1, 2, {2, 0, 0, 0}, 2, RLC_U8, 0, 1, rlc::kHeaderWords + 15, 55, 1, RLC_STATE_SOA, {0, 0, 0} },
-    { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, RLC_STATE_SOA, {0, 0, 0} },
-    { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, RLC_STATE_SOA, {0, 0, 0} },
-    { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 38, 256, 1, RLC_STATE_SOA, {0, 0, 0} },
-    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, RLC_STATE_ROWS, {0, 0, 0} },
-    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, RLC_STATE_ROWS, {0, 0, 0} },
+    { RLC_BLACKJACK, 1, 2, {2, 0, 0, 0}, 2, RLC_U8, 0, 1, rlc::kHeaderWords + 15, 55, 1, RLC_STATE_SOA, rlc::kHeaderWords + 4, {0, 0} },
+    { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, RLC_STATE_SOA, rlc::kHeaderWords + 1, {0, 0} },
+    { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, RLC_STATE_SOA, rlc::kHeaderWords + 4, {0, 0} },
+    { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 66, 256, 1, RLC_STATE_SOA, rlc::kHeaderWords + 19, {0, 0} },
+    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, RLC_STATE_ROWS, rlc::kHeaderWords + 20, {0, 0} },
+    { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, RLC_STATE_ROWS, rlc::kHeaderWords + 23, {0, 0} },
 #ifdef RLC_HAVE_NOLIMIT
-    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, RLC_STATE_SOA, rlc::kHeaderWords + 4, {0, 0} },
 #else
-    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, 0, 53, 1, RLC_STATE_SOA, {0, 0, 0} },
+    { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, 0, 53, 1, RLC_STATE_SOA, 0, {0, 0} },
 #endif
 };
 
@@ -103,6 +104,10 @@ static int fill(int game, const rlc_buffers *b, int n, rlc::KParams &p) {
     p.tape = b->tape; p.tape_stride = b->tape_stride; p.tape_pos = b->tape_pos; p.mt = b->mt;
     p.obs = b->obs; p.mask = b->mask; p.cur_player = b->cur_player; p.done = b->done; p.payoffs = b->payoffs;
     p.terminal_obs = b->terminal_obs; p.err = b->err;
+    if (b->legal_order) {
+        if (b->legal_order_stride <= 0) return fail(RLC_EINVAL, "legal_order needs a positive legal_order_stride");
+        p.order = b->legal_order; p.order_stride = b->legal_order_stride;
+    }
     return RLC_OK;
 }
 
@@ -125,6 +130,10 @@ int rlc_upload_tables(int game_id, int device, const void *blob, size_t nbytes) 
         return e == cudaSuccess ? RLC_OK : fail(RLC_ECUDA, "table upload: %s", cudaGetErrorString(e));
     }
 #endif
+    if (game_id == RLC_LEDUC) {      /* no blob: the betting-state table is tabulated on the device from the engine itself */
+        cudaError_t e = rlc::leduc_init(device);
+        return e == cudaSuccess ? RLC_OK : fail(RLC_ECUDA, "leduc table build: %s", cudaGetErrorString(e));
+    }
     (void)device; (void)blob; (void)nbytes;
     if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
     return RLC_OK;   /* the other games have no uploaded tables */

@@ -19,13 +19,25 @@ cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     if (device < 0 || device >= 64 || !blob || nbytes < sizeof(DdzBlobHeader)) return cudaErrorInvalidValue;
     DdzBlobHeader h; memcpy(&h, blob, sizeof h);
     if (memcmp(h.magic, "DDZ2", 4) != 0 || h.n_actions != 27472 || h.n_words_padded != 896 || h.total != nbytes || h.n_types != 38) return cudaErrorInvalidValue;
+    // every array the kernels index must lie inside the blob (and be aligned for its element type)
+    const auto inside = [&](uint64_t off, uint64_t bytes, uint64_t align) { return off % align == 0 && off <= nbytes && bytes <= nbytes - off; };
+    if (!inside(h.off_rows, 8ull * h.n_actions, 8) || !inside(h.off_need, 16ull * h.n_words_padded, 16) ||
+        !inside(h.off_type, h.n_actions, 1) || !inside(h.off_weight, h.n_actions, 1) || !inside(h.off_tw, 4ull * 38 * 17, 4))
+        return cudaErrorInvalidValue;
     int prev = 0; cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
-    if (g_dev_blob[device]) { cudaFree(g_dev_blob[device]); g_dev_blob[device] = nullptr; }
-    e = cudaMalloc(&g_dev_blob[device], nbytes);
-    if (e == cudaSuccess) e = cudaMemcpy(g_dev_blob[device], blob, nbytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
+    if (g_dev_blob[device]) { cudaFree(g_dev_blob[device]); g_dev_blob[device] = nullptr; memset(&g_tab[device], 0, sizeof g_tab[device]); }
+    void *dev_blob = nullptr;
+    e = cudaMalloc(&dev_blob, nbytes);
+    if (e == cudaSuccess) e = cudaMemcpy(dev_blob, blob, nbytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {                                   // nothing half-installed: later calls keep answering NotReady
+        if (dev_blob) cudaFree(dev_blob);
+        cudaSetDevice(prev);
+        return e;
+    }
+    g_dev_blob[device] = dev_blob;
+    {
         const char *b = reinterpret_cast<const char *>(g_dev_blob[device]);
         g_tab[device].rows = reinterpret_cast<const uint64_t *>(b + h.off_rows);
         g_tab[device].need = reinterpret_cast<const ulonglong2 *>(b + h.off_need);

@@ -101,26 +101,34 @@ __global__ void k_leduc_build_fsm(uint4 *tab, int *count) {
     }
     *count = n;
 }
-static cudaError_t leduc_fsm(const uint4 **out) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev >= 64) return cudaErrorInvalidValue;
+// Built once per device by rlc_upload_tables(RLC_LEDUC, device, NULL, 0) (VecEnv does it at construction): an explicit,
+// synchronous initialisation, so that rlc_rollout_random itself never allocates, never touches another stream and stays
+// capturable in a CUDA graph.  Until then the rollout runs the generic register engine (same results).
+cudaError_t leduc_init(int device) {
+    if (device < 0 || device >= 64) return cudaErrorInvalidValue;
     std::lock_guard<std::mutex> lock(g_fsm_mu);
-    if (!g_fsm[dev]) {
-        uint4 *tab = nullptr; int *cnt = nullptr, h = 0;
-        if ((e = cudaMalloc(&tab, sizeof(uint4) * kFsmMax)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&cnt, sizeof(int))) != cudaSuccess) return e;
-        cudaMemset(tab, 0, sizeof(uint4) * kFsmMax);
-        k_leduc_build_fsm<<<1, 32>>>(tab, cnt);
-        e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
-        cudaFree(cnt);
-        if (e != cudaSuccess) return e;
-        if (h <= 0) return cudaErrorUnknown;
-        g_fsm[dev] = tab;
-    }
-    *out = g_fsm[dev];
-    return cudaSuccess;
+    if (g_fsm[device]) return cudaSuccess;
+    int prev = 0; cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    uint4 *tab = nullptr; int *cnt = nullptr, h = 0;
+    e = cudaMalloc(&tab, sizeof(uint4) * kFsmMax);
+    if (e == cudaSuccess) e = cudaMalloc(&cnt, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(tab, 0, sizeof(uint4) * kFsmMax);
+    if (e == cudaSuccess) { k_leduc_build_fsm<<<1, 32>>>(tab, cnt); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && h <= 0) e = cudaErrorUnknown;
+    if (cnt) cudaFree(cnt);
+    if (e == cudaSuccess) g_fsm[device] = tab;
+    else if (tab) cudaFree(tab);
+    cudaSetDevice(prev);
+    return e;
+}
+static const uint4 *leduc_fsm_on_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_fsm_mu);
+    return g_fsm[dev];
 }
 
 // byte k (k < 4) of w, zero extended / sign extended: one PRMT each
@@ -173,6 +181,12 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
             cards |= leduc_showdown_code(cards) << 6;
             const uint32_t key = w & ~127u;
             for (int j = 0; j < kFsmMax; j++) if ((stab[j].x & ~127u) == key) { sid = (uint32_t)j; break; }
+            if ((stab[sid].x >> 4) & 1u) {   // a finished episode was left in the state (rlc_step without auto reset): deal
+                ch.begin_reset(h.k);         // the next one, exactly like the generic kernel
+                cards = lut[ch.chain(120u)];
+                sid = ch.chain(2u);
+                h.episode++; h.t = 0;
+            }
         }
     }
     uint4 e = stab[sid];
@@ -234,10 +248,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
 }
 
 template <class ObsT>
-static cudaError_t launch_leduc_fsm(const KParams &p, cudaStream_t s) {
-    const uint4 *tab = nullptr;
-    cudaError_t e = leduc_fsm(&tab);
-    if (e != cudaSuccess) return e;
+static cudaError_t launch_leduc_fsm(const KParams &p, const uint4 *tab, cudaStream_t s) {
     constexpr int BLOCK = 64;
     const size_t smem = (size_t)BLOCK * Leduc::OBS * sizeof(ObsT) + sizeof(uint4) * kFsmMax + 128;
     k_rollout_leduc_fsm<ObsT, BLOCK><<<(unsigned)((p.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(p, tab);
@@ -246,12 +257,13 @@ static cudaError_t launch_leduc_fsm(const KParams &p, cudaStream_t s) {
 
 cudaError_t dispatch_leduc(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t s) {
     // the bench / training case (throughput mode, every trajectory stream, aligned rows) runs the tabulated engine
-    if (op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & 0x100) && p.t_obs && p.t_mask && p.t_action &&
-        p.t_player && p.t_done && p.t_payoffs) {
+    const uint4 *tab = nullptr;
+    if (op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & kFlagNoFsm) && p.t_obs && p.t_mask && p.t_action &&
+        p.t_player && p.t_done && p.t_payoffs && (tab = leduc_fsm_on_device()) != nullptr) {
         if (obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Leduc::OBS)) & 15u) == 0)
-            return launch_leduc_fsm<uint8_t>(p, s);
+            return launch_leduc_fsm<uint8_t>(p, tab, s);
         if (obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Leduc::OBS * 4)) & 15u) == 0)
-            return launch_leduc_fsm<float>(p, s);
+            return launch_leduc_fsm<float>(p, tab, s);
     }
     return dispatch_game<Leduc>(op, chance, obs_dtype, p, s);
 }

@@ -72,7 +72,8 @@ class Env:
             raise NotImplementedError('allow_step_back=True is not supported by the batched simulator')
         self.device = device
         self._spec = _SPECS[env_id]
-        self._vec = VecEnv(env_id, 1, device=device, mode='mt19937', auto_reset=False)
+        self._vec = VecEnv(env_id, 1, device=device, mode='mt19937', auto_reset=False, legal_order=True)
+        self._hbuf, self._h = self._vec.alloc_host_step()      # pinned mirror: one D2H per reset / step / get_state
         self.num_players = self._vec.num_players
         self.num_actions = self._vec.num_actions
         self.state_shape = [list(_STATE_SHAPE.get(env_id, [d])) for d in self._vec.obs_dims]
@@ -84,6 +85,9 @@ class Env:
         self.timestep = 0
         self.action_recorder = []
         self.agents = None
+        self._h_action = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._d_action = torch.zeros(1, dtype=torch.int32, device=self._vec.device)
+        self._pid, self._done, self._pay, self._cur_state = 0, False, np.zeros(self.num_players), None
         self.seed(cfg['seed'])
 
     # -- seeding (env.py:228-231, utils/seeding.py:33-41)
@@ -98,18 +102,26 @@ class Env:
         return seed
 
     # -- state dict assembly (the per-env _extract_state)
-    def _state_dict(self):
-        v = self._vec
-        pid = int(v.cur_player[0].item())
-        return self._dict_from(v.obs[0], v.mask[0], pid), pid
+    def _fetch(self):
+        """One device-to-host copy of everything the last launch wrote (obs, mask, ordered legal ids, player, done,
+        payoffs); is_over / get_player_id / get_payoffs then answer from this host copy."""
+        self._hbuf.copy_(self._vec._out, non_blocking=True)
+        torch.cuda.current_stream(self._vec.device).synchronize()
+        h = self._h
+        self._pid, self._done = int(h['cur_player'][0]), bool(h['done'][0])
+        self._pay = h['payoffs'][0].numpy().astype(np.float64)
 
-    def _dict_from(self, obs_row, mask_row, seat_for_dim):
+    def _state_dict(self):
+        self._fetch()
+        self._cur_state = self._dict_from(self._pid)
+        return self._cur_state, self._pid
+
+    def _dict_from(self, seat_for_dim):
+        h = self._h
         d = self._vec.obs_dims[seat_for_dim]
-        obs = obs_row[:d].cpu().numpy().astype(self._spec['dtype']).reshape(self._spec['shape'](d))
-        m = mask_row.cpu().numpy()
-        if self._vec.mask_bitpacked:
-            m = np.unpackbits(m.view(np.uint8), bitorder='little')[:self.num_actions]
-        ids = np.nonzero(m)[0].tolist()
+        obs = h['obs'][0, :d].numpy().astype(self._spec['dtype']).reshape(self._spec['shape'](d))
+        order = h['legal_order'][0].numpy()
+        ids = order[order >= 0].tolist()                  # the reference's insertion order (rlc_buffers.legal_order)
         if self.name == 'doudizhu':                                        # envs/doudizhu.py:112-120: id -> 54-d feature
             state = {'obs': obs, 'legal_actions': OrderedDict((int(a), self._features[a]) for a in ids)}
         else:
@@ -129,8 +141,9 @@ class Env:
             action = self.actions.index(action)
         self.timestep += 1
         self.action_recorder.append((self.get_player_id(), self.actions[action] if self.actions else action))
-        a = torch.tensor([int(action)], dtype=torch.int32, device=self._vec.device)
-        self._vec.step(a, auto_reset=False)
+        self._h_action[0] = int(action)
+        self._d_action.copy_(self._h_action, non_blocking=True)
+        self._vec.step(self._d_action, auto_reset=False)       # one launch; _state_dict makes the one D2H
         return self._state_dict()
 
     def step_back(self):
@@ -140,20 +153,19 @@ class Env:
         self.agents = agents
 
     def is_over(self):
-        self._vec.get_state(None)
-        return bool(self._vec.done[0].item())
+        return self._done
 
     def get_player_id(self):
-        return int(self._vec.cur_player[0].item())
+        return self._pid
 
     def get_state(self, player_id):
         self._vec.get_state(int(player_id))
-        return self._dict_from(self._vec.obs[0], self._vec.mask[0], int(player_id))
+        self._fetch()
+        return self._dict_from(int(player_id))
 
     def get_payoffs(self):
-        self._vec.get_state(None)
-        p = self._vec.payoffs[0].cpu().numpy().astype(np.float64)
-        return p.astype(np.int64) if self.name in _INT_PAYOFF else p
+        p = self._pay
+        return p.astype(np.int64) if self.name in _INT_PAYOFF else p.copy()
 
     def get_action_feature(self, action):
         if self.name == 'doudizhu':
@@ -165,10 +177,9 @@ class Env:
     # -- the per-env helpers the reference's callers and tests touch (envs/<game>.py)
     def _get_legal_actions(self):
         """OrderedDict of the current player's legal action ids (envs/<game>.py _get_legal_actions)."""
-        if self.name == 'blackjack' and self._vec.state.view(-1)[0].item() == 0:   # before the first reset: {0, 1}
-            return OrderedDict([(0, None), (1, None)])
-        self._vec.get_state(None)
-        return self._dict_from(self._vec.obs[0], self._vec.mask[0], self.get_player_id())['legal_actions']
+        if self._cur_state is None:                      # before the first reset (blackjack's env tests do this): all ids
+            return OrderedDict((a, None) for a in range(self.num_actions))
+        return self._cur_state['legal_actions']
 
     def _decode_action(self, action_id):
         """id -> raw action with the reference's per-env fallback for illegal ids: poker 'check' else 'fold'
@@ -187,9 +198,8 @@ class Env:
         """envs/<game>.py get_perfect_information from the packed device state.  Exact for limit-holdem; Leduc
         cards are reported by rank only (the packed state drops the suit, which never influences play); the other
         games report the fields that do not need a decoder (current player, legal actions)."""
-        self._vec.get_state(None)
         pid = self.get_player_id()
-        legal = [self.actions[a] for a in self._dict_from(self._vec.obs[0], self._vec.mask[0], pid)['legal_actions']]
+        legal = [self.actions[a] for a in self._get_legal_actions()]
         info = {'current_player': pid, 'legal_actions': legal}
         st = self._vec.state[0] if self._vec.state_rows else self._vec.state[:, 0]
         w = [int(x) & 0xffffffff for x in st.cpu().tolist()][3:]                       # game words after the header

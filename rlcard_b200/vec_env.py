@@ -57,7 +57,7 @@ class VecEnv:
     """
 
     def __init__(self, env_id, num_envs, device='cuda:0', seed=0, mode='throughput', obs_dtype=None,
-                 env_id_base=0, auto_reset=True, terminal_obs=False):
+                 env_id_base=0, auto_reset=True, terminal_obs=False, legal_order=False):
         if env_id not in GAME_IDS:
             raise ValueError('unknown env id %r (have %s)' % (env_id, sorted(GAME_IDS)))
         self.L = lib()                     # raises if the CUDA extension is missing
@@ -96,7 +96,8 @@ class VecEnv:
             # consumer fetches a whole step with a single device-to-host copy (step_host)
             esz = 4 if obs_dtype == torch.float32 else 1
             msz = (self.mask_words * 4) if self.mask_bitpacked else self.num_actions
-            sizes = [N * self.obs_stride * esz, N * msz, N * 4, N, N * self.num_players * 4]
+            sizes = [N * self.obs_stride * esz, N * msz, N * 4, N, N * self.num_players * 4,
+                     N * min(self.num_actions, 1024) * 4 if legal_order else 0]
             offs, cur = [], 0
             for sz in sizes:
                 offs.append(cur)
@@ -115,6 +116,11 @@ class VecEnv:
             self.err = torch.zeros(N, dtype=torch.int32, device=dev)
             self.terminal_obs = (torch.zeros((N, self.num_players, self.obs_stride), dtype=obs_dtype, device=dev)
                                  if terminal_obs else None)
+            # legal ids in the reference's insertion order (rlc_buffers.legal_order), -1 padded; doudizhu rows are cut
+            # at 1024 ids (widest legal set: 519)
+            self.legal_order = sec(5).view(torch.int32).view(N, min(self.num_actions, 1024)) if legal_order else None
+            if legal_order:
+                self.legal_order.fill_(-1)
         self.tape = None
         self.tape_pos = None
         self.mt = None
@@ -122,6 +128,9 @@ class VecEnv:
         self.launches = 0
         if env_id == 'doudizhu':
             _upload_doudizhu_tables(self.L, self.device)
+        elif env_id == 'leduc-holdem':             # betting-state table of the tabulated rollout: explicit one-time init
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            check(self.L.rlc_upload_tables(self.gid, idx, None, 0))
 
     # ------------------------------------------------------------------ chance sources
     def set_tape(self, tape):
@@ -173,6 +182,8 @@ class VecEnv:
             b.payoffs = self.payoffs.data_ptr()
             b.terminal_obs = self.terminal_obs.data_ptr() if self.terminal_obs is not None else None
             b.err = self.err.data_ptr()
+            if self.legal_order is not None:
+                b.legal_order, b.legal_order_stride = self.legal_order.data_ptr(), self.legal_order.shape[1]
             self._buf = b
         return self._buf
 
@@ -221,6 +232,8 @@ class VecEnv:
                  'mask': sec(1).view(torch.int32).view(N, self.mask_words) if self.mask_bitpacked else sec(1).view(N, self.num_actions),
                  'cur_player': sec(2).view(torch.int32), 'done': sec(3),
                  'payoffs': sec(4).view(torch.float32).view(N, self.num_players)}
+        if self.legal_order is not None:
+            views['legal_order'] = sec(5).view(torch.int32).view(N, self.legal_order.shape[1])
         return buf, views
 
     def step_host(self, host_actions, host_buf, device_actions=None):

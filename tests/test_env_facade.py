@@ -141,3 +141,33 @@ def test_get_perfect_information(game):
         assert info['chips'] in ([1, 2], [2, 1]) and info['public_card'] is None and len(info['hand_cards'][0]) == 2
     if game == 'leduc-holdem':
         assert info['chips'] in ([1, 2], [2, 1]) and info['public_card'] is None and info['current_round'] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('game', ['uno', 'scout', 'leduc-holdem', 'limit-holdem', 'blackjack', 'no-limit-holdem'])
+def test_random_agent_draws_replay_exactly(game):
+    """examples/run_random.py with the facade: the legal ids come in the reference's insertion order (UNO hand order,
+    Scout enumeration order), so RandomAgent's np.random.choice picks the same actions as on the reference under the
+    same env seed and global numpy seed (tests/golden/legal_order.npz, recorded from the live reference)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'legal_order.npz'))
+    k = game.replace('-', '_')
+    ids, off, acts, pays = z[k + '_ids'], z[k + '_off'], z[k + '_actions'], z[k + '_payoffs']
+    env = rlcard_b200.make(game, {'seed': int(z['env_seed'])})
+    seen = []
+
+    class Agent(rlcard_b200.RandomAgent):
+        use_raw = False
+
+        def step(self, state):
+            i = len(seen)
+            assert list(state['legal_actions'].keys()) == ids[off[i]:off[i + 1]].tolist(), (game, 'decision', i)
+            a = rlcard_b200.RandomAgent.step(state)
+            seen.append(a)
+            return a
+    env.set_agents([Agent(env.num_actions) for _ in range(env.num_players)])
+    np.random.seed(int(z['np_seed']))
+    for ep in range(len(pays)):
+        _, payoffs = env.run(is_training=True)
+        np.testing.assert_array_equal(np.asarray(payoffs, np.float64), pays[ep], err_msg='%s episode %d' % (game, ep))
+    assert seen == acts.tolist()
