@@ -351,6 +351,30 @@ def bench_game(game, args, ctx, envs=None, steps=None, e2e_steps=None, headline=
                        'clock, max over ranks' % args.e2e_chunk}
         env2.check_errors()
         assert h_traj['done'].numpy().any(), 'e2e trajectory did not reach the host'
+        # ---- the same leg with the compact wire format (Leduc 4 B, Limit 12 B per env-step instead of 57 / 93): the chunk
+        # is re-encoded on the device, only the records cross PCIe; the consumer expands rows on demand (compact.expand)
+        if env2.compact_words():
+            h_pack = env2.alloc_host_compact(T)
+            for _ in range(min(W, 3) if headline else 1):
+                env2.rollout_random_host(T, h_pack, chunk=args.e2e_chunk, host_state=h_state, compact=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                env2.rollout_random_host(T, h_pack, chunk=args.e2e_chunk, host_state=h_state, compact=True)
+            torch.cuda.synchronize(dev)
+            barrier()
+            dtc = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+            d2hc = h_pack.numel() * 4 + state_bytes
+            e2e['compact'] = {'value': world * E * T * Ke / float(dtc.item()), 'unit': UNIT, 'h2d_bytes_per_step': state_bytes,
+                              'd2h_bytes_per_step': d2hc, 'ms_per_step': 1e3 * float(dtc.item()) / Ke,
+                              'pcie_gbs': (d2hc + state_bytes) * Ke / float(dtc.item()) / 1e9,
+                              'what': 'rollout_random_host(compact=True): %d-byte records per env-step re-encoded on the device '
+                                      '(rlc_compact_trajectory), expanded lazily on the host; expansion is not in the timed region'
+                                      % (4 * env2.compact_words())}
+            assert (h_pack.numpy()[..., -1] >> 19 & 1).any(), 'compact e2e trajectory did not reach the host'
+            del h_pack
         del h_traj, env2, h_state
 
     # ---- secondary: the per-step API driven by a host-resident agent (numpy uniform-legal policy), one

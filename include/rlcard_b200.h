@@ -260,6 +260,13 @@ int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T
  * key_len int32 [n] -> mt uint32 [625][n] in the layout of rlc_buffers.mt (624 state words + index). */
 int rlc_seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt, void *stream);
 
+/* Compact host wire format of a dense trajectory window (csrc/tu_compact.cu has the record layouts): [T][n] cells of
+ * obs + mask + action + player + done + payoffs -> out uint32 [T][n][words], words = rlc_compact_words(game) (Leduc 1,
+ * Limit Hold'em 3; 0 = the game has no compact format and rlc_compact_trajectory returns RLC_ENOTIMPL).  A host consumer
+ * behind PCIe fetches 4 / 12 bytes per env-step instead of 57 / 93 and expands rows on demand (rlcard_b200/compact.py). */
+int rlc_compact_words(int game_id);
+int rlc_compact_trajectory(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, uint32_t *out, void *stream);
+
 /* number of kernels this library has launched in this process (bench bookkeeping) */
 int64_t rlc_launch_count(void);
 

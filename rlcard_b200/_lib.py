@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_DIR, 'librlcard_b200.so')
+# RLC_SO_VARIANT=tma loads the measurement build whose tile flushes are TMA bulk copies (csrc/Makefile TMA=1)
+_VARIANT = os.environ.get('RLC_SO_VARIANT', '')
+SO_PATH = os.path.join(_DIR, 'librlcard_b200%s.so' % ('_' + _VARIANT if _VARIANT else ''))
 
 RLC_MAX_PLAYERS = 4
 GAME_IDS = {'blackjack': 0, 'leduc-holdem': 1, 'limit-holdem': 2, 'uno': 3, 'doudizhu': 4, 'scout': 5, 'no-limit-holdem': 6}
@@ -62,7 +64,7 @@ class RlcRlBuffers(C.Structure):
 EXPORTS = ['rlc_abi_version', 'rlc_last_error', 'rlc_game_info', 'rlc_upload_tables', 'rlc_reset', 'rlc_step',
            'rlc_observe', 'rlc_rollout_random', 'rlc_launch_count', 'rlc_judge_holdem', 'rlc_judge_leduc',
            'rlc_judge_doudizhu', 'rlc_encode_uno', 'rlc_dmc_collect', 'rlc_rl_feed', 'rlc_legal_ids', 'rlc_action_features',
-           'rlc_reorganize', 'rlc_seed_mt19937']
+           'rlc_reorganize', 'rlc_seed_mt19937', 'rlc_compact_words', 'rlc_compact_trajectory']
 
 _LIB = None
 
@@ -99,6 +101,8 @@ def lib():
         L.rlc_dmc_collect.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcDmcBuffers), vp]
         L.rlc_reorganize.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, C.POINTER(RlcRlBuffers), vp]
         L.rlc_seed_mt19937.argtypes = [vp, vp, i32, vp, vp]
+        L.rlc_compact_words.argtypes = [i32]
+        L.rlc_compact_trajectory.argtypes = [i32, C.POINTER(RlcTrajectory), i32, i32, i32, vp, vp]
         if L.rlc_abi_version() != ABI_VERSION:
             raise RlcError('%s has ABI %d, the Python side expects %d: rebuild (__graft_entry__.build())'
                            % (SO_PATH, L.rlc_abi_version(), ABI_VERSION))

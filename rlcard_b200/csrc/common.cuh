@@ -260,6 +260,57 @@ __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *til
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tile store in two halves, so that the copy engine can take the flush off the instruction stream:
+//   tile_store_begin   hands the (full, 16-byte aligned) tile to the destination
+//   tile_store_end     returns when the tile may be written again; the tile is all zero then
+// TMA = false (default, RLC_TMA_FLUSH = 0): begin = warp_tile_flush_full (LDS.128 + STS.128 zero + STG.128.cs per chunk and lane), end = nothing.
+// TMA = true (RLC_TMA_FLUSH = 1 builds it everywhere): begin = one cp.async.bulk.global.shared::cta (SASS UBLKCP.G.S) issued by lane 0 after the writer
+//   lanes have fenced their generic-proxy stores into the async proxy, L2 evict-first hint (the trajectory is written once
+//   and never re-read); end = cp.async.bulk.wait_group.read 0 by lane 0, then the lanes re-zero the tile.  The transition
+//   code that runs between begin and end overlaps the copy.
+// Measured on B200 (profiles/r02_tma_flush.md): only the tabulated Leduc rollout gains (0.0915 -> 0.0906 ms); the
+// register engines lose 0.5-12 % (fence + wait + re-zero sit on their latency-bound critical path), so only
+// k_rollout_leduc_fsm asks for TMA = true.
+// ------------------------------------------------------------------------------------------
+#ifndef RLC_TMA_FLUSH
+#define RLC_TMA_FLUSH 0
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int TILE_BYTES, bool TMA = (RLC_TMA_FLUSH != 0)>
+__device__ __forceinline__ void tile_store_begin(uint8_t *gdst, uint8_t *tile, int lane) {
+  if constexpr (TMA) {
+    static_assert(TILE_BYTES % 16 == 0, "bulk copies move whole 16-byte units");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     :: "l"(gdst), "r"(smem_u32(tile)), "r"(TILE_BYTES), "l"(pol) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else {
+    warp_tile_flush_full<TILE_BYTES>(gdst, tile, lane);
+  }
+}
+template <int TILE_BYTES, bool TMA = (RLC_TMA_FLUSH != 0)>
+__device__ __forceinline__ void tile_store_end(uint8_t *tile, int lane) {
+  if constexpr (TMA) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    constexpr int kChunks = TILE_BYTES / 16;
+#pragma unroll
+    for (int c0 = 0; c0 < kChunks; c0 += kWarp) {
+        const int c = c0 + lane;
+        if (c0 + kWarp <= kChunks || c < kChunks) reinterpret_cast<uint4 *>(tile)[c] = z;
+    }
+  } else {
+    (void)tile; (void)lane;
+  }
+}
+
 // per-env header words stored in front of the game words of the state
 struct EnvHeader {
     uint32_t episode;   // episodes started (0 = never reset); the running episode has index episode-1

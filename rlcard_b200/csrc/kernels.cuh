@@ -304,12 +304,12 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
         if constexpr (kStageMask) {
             uint8_t *gm = reinterpret_cast<uint8_t *>(p.t_mask) + (rowi - lane) * (size_t)G::A;
             if constexpr (ALL) {
-                if (full_warp) warp_tile_flush_full<EPW * G::A>(gm, mtile, lane);
+                if (full_warp) tile_store_begin<EPW * G::A>(gm, mtile, lane);
                 else warp_tile_flush(gm, mtile, nvalid * G::A, lane);
             } else if (p.t_mask) warp_tile_flush(gm, mtile, nvalid * G::A, lane);
         }
         if constexpr (ALL) {
-            if (full_warp) warp_tile_flush_full<EPW * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+            if (full_warp) tile_store_begin<EPW * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
             else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         } else {
             if (p.t_obs) warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
@@ -384,6 +384,15 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             }
         }
         if constexpr (kWarpDeal) g.warp_deal(ch, starts, lane);
+        if constexpr (ALL) {                                  // the tiles are free (and zero) again before the next rows
+            if (full_warp) {
+                if constexpr (kStageMask) tile_store_end<EPW * G::A>(mtile, lane);
+                tile_store_end<EPW * kRowBytes>(reinterpret_cast<uint8_t *>(tile), lane);
+#if RLC_TMA_FLUSH
+                __syncwarp();
+#endif
+            }
+        }
     }
     if (valid) {
         ChanceIO<Ch>::close(ch, p, i);

@@ -67,6 +67,32 @@ __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const u
     }
 }
 
+// rollout form of the row flush: begin hands the row to the destination, end makes the (zeroed) row writable again
+template <class G, class ObsT>
+__device__ __forceinline__ bool warp_row_store_begin(void *gobs, size_t row, ObsT *srow, int lane) {
+    constexpr int kBytes = G::OBS * (int)sizeof(ObsT);
+    uint8_t *dst = reinterpret_cast<uint8_t *>(gobs) + row * (size_t)kBytes;
+#if RLC_TMA_FLUSH
+    if constexpr (kBytes % 16 == 0) {
+        if ((reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) { tile_store_begin<kBytes>(dst, reinterpret_cast<uint8_t *>(srow), lane); return true; }
+    }
+#endif
+    if constexpr (G::kRowFlushFull && kBytes % 16 == 0) {
+        if ((reinterpret_cast<uintptr_t>(gobs) & 15u) == 0) { warp_tile_flush_full<kBytes>(dst, reinterpret_cast<uint8_t *>(srow), lane); return false; }
+    }
+    warp_tile_flush(dst, reinterpret_cast<uint8_t *>(srow), kBytes, lane);
+    return false;
+}
+template <class G, class ObsT>
+__device__ __forceinline__ void warp_row_store_end(ObsT *srow, bool pending, int lane) {
+#if RLC_TMA_FLUSH
+    constexpr int kBytes = G::OBS * (int)sizeof(ObsT);
+    if constexpr (kBytes % 16 == 0) { if (pending) { tile_store_end<kBytes>(reinterpret_cast<uint8_t *>(srow), lane); __syncwarp(); } }
+#else
+    (void)srow; (void)pending; (void)lane;
+#endif
+}
+
 template <class G, class ObsT>
 __device__ __forceinline__ void warp_flush_row(void *gobs, size_t row, ObsT *srow, int lane) {
     constexpr int kBytes = G::OBS * (int)sizeof(ObsT);
@@ -193,10 +219,11 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     __syncwarp();
     size_t rowi = env;
     for (int t = 0; t < p.T; t++, rowi += p.n) {
+        bool row_pending = false;
         if (p.t_obs) {
             g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
             __syncwarp();
-            warp_flush_row<G, ObsT>(p.t_obs, rowi, srow, lane);
+            row_pending = warp_row_store_begin<G, ObsT>(p.t_obs, rowi, srow, lane);
         }
         if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
@@ -215,6 +242,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
             h.t++; h.k++;
             over = g.over();
         }
+        if constexpr (EXT) { warp_row_store_end<G, ObsT>(srow, row_pending, lane); row_pending = false; }   // srow is reused below
         if (EXT && p.tm_row) {                                    // per-seat terminal states into the pool (env.py:161-164)
             int r = -1;
             if (over) {
@@ -243,6 +271,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
         __syncwarp();
         if (!EXT || a >= 0) cnt = g.legal(smask, scratch, lane);  // legal set of the state the next iteration emits
         __syncwarp();
+        warp_row_store_end<G, ObsT>(srow, row_pending, lane);
         if (lane == 0) {
             if (p.t_player) st_stream(p.t_player + rowi, pl);
             if (p.t_action) st_stream(p.t_action + rowi, a);

@@ -28,6 +28,9 @@ cudaError_t dispatch_doudizhu(int, int, int, const KParams &, cudaStream_t);
 cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes);
 cudaError_t judge_doudizhu(const uint8_t *, const int32_t *, int, uint32_t *, cudaStream_t);
 #endif
+#ifdef RLC_HAVE_COMPACT
+cudaError_t compact_trajectory(int, const rlc_trajectory *, int, size_t, uint32_t *, cudaStream_t);
+#endif
 #ifdef RLC_HAVE_DMC
 cudaError_t dmc_collect(const rlc_info &, const rlc_trajectory *, int, int, int, const rlc_dmc_buffers *, cudaStream_t);
 cudaError_t legal_ids(const rlc_info &, const void *, int, int, int32_t *, int32_t *, cudaStream_t);
@@ -287,6 +290,21 @@ int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T
     return judged(rlc::reorganize(kInfo[game_id], traj, obs_dtype, T, n, b, reinterpret_cast<cudaStream_t>(stream)));
 #else
     return fail(RLC_ENOTIMPL, "the transition collector is not in this build");
+#endif
+}
+
+int rlc_compact_words(int game_id) { return game_id == RLC_LEDUC ? 1 : (game_id == RLC_LIMIT ? 3 : 0); }
+
+int rlc_compact_trajectory(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, uint32_t *out, void *stream) {
+    if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
+    if (!traj || !out || T <= 0 || n <= 0) return fail(RLC_EINVAL, "null buffers or empty window");
+    if (!traj->obs || !traj->mask || !traj->action || !traj->player || !traj->done || !traj->payoffs)
+        return fail(RLC_EINVAL, "rlc_compact_trajectory needs every dense stream of the window");
+    if (rlc_compact_words(game_id) == 0) return fail(RLC_ENOTIMPL, "game %d has no compact wire format", game_id);
+#ifdef RLC_HAVE_COMPACT
+    return judged(rlc::compact_trajectory(game_id, traj, obs_dtype, (size_t)T * (size_t)n, out, reinterpret_cast<cudaStream_t>(stream)));
+#else
+    return fail(RLC_ENOTIMPL, "not in this build");
 #endif
 }
 

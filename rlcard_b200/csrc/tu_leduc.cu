@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
             row[byte_of(e.w, 1)] = (ObsT)1;
         }
         __syncwarp();
-        if constexpr (kFull) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+        if constexpr (kFull) tile_store_begin<32 * kRowBytes, true>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
         else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         // no barrier here: the transition below does not touch the tile, so its table look-ups overlap the flush; the
         // barrier that orders the flush's zeroing before the next row is written sits at the end of the step
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_leduc_fsm(const KParams p, co
             p.t_done[rowi] = over ? 1 : 0;
             st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
         }
+        if constexpr (kFull) tile_store_end<32 * kRowBytes, true>(reinterpret_cast<uint8_t *>(tile), lane);
         __syncwarp();
     }
     };

@@ -315,13 +315,27 @@ class VecEnv:
                 'action': mk((T, N), torch.int32), 'player': mk((T, N), torch.int32),
                 'done': mk((T, N), torch.uint8), 'payoffs': mk((T, N, self.num_players), torch.float32)}
 
-    def rollout_random_host(self, T, host_out, chunk=16, host_state=None):
+    def compact_words(self):
+        """uint32 words per env-step of the compact wire format (0 = this game has none)."""
+        return int(self.L.rlc_compact_words(self.gid))
+
+    def alloc_host_compact(self, T, pinned=True):
+        """Pinned host buffer for rollout_random_host(compact=True): uint32 (as int32) [T, N, words]."""
+        w = self.compact_words()
+        if w == 0:
+            raise _lib.RlcError('%s has no compact wire format' % self.name)
+        return torch.empty((T, self.num_envs, w), dtype=torch.int32, pin_memory=pinned)
+
+    def rollout_random_host(self, T, host_out, chunk=16, host_state=None, compact=False):
         """The Env.run loop with random agents for a HOST consumer (what examples/run_random.py does: the
         trajectories end up in host memory).  T env-steps per env are produced in chunks of ``chunk`` steps by
         rlc_rollout_random into two device staging buffers; while chunk c+1 is being simulated, chunk c is
         copied device->host into the pinned ``host_out`` tensors on a second stream.  If ``host_state`` (a pinned
         int32 tensor shaped like ``self.state``) is given, the packed env state is uploaded from it before the
         first chunk and written back after the last one, i.e. the caller owns the state in host memory.
+        ``compact=True`` (Leduc, Limit Hold'em): ``host_out`` is the tensor of alloc_host_compact; every chunk is
+        re-encoded on the device by rlc_compact_trajectory and only the 4 / 12-byte records cross PCIe
+        (rlcard_b200.compact.expand rebuilds the dense rows on the host, bit-exact).
         Returns after everything has landed in host memory."""
         dev = self.device
         chunk = max(1, min(int(chunk), int(T)))
@@ -330,6 +344,12 @@ class VecEnv:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_full = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_packed = None
+        if compact and self._stage_packed is None:
+            w = self.compact_words()
+            if w == 0:
+                raise _lib.RlcError('%s has no compact wire format' % self.name)
+            self._stage_packed = [torch.empty((chunk, self.num_envs, w), dtype=torch.int32, device=dev) for _ in range(2)]
         main = torch.cuda.current_stream(dev)
         keys = ('obs', 'mask', 'action', 'player', 'done', 'payoffs')
         with torch.cuda.device(dev):
@@ -342,11 +362,21 @@ class VecEnv:
                 if c >= 2:
                     main.wait_event(self._stage_free[b])            # the copy of chunk c-2 has left this buffer
                 self.rollout_random(tc, out=self._stage[b])
+                if compact:
+                    tr = RlcTrajectory()
+                    for k in keys:
+                        setattr(tr, k, self._stage[b][k].data_ptr())
+                    check(self.L.rlc_compact_trajectory(self.gid, C.byref(tr), DTYPE_F32 if self.obs_dtype == torch.float32 else DTYPE_U8,
+                                                        tc, self.num_envs, _ptr(self._stage_packed[b]), self._stream()))
+                    self.launches += 1
                 self._stage_full[b].record(main)
                 with torch.cuda.stream(self._copy_stream):
                     self._copy_stream.wait_event(self._stage_full[b])
-                    for k in keys:
-                        host_out[k][t0:t0 + tc].copy_(self._stage[b][k][:tc], non_blocking=True)
+                    if compact:
+                        host_out[t0:t0 + tc].copy_(self._stage_packed[b][:tc], non_blocking=True)
+                    else:
+                        for k in keys:
+                            host_out[k][t0:t0 + tc].copy_(self._stage[b][k][:tc], non_blocking=True)
                     self._stage_free[b].record(self._copy_stream)
                 t0 += tc
                 c += 1

@@ -269,6 +269,28 @@ def test_host_rollout_equals_device_rollout():
     assert torch.equal(h_state, a.state.cpu())
 
 
+@pytest.mark.parametrize('game', ['leduc-holdem', 'limit-holdem'])
+@pytest.mark.parametrize('obs_dtype', [torch.uint8, torch.float32])
+def test_compact_host_rollout_expands_to_dense_rows(game, obs_dtype):
+    """rollout_random_host(compact=True): the 4 / 12-byte records that cross PCIe expand on the host
+    (rlcard_b200.compact.expand) into exactly the dense trajectory a device-side rollout of the same envs produces."""
+    from rlcard_b200 import compact
+    n, T, seed = 4099, 70, 99                     # ragged batch, more steps than one chunk
+    a = rlcard_b200.VecEnv(game, n, seed=seed, obs_dtype=obs_dtype)
+    b = rlcard_b200.VecEnv(game, n, seed=seed, obs_dtype=obs_dtype)
+    a.reset(); b.reset()
+    ref = a.rollout_random(T)
+    packed = b.rollout_random_host(T, b.alloc_host_compact(T), chunk=16, compact=True)
+    assert packed.shape == (T, n, b.compact_words()) and packed.numel() * 4 * 4 < ref['obs'].numel()
+    got = compact.expand(game, packed.numpy())
+    for k in ('obs', 'mask', 'action', 'player', 'done', 'payoffs'):
+        want = to_np(ref[k])
+        assert np.array_equal(got[k].astype(want.dtype), want), (game, k)
+    assert torch.equal(a.state, b.state)
+    with pytest.raises(rlcard_b200.RlcError):
+        rlcard_b200.VecEnv('uno', 64, seed=1).alloc_host_compact(4)
+
+
 @pytest.mark.parametrize('game', GAMES)
 def test_step_api_equals_fused_rollout(game):
     """Env.step kernel == fused rollout kernel: feeding the rollout's actions through step() (auto reset)
