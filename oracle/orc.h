@@ -35,6 +35,7 @@ typedef struct orc_chance {
      * k = env-steps taken so far, dom = 1 inside a step / 2 reset outside a step, R = chain register,
      * draw = index of the next fresh word */
     uint32_t key0, key1, env_id, k, dom, R, draw;
+    uint32_t episode;       /* philox: ordinal (1, 2, ...) of the episode being dealt: deal words are keyed by it */
     /* numpy-legacy MT19937 (np.random.RandomState) */
     uint32_t mt[624]; int mti;
     /* optional recording of the draws made (any kind) */
@@ -44,6 +45,7 @@ typedef struct orc_chance {
 uint32_t orc_below(orc_chance *ch, uint32_t n);          /* uniform in [0, n) */
 uint32_t orc_chain(orc_chance *ch, uint32_t n);          /* philox: peeled off the step's base word; else = orc_below */
 uint32_t orc_philox_begin_step(orc_chance *ch, uint32_t k, uint32_t n_legal);   /* -> index of the policy's action */
+uint32_t orc_deal_below(orc_chance *ch, uint32_t j, uint32_t n);   /* philox: mulhi(deal word D_j of ch->episode, n) */
 void orc_philox_begin_reset(orc_chance *ch, uint32_t k);
 void orc_shuffle_u8(orc_chance *ch, uint8_t *x, int n);   /* numpy legacy list shuffle */
 void orc_shuffle_tail_u8(orc_chance *ch, uint8_t *x, int n, int tail);

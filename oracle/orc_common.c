@@ -75,7 +75,9 @@ void orc_philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint32_t
  *   policy                   index among the n legal actions = mulhi(W_k, n); chain register R = lo32(W_k * n)
  *   chain(m)                 v = mulhi(R, m), R = lo32(R * m)
  *   fresh draw j of step k   F_j = (k, j >> 2, env, dom 1)[j & 3]
- *   reset outside a step     F_j = (k, j >> 2, env, dom 2)[j & 3]; R starts as F_0, fresh draws at j = 1 */
+ *   reset outside a step     F_j = (k, j >> 2, env, dom 2)[j & 3]; R starts as F_0, fresh draws at j = 1
+ *   deal word j of episode E D_j = (E, j >> 2, env, dom 3)[j & 3], E = 1, 2, ... the ordinal of the episode being dealt
+ *                            (Limit Hold'em: the deal is a pure function of (seed, env, E)) */
 uint32_t orc_philox_word(uint32_t k0, uint32_t k1, uint32_t env_id, uint32_t c0, uint32_t c1, uint32_t dom, uint32_t word) {
     uint32_t ctr[4] = { c0, c1, env_id, dom }, out[4];
     orc_philox4x32_10(ctr, k0, k1, out);
@@ -86,6 +88,12 @@ uint32_t orc_philox_begin_step(orc_chance *ch, uint32_t k, uint32_t n_legal) {
     ch->k = k; ch->dom = 1u; ch->draw = 0u;
     ch->R = w * n_legal;
     return (uint32_t)(((uint64_t)w * n_legal) >> 32);
+}
+uint32_t orc_deal_below(orc_chance *ch, uint32_t j, uint32_t n) {
+    uint32_t w = orc_philox_word(ch->key0, ch->key1, ch->env_id, ch->episode, j >> 2, 3u, j & 3u);
+    uint32_t v = (uint32_t)(((uint64_t)w * n) >> 32);
+    if (ch->rec) { if (ch->rec_len < ch->rec_cap) ch->rec[ch->rec_len] = (uint8_t)v; ch->rec_len++; }
+    return v;
 }
 void orc_philox_begin_reset(orc_chance *ch, uint32_t k) {
     ch->k = k; ch->dom = 2u; ch->draw = 1u;
@@ -190,6 +198,7 @@ int64_t orc_env_tape_pos(const orc_env *e) { return e->ch.tape_pos; }
 int orc_env_tape_err(const orc_env *e) { return e->ch.tape_err; }
 int orc_env_reset(orc_env *e) {
     e->t = 0;
+    e->ch.episode++;
     if (e->ch.kind == ORC_CHANCE_PHILOX) orc_philox_begin_reset(&e->ch, e->k);
     return e->vt->reset(e->st, &e->ch);
 }
@@ -242,6 +251,7 @@ typedef struct {
 static void env_new_episode(orc_env *e, int first) {
     if (first) { orc_philox_begin_reset(&e->ch, e->k); e->episode = 0; }
     else e->episode++;
+    e->ch.episode = e->episode + 1u;
     e->t = 0;
     e->vt->reset(e->st, &e->ch);
 }

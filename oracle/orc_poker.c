@@ -207,8 +207,8 @@ static int limit_reset(void *s, orc_chance *ch) {
     memcpy(g->shown_raise_nums, g->raise_nums, sizeof g->raise_nums);   /* stale list seen by the reset() state */
     for (int i = 0; i < 52; i++) g->deck[i] = (uint8_t)i;               /* utils/utils.py:34-43 == card2index.json */
     int sb;
-    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: three words deal nine cards + blind */
-        uint32_t x1 = orc_below(ch, 52u * 51u * 50u), x2 = orc_below(ch, 49u * 48u * 47u), x3 = orc_below(ch, 46u * 45u * 44u * 2u);
+    if (ch->kind == ORC_CHANCE_PHILOX) {                 /* throughput spec: three deal words (keyed by the episode ordinal) deal nine cards + blind */
+        uint32_t x1 = orc_deal_below(ch, 0u, 52u * 51u * 50u), x2 = orc_deal_below(ch, 1u, 49u * 48u * 47u), x3 = orc_deal_below(ch, 2u, 46u * 45u * 44u * 2u);
         uint32_t z = x3 >> 1;
         int j[9] = { (int)(x1 / 2550), (int)((x1 / 50) % 51), (int)(x1 % 50), (int)(x2 / 2256), (int)((x2 / 47) % 48),
                      (int)(x2 % 47), (int)(z / 1980), (int)((z / 44) % 45), (int)(z % 44) };

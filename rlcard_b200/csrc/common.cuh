@@ -22,6 +22,10 @@ constexpr int kWarp = 32;
 // env, 2))[j & 3]; its chain register starts as R = F_0 and its fresh draws at j = 1.
 // chain() is only used where the product of the ranges stays tiny (Leduc: cnt * 120 * 2 <= 960), so the
 // non-uniformity of the last value is below 2^-22.
+//   deal word   D_j = Philox(ctr = (E, j >> 2, env, 3))[j & 3], E = 1, 2, ... the ordinal of the episode being dealt.
+// Games with kEpisodeDeal (Limit Hold'em) draw their whole deal from D_0..D_3: the deal is then a pure function of
+// (seed, global env id, episode ordinal) -- not of the step at which the previous episode happened to end -- so the
+// fused rollout can have a dealer warp prepare the deals of future episodes while the env warp is still playing.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1,
@@ -40,7 +44,7 @@ __device__ __forceinline__ uint32_t sel4(uint32_t a, uint32_t b, uint32_t c, uin
     const uint32_t lo = (i & 1u) ? b : a, hi = (i & 1u) ? d : c;
     return (i & 2u) ? hi : lo;
 }
-enum { kDomBase = 0, kDomStep = 1, kDomReset = 2 };
+enum { kDomBase = 0, kDomStep = 1, kDomReset = 2, kDomDeal = 3 };
 
 // ------------------------------------------------------------------------------------------
 // Chance sources.  All engines draw through below(n) (uniform in [0,n)); skip_fy(i_hi, i_lo)
@@ -54,8 +58,13 @@ struct ChancePhilox {
     uint32_t b0, b1, b2, b3, btag;     // cached base block (index k >> 2)
     uint32_t x0, x1, x2, x3, xtag;     // cached fresh block of the current (k, dom)
     uint32_t R, d; int err;
+    uint32_t ep;                       // ordinal of the episode being dealt (deal words)
+    __device__ __forceinline__ void begin_episode(uint32_t e) { ep = e; }
+    __device__ __forceinline__ void deal_words(uint32_t &d0, uint32_t &d1, uint32_t &d2, uint32_t &d3) const {
+        philox4x32_10(ep, 0u, env, (uint32_t)kDomDeal, k0, k1, d0, d1, d2, d3);
+    }
     __device__ __forceinline__ void init(uint64_t seed, uint32_t env_) {
-        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; err = 0; d = 0; k = 0; dom = kDomStep; R = 0;
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); env = env_; err = 0; d = 0; k = 0; dom = kDomStep; R = 0; ep = 0;
         b0 = b1 = b2 = b3 = x0 = x1 = x2 = x3 = 0; btag = xtag = 0xffffffffu;
     }
     // step k begins: returns the base word W_k (policy word)
@@ -99,6 +108,7 @@ struct ChanceTape {
     __device__ __forceinline__ uint32_t begin_step(uint32_t) { return 0u; }
     __device__ __forceinline__ void seed_chain(uint32_t, uint32_t) {}
     __device__ __forceinline__ void begin_reset(uint32_t) {}
+    __device__ __forceinline__ void begin_episode(uint32_t) {}
 };
 
 // np.random.RandomState (MT19937) with numpy's legacy bounded draws: mask-and-reject on 32-bit
@@ -136,6 +146,7 @@ struct ChanceMt {
     __device__ __forceinline__ uint32_t begin_step(uint32_t) { return 0u; }
     __device__ __forceinline__ void seed_chain(uint32_t, uint32_t) {}
     __device__ __forceinline__ void begin_reset(uint32_t) {}
+    __device__ __forceinline__ void begin_episode(uint32_t) {}
 };
 
 // RandomState.shuffle on a list: for i = n-1 .. 1: j = below(i+1); swap(x[i], x[j]).

@@ -233,6 +233,7 @@ __device__ __forceinline__ uint32_t holdem_strength_masks(const uint32_t (&s)[4]
 struct Limit {
     static constexpr int kGameId = 2, P = 2, A = 4, OBS = 72, GAME_WORDS = 4, MASK_WORDS = 1;
     static constexpr bool kUsesChain = false;   // reset draws ride on the policy word (common.cuh chain())
+    static constexpr bool kEpisodeDeal = true;  // throughput-mode deals are keyed by the episode ordinal (common.cuh deal words)
     static constexpr int kMaxResetDraws = 52;
     static constexpr int kRolloutMinEpw = 32;    // measured: fewer envs per warp only adds idle lanes (kernels.cuh)
     static constexpr bool kHasApply = false;
@@ -272,8 +273,10 @@ struct Limit {
     // games/limitholdem/game.py:46-103: only the last 9 deck positions are ever popped
     template <class Ch> __device__ __forceinline__ void reset(Ch &ch) {
         int j[9], sb;                                          // swap partners of positions 51..43
-        if constexpr (Ch::kKind == 0) {                        // throughput: three words deal nine cards + blind
-            const uint32_t x1 = ch.below(52u * 51u * 50u), x2 = ch.below(49u * 48u * 47u), x3 = ch.below(46u * 45u * 44u * 2u);
+        if constexpr (Ch::kKind == 0) {                        // throughput: three deal words (keyed by the episode ordinal,
+            uint32_t d0, d1, d2, d3;                           // common.cuh) give nine cards + blind
+            ch.deal_words(d0, d1, d2, d3);
+            const uint32_t x1 = __umulhi(d0, 52u * 51u * 50u), x2 = __umulhi(d1, 49u * 48u * 47u), x3 = __umulhi(d2, 46u * 45u * 44u * 2u);
             j[0] = (int)(x1 / 2550u); j[1] = (int)((x1 / 50u) % 51u); j[2] = (int)(x1 % 50u);
             j[3] = (int)(x2 / 2256u); j[4] = (int)((x2 / 47u) % 48u); j[5] = (int)(x2 % 47u);
             const uint32_t z = x3 >> 1;
@@ -308,21 +311,27 @@ struct Limit {
         rn = (rn & ~(7u << (3 * rc))) | ((uint32_t)r.have_raised << (3 * rc));   // game.py:133
         if (r.not_raise_num >= 2) { rc++; r.start(r.pointer, 0, 0); }
     }
+    // who wins a showdown of this deal: 0 seat 0, 1 seat 1, 2 split (judger.py:11-108 over utils.py:526-614)
+    __device__ __forceinline__ int showdown_outcome() const {
+        uint32_t bd[4] = {0, 0, 0, 0};                               // the five board cards are shared by both hands
+#pragma unroll
+        for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
+        uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
+        holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
+        holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
+        const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
+        return s0 > s1 ? 0 : (s1 > s0 ? 1 : 2);
+    }
     // game.py:233-243, judger.py:11-108 for two players: winner takes min(chips) from the loser
     __device__ __forceinline__ void payoffs(float *out) const {
         // random Limit play mostly ends by a fold (a showdown needs eight actions without one), so the evaluator stays
         // behind a branch that whole warps skip; inside, it is branch free
-        int w0 = fold1, w1 = fold0;
-        if (fold0 + fold1 != 1) {
-            uint32_t bd[4] = {0, 0, 0, 0};                           // the five board cards are shared by both hands
-#pragma unroll
-            for (int k = 4; k < 9; k++) holdem_add_card(bd, card[k]);
-            uint32_t m0[4] = { bd[0], bd[1], bd[2], bd[3] }, m1[4] = { bd[0], bd[1], bd[2], bd[3] };
-            holdem_add_card(m0, card[0]); holdem_add_card(m0, card[2]);
-            holdem_add_card(m1, card[1]); holdem_add_card(m1, card[3]);
-            const uint32_t s0 = holdem_strength_masks(m0), s1 = holdem_strength_masks(m1);
-            w0 = s0 >= s1; w1 = s1 >= s0;
-        }
+        int oc = fold1 ? 0 : 1;
+        if (fold0 + fold1 != 1) oc = showdown_outcome();
+        payoffs_given(out, oc);
+    }
+    __device__ __forceinline__ void payoffs_given(float *out, int outcome) const {
+        const int w0 = outcome != 1, w1 = outcome != 0;
         const int pot = min(chips0, chips1);
         float p0 = 0.f;
         if (w0 != w1) p0 = w0 ? (float)pot : -(float)pot;

@@ -75,6 +75,7 @@ __device__ __forceinline__ void game_store(const G &g, uint32_t *st, size_t n, s
 template <class G, class Ch>
 __device__ __forceinline__ void new_episode(G &g, Ch &ch, EnvHeader &h) {
     h.episode++; h.t = 0;
+    ch.begin_episode(h.episode);          // deal words are keyed by the episode ordinal (games with kEpisodeDeal)
     g.reset(ch);
 }
 

@@ -30,6 +30,7 @@ struct WarpChance {
     __device__ __forceinline__ void skip_fy(int a, int b) { if (lane == 0) ch.skip_fy(a, b); }
     __device__ __forceinline__ void begin_step(uint32_t k) { if (lane == 0) (void)ch.begin_step(k); }
     __device__ __forceinline__ void begin_reset(uint32_t k) { if (lane == 0) ch.begin_reset(k); }
+    __device__ __forceinline__ void begin_episode(uint32_t e) { if (lane == 0) ch.begin_episode(e); }
     __device__ __forceinline__ int err() { return __shfl_sync(kFull, ch.err, 0); }
 };
 template <class Ch>

@@ -2,7 +2,270 @@
 #include "game_poker.cuh"
 #include "kernels.cuh"
 namespace rlc {
+
+// ==========================================================================================
+// Warp-specialised Limit Hold'em rollout (throughput mode, every trajectory stream, whole warps).
+//
+// 16 384 envs are 512 warps for the 592 warp schedulers of a B200: with a thread per env the kernel is bound by the
+// latency of ONE warp's dependent instruction chain per env-step (obs row, flush, legal set, policy, betting transition,
+// and -- episodes last ~3 steps -- a deal and now and then a showdown for some lane), at IPC 0.33.  Here every group of 32
+// envs is played by FOUR warps that run concurrently (lane = env in each of them), connected by rings in shared memory:
+//   ENV    the transition only: legal set -> policy (Philox) -> betting step -> payoffs -> next deal popped from the deal
+//          ring; publishes a 3-word snapshot per env-step (cards, legal nibble, player, public-card count, raise counters)
+//          and writes the action / done / payoffs streams;
+//   EMIT   turns snapshots into trajectory rows: the 72-element obs row (tile in shared memory, 128-bit streaming stores),
+//          the legal mask and the player stream;
+//   DEAL   keeps the deal ring full: episode E of an env is a pure function of (seed, env, E) (deal words, common.cuh):
+//          Philox block -> nine-card Fisher-Yates traceback -> 64-bit record (nine 6-bit cards + small blind);
+//   JUDGE  runs the 7-card evaluator on every record behind the dealer (who wins if nobody folds), so that a showdown costs
+//          the ENV warp one shared-memory read.
+// Counters (deals produced / judged / released, steps published / emitted) live in shared memory, accessed volatile with
+// __threadfence_block() between payload and counter; a warp only spins when it overtakes its producer.  Roles are rotated
+// over the warp slots by block index so that every scheduler of an SM hosts a mix of roles.  Results are identical to
+// k_rollout<Limit, ChancePhilox, ...>: same engine functions (game_poker.cuh), same deal words.
+// ==========================================================================================
+constexpr int kWsWarps = 4;
+constexpr int kRing = 8;        // deals in flight per env
+constexpr int kSnap = 4;        // env-steps ENV may run ahead of EMIT
+constexpr int kPol = 2;         // policy blocks (4 env-steps each) in flight per env
+
+__device__ __forceinline__ uint2 limit_pack_cards(const Limit &g) {
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) lo |= (uint32_t)g.card[k] << (6 * k);
+#pragma unroll
+    for (int k = 0; k < 4; k++) hi |= (uint32_t)g.card[5 + k] << (6 * k);
+    return make_uint2(lo, hi);
+}
+__device__ __forceinline__ void limit_unpack_cards(Limit &g, uint2 d) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.card[k] = (int)bf_get(d.x, 6 * k, 6);
+#pragma unroll
+    for (int k = 0; k < 4; k++) g.card[5 + k] = (int)bf_get(d.y, 6 * k, 6);
+}
+// the part of Limit::reset after the cards and the blind are known (game.py:71-103)
+__device__ __forceinline__ void limit_open_episode(Limit &g, int sb) {
+    g.chips0 = sb == 0 ? 1 : 2; g.chips1 = sb == 0 ? 2 : 1;
+    g.fold0 = g.fold1 = 0; g.rc = 0;
+    g.r.start(sb, g.chips0, g.chips1);
+    g.rn_shown = g.rn;                                       // Q-LH1
+    g.rn = 0;
+}
+struct LimitWsSmem {                 // per block (= one group of 32 envs), after the obs tile
+    static constexpr int kDeal = 0;                                   // uint2 [kRing][32]        DEAL -> ENV
+    static constexpr int kSnapBuf = kDeal + kRing * 32 * 8;           // uint32 [kSnap][3][32]    ENV -> EMIT
+    static constexpr int kPolBuf = kSnapBuf + kSnap * 3 * 32 * 4;     // uint32 [kPol][4][32]     DEAL -> ENV (policy words)
+    static constexpr int kMail = kPolBuf + kPol * 4 * 32 * 4;         // uint32 [4][32]           ENV -> JUDGE (showdown requests)
+    static constexpr int kCounters = kMail + 4 * 32 * 4;              // per lane: filled, released, pol_filled, pol_released, mail_state
+    static constexpr int kBytes = kCounters + 5 * 32 * 4 + 16;        // + pub, emitted, stop
+};
+
+template <class ObsT>
+__global__ void __launch_bounds__(32 * kWsWarps) k_rollout_limit_ws(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = 32 * kRowBytes;
+    uint8_t *sm = reinterpret_cast<uint8_t *>(smem_raw);
+    uint8_t *ws = sm + kTileBytes;
+    volatile uint2 *ring = reinterpret_cast<volatile uint2 *>(ws + LimitWsSmem::kDeal);
+    volatile uint32_t *snap = reinterpret_cast<volatile uint32_t *>(ws + LimitWsSmem::kSnapBuf);
+    volatile uint32_t *pol = reinterpret_cast<volatile uint32_t *>(ws + LimitWsSmem::kPolBuf);
+    volatile uint32_t *mail = reinterpret_cast<volatile uint32_t *>(ws + LimitWsSmem::kMail);
+    volatile uint32_t *filled = reinterpret_cast<volatile uint32_t *>(ws + LimitWsSmem::kCounters);   // deals produced
+    volatile uint32_t *released = filled + 32;                            // deals whose episode is over
+    volatile uint32_t *pol_filled = released + 32, *pol_released = pol_filled + 32;
+    volatile uint32_t *mail_state = pol_released + 32;                    // 1: a showdown waits for the JUDGE lane
+    volatile uint32_t *pub = mail_state + 32, *emitted = pub + 1, *stop = pub + 2;
+    const int lane = threadIdx.x & 31;
+    const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) % kWsWarps);   // 0 ENV, 1 EMIT, 2 DEAL, 3 JUDGE
+    const size_t i = (size_t)blockIdx.x * 32 + lane;                     // the launcher guarantees n % 32 == 0
+    if (threadIdx.x < 32) {
+        filled[lane] = 0; released[lane] = 0; pol_filled[lane] = 0; pol_released[lane] = 0; mail_state[lane] = 0;
+        if (lane == 0) { *pub = 0; *emitted = 0; *stop = 0; }
+    }
+    __syncthreads();
+
+    if (role == 2) {                                                     // ---- DEAL: policy blocks first, then deals
+        const uint32_t base_ep = p.state[i];                             // episodes this env has started so far
+        const uint32_t q0 = p.state[2 * p.n + i] >> 2;                   // first policy block the env will ask for (k >> 2)
+        ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
+        uint32_t f = 0, pf = 0;
+        while (*stop == 0) {
+            const bool want_pol = pf - pol_released[lane] < (uint32_t)kPol;
+            if (want_pol) {
+                uint32_t b0, b1, b2, b3;
+                philox4x32_10(q0 + pf, 0u, ch.env, (uint32_t)kDomBase, ch.k0, ch.k1, b0, b1, b2, b3);
+                volatile uint32_t *dst = pol + (pf % kPol) * 128 + lane;
+                dst[0] = b0; dst[32] = b1; dst[64] = b2; dst[96] = b3;
+                __threadfence_block();
+                pf++;
+                pol_filled[lane] = pf;
+            }
+            const bool room = f - released[lane] < (uint32_t)kRing;
+            if (room) {
+                Limit g; g.rn = 0;
+                ch.begin_episode(base_ep + f + 1u);
+                g.reset(ch);
+                const uint2 d = limit_pack_cards(g);
+                const int slot = (int)(f % kRing) * 32 + lane;
+                ring[slot].x = d.x | ((uint32_t)g.r.pointer << 30); ring[slot].y = d.y;
+                __threadfence_block();
+                f++;
+                filled[lane] = f;
+            }
+            if (!__any_sync(0xffffffffu, room || want_pol)) __nanosleep(100);
+        }
+        return;
+    }
+    if (role == 3) {                                                     // ---- JUDGE: showdowns on request
+        for (;;) {
+            const uint32_t stopping = *stop;
+            const bool work = mail_state[lane] != 0;
+            if (work) {
+                __threadfence_block();
+                const volatile uint32_t *mb = mail + lane;
+                uint2 d; d.x = mb[0]; d.y = mb[32];
+                const uint32_t cell = mb[64], pot = mb[96];
+                Limit g;
+                limit_unpack_cards(g, d);
+                const int oc = g.showdown_outcome();
+                const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * (float)pot;
+                st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + ((size_t)(cell / 32u) * p.n + (size_t)blockIdx.x * 32 + (cell & 31u)),
+                          make_float2(p0, -p0));
+                mail_state[lane] = 0;
+            }
+            if (!__any_sync(0xffffffffu, work)) { if (stopping) break; __nanosleep(200); }
+        }
+        return;
+    }
+    if (role == 1) {                                                     // ---- EMIT
+        ObsT *tile = reinterpret_cast<ObsT *>(sm);
+        ObsT *row = tile + lane * Limit::OBS;
+        warp_tile_zero(reinterpret_cast<uint8_t *>(tile), kTileBytes, lane);
+        __syncwarp();
+        uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + (i - lane) * (size_t)kRowBytes;
+        const size_t obs_step = p.n * (size_t)kRowBytes;
+        size_t rowi = i;
+        for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
+            while (*pub <= (uint32_t)t) { }
+            __threadfence_block();
+            const volatile uint32_t *sp = snap + (t % kSnap) * 96 + lane;
+            const uint32_t c_lo = sp[0], c_hi = sp[32], meta = sp[64];
+            // envs/limitholdem.py:40-71 from the packed fields
+            const uint32_t seat = (meta >> 4) & 1u, npub = (meta >> 5) & 7u;
+            row[(c_lo >> (6 * seat)) & 63u] = (ObsT)1;
+            row[(c_lo >> (12 + 6 * seat)) & 63u] = (ObsT)1;
+            if (npub > 0) { row[(c_lo >> 24) & 63u] = (ObsT)1; row[c_hi & 63u] = (ObsT)1; row[(c_hi >> 6) & 63u] = (ObsT)1; }
+            if (npub > 3) row[(c_hi >> 12) & 63u] = (ObsT)1;
+            if (npub > 4) row[(c_hi >> 18) & 63u] = (ObsT)1;
+#pragma unroll
+            for (int k = 0; k < 4; k++) row[52 + 5 * k + ((meta >> (8 + 3 * k)) & 7u)] = (ObsT)1;
+            __syncwarp();
+            if (lane == 0) *emitted = (uint32_t)t + 1u;                  // every lane has consumed its snapshot: ENV may reuse the slot
+            tile_store_begin<kTileBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+            const uint32_t m[1] = { meta & 15u };
+            write_mask_row<Limit>(reinterpret_cast<uint8_t *>(p.t_mask), rowi, m);
+            st_stream(p.t_player + rowi, (int)seat);
+            tile_store_end<kTileBytes>(reinterpret_cast<uint8_t *>(tile), lane);
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---- ENV
+    Limit g; EnvHeader h; int err = 0;
+    h.load(p.state, p.n, i);
+    g.load(p.state + kHeaderWords * p.n, p.n, i);
+    uint2 cards = limit_pack_cards(g);
+    uint32_t popped = 0;                                                 // deals taken from the ring by this lane
+    const uint32_t q0 = h.k >> 2;
+    uint32_t bq = 0xffffffffu, b0 = 0, b1 = 0, b2 = 0, b3 = 0;           // policy block held in registers (index relative to q0)
+    auto pop_deal = [&]() {
+        released[lane] = popped;                                         // the slots of the finished episodes may be reused
+        while (filled[lane] <= popped) { }
+        __threadfence_block();
+        const int slot = (int)(popped % kRing) * 32 + lane;
+        const uint32_t x = ring[slot].x;
+        cards = make_uint2(x & 0x3fffffffu, ring[slot].y);
+        popped++;
+        h.episode++; h.t = 0;
+        limit_open_episode(g, (int)((x >> 30) & 1u));
+    };
+    if (h.episode == 0 || g.over()) pop_deal();
+    ChancePhilox nochance; nochance.init(0, 0);
+    for (int t = 0; t < p.T; t++) {
+        uint32_t m[1];
+        g.legal(m);
+        {   // publish the snapshot of this env-step
+            while ((uint32_t)t - *emitted >= (uint32_t)kSnap) { }
+            const uint32_t shown = h.t == 0 ? g.rn_shown : g.rn;           // Q-LH1: the reset() state shows last episode's list
+            volatile uint32_t *sp = snap + (t % kSnap) * 96 + lane;
+            sp[0] = cards.x; sp[32] = cards.y;
+            sp[64] = (m[0] & 15u) | ((uint32_t)g.r.pointer << 4) | ((uint32_t)g.n_public() << 5) | (shown << 8);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *pub = (uint32_t)t + 1u;
+        }
+        const uint32_t q = (h.k >> 2) - q0;                               // policy word W_k from the DEAL warp's blocks
+        if (q != bq) {
+            while (pol_filled[lane] <= q) { }
+            __threadfence_block();
+            const volatile uint32_t *src = pol + (q % kPol) * 128 + lane;
+            b0 = src[0]; b1 = src[32]; b2 = src[64]; b3 = src[96];
+        }
+        const uint32_t word = sel4(b0, b1, b2, b3, h.k & 3u);
+        const size_t rowi = (size_t)t * p.n + i;
+        int cnt;
+        const int a = pick_action<Limit>(m, word, cnt);
+        st_stream(p.t_action + rowi, a);
+        if (q != bq) { bq = q; pol_released[lane] = q + 1u; }            // the block is in registers (its words were just used): slot free
+        g.step(a, nochance, err);
+        h.t++; h.k++;
+        const bool over = g.over();
+        p.t_done[rowi] = over ? 1 : 0;
+        if (over) {
+            if (g.fold0 + g.fold1 == 1) {
+                float pay[2];
+                g.payoffs_given(pay, g.fold1 ? 0 : 1);
+                st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
+            } else {                                                      // showdown: hand the cell to the JUDGE lane
+                while (mail_state[lane] != 0) { }
+                volatile uint32_t *mb = mail + lane;
+                mb[0] = cards.x; mb[32] = cards.y; mb[64] = (uint32_t)t * 32u + (uint32_t)lane; mb[96] = (uint32_t)min(g.chips0, g.chips1);
+                __threadfence_block();
+                mail_state[lane] = 1;
+            }
+            pop_deal();
+        } else st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(0.f, 0.f));
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) *stop = 1;
+    limit_unpack_cards(g, cards);
+    h.store(p.state, p.n, i);
+    g.store(p.state + kHeaderWords * p.n, p.n, i);
+    if (err && p.err) p.err[i] |= err;
+}
+
+template <class ObsT>
+static cudaError_t launch_limit_ws(const KParams &p, cudaStream_t s) {
+    constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
+    const size_t smem = 32 * kRowBytes + LimitWsSmem::kBytes;
+    k_rollout_limit_ws<ObsT><<<(unsigned)(p.n / 32), 32 * kWsWarps, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t dispatch_limit(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t s) {
+    // the bench / training case (throughput mode, every trajectory stream, whole warps, aligned rows)
+    // opt-in (RLC_LIMIT_WS=1): measured on B200 at 16 384 envs it is 2 % faster than the generic kernel (0.1045 vs 0.1067 ms,
+    // profiles/r02_limit_ws.md) -- the ENV warp's 175-instruction chain still sets the pace -- which does not pay for four
+    // spin-coupled warps per group, so the generic kernel stays the default
+    const char *ws = getenv("RLC_LIMIT_WS");
+    if (ws && ws[0] == '1' && op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & kFlagNoFsm) && p.n % 32 == 0 && p.t_obs &&
+        p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs) {
+        if (obs_dtype == RLC_U8 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0) return launch_limit_ws<uint8_t>(p, s);
+        if (obs_dtype == RLC_F32 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0) return launch_limit_ws<float>(p, s);
+    }
     return dispatch_game<Limit>(op, chance, obs_dtype, p, s);
 }
 

@@ -448,6 +448,23 @@ def test_partial_streams_and_unaligned_batches(game):
     odd.check_errors()
 
 
+@pytest.mark.timeout(300)
+def test_limit_warp_specialised_rollout_equals_oracle(monkeypatch):
+    """RLC_LIMIT_WS=1: the four-role Limit rollout (ENV / EMIT / DEAL / JUDGE warps coupled by shared-memory rings,
+    tu_limit.cu) gives the oracle's trajectory, over two launches (episodes under way at the launch boundary)."""
+    monkeypatch.setenv('RLC_LIMIT_WS', '1')
+    n, T, seed = 2048, 48, 606
+    env = rlcard_b200.VecEnv('limit-holdem', n, seed=seed)
+    orc = oracle.OracleVec('limit-holdem', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (launch, k)
+    env.check_errors()
+
+
 THREAD_GAMES = [g for g in GAMES if g not in ('doudizhu', 'scout')]
 
 
