@@ -61,11 +61,18 @@ class Env:
     def __init__(self, env_id, config=None, device='cuda:0'):
         cfg = dict(DEFAULT_CONFIG)
         cfg.update(config or {})
+        # envs/env.py:30-39 forwards game_* keys to game.configure (blackjack, leduc, limit, no-limit), envs/scout.py:14-28
+        # reads hand_size / rank_count.  The kernels are built for the reference's default geometry only: anything else is
+        # refused loudly (never silently ignored).
+        defaults = {'game_num_players': {'blackjack': 1, 'doudizhu': 3, 'scout': 4}.get(env_id, 2), 'game_num_decks': 1,
+                    'hand_size': 16, 'rank_count': 10, 'chips_for_each': 100, 'dealer_id': None}
         for k, v in cfg.items():
-            if k.startswith('game_'):
-                default = {'game_num_players': {'blackjack': 1}.get(env_id, 2), 'game_num_decks': 1}.get(k)
-                if default is not None and v != default:
-                    raise NotImplementedError('%s=%r: only the reference default (%r) is built' % (k, v, default))
+            if k in ('allow_step_back', 'seed'):
+                continue
+            if k not in defaults:
+                raise ValueError('unknown config key %r' % k)
+            if v != defaults[k]:
+                raise NotImplementedError('%s=%r: only the reference default (%r) is built' % (k, v, defaults[k]))
         self.name = env_id
         self.allow_step_back = cfg['allow_step_back']
         if self.allow_step_back:

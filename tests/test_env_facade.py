@@ -128,6 +128,14 @@ def test_unsupported_variants_raise():
         rlcard_b200.make('blackjack', config={'game_num_players': 5})
     with pytest.raises(NotImplementedError):
         rlcard_b200.make('leduc-holdem', config={'allow_step_back': True})
+    for cfg in ({'hand_size': 12}, {'rank_count': 8}, {'game_num_players': 3}):     # envs/scout.py:14-28: refused, never ignored
+        with pytest.raises(NotImplementedError):
+            rlcard_b200.make('scout', config=cfg)
+    with pytest.raises(NotImplementedError):
+        rlcard_b200.make('limit-holdem', config={'game_num_players': 3})
+    with pytest.raises(ValueError):
+        rlcard_b200.make('uno', config={'no_such_key': 1})
+    rlcard_b200.make('scout', config={'hand_size': 16, 'rank_count': 10, 'game_num_players': 4})      # the defaults pass
 
 
 @pytest.mark.parametrize('game', GAMES)
