@@ -183,7 +183,7 @@ int rlc_judge_leduc(const int32_t *cases, int n, float *payoffs, void *stream);
 
 /* games/doudizhu/judger.py:124-258 playable_cards_from_hand (targets NULL or targets[i] < 0: lead) and
  * games/doudizhu/utils.py:225-262 get_gt_cards (targets[i] = action id to beat): hands uint8 [n][15] rank counts
- * (3456789TJQKA2BR) -> bit-packed legal sets uint32 [n][859].  Needs rlc_upload_tables(RLC_DOUDIZHU, ...). */
+ * (3456789TJQKA2BR) -> bit-packed legal sets uint32 [n][860] (859 words of ids + one pad word).  Needs rlc_upload_tables(RLC_DOUDIZHU, ...). */
 int rlc_judge_doudizhu(const uint8_t *hands, const int32_t *targets, int n, uint32_t *mask, void *stream);
 
 /* games/uno/utils.py:86-127 encode_hand + encode_target: hands uint8 [n][32] card codes 15*colour + trait

@@ -60,12 +60,14 @@ __device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of ca
 }
 
 struct Doudizhu {
-    static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 859;
+    static constexpr int kGameId = 4, P = 3, A = 27472, OBS = 912, GAME_WORDS = 20, MASK_WORDS = 860;   // 27 472 ids = 859 words, rows padded to 860 (3440 B: whole 16-byte units, so a row can leave as one bulk copy)
     static constexpr bool kMaskBitpacked = true;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for
     static constexpr int kScratchBytes = 64 + 4 * 864 + 128 + 48;   // reset: 54-card deck | legal(): list of non-empty mask words | encode_obs: 16 count words | hands, played piles
     static constexpr int kObsScratch = 64 + 4 * 864;
     static constexpr bool kRowFlushFull = false;  // the batched flush spills at the 72-register cap (measured 2 % slower)
+    static constexpr int kBulkDefault = 3;        // mask + obs rows as bulk copies: 1.350 -> 1.218 ms (profiles/r02_ddz_bulk.md)
+    static constexpr bool kMaskBulk = true;       // the fused rollout may hand the 3440-byte mask row to the copy engine (kernels_warp.cuh)
     int n_legal, n_live; bool has_pass;                  // summary of the last legal() (warp-uniform)
     DdzTables tab;
     uint64_t *hand, *played;   // [3] each, in the warp's shared memory: every lane writes the same values (replicated state),
@@ -216,7 +218,7 @@ struct Doudizhu {
     __device__ void legal_order(const uint32_t *smask, int32_t *out, int stride, int lane) const {
         if (lane != 0) return;
         int n = 0;
-        for (int w = 0; w < 859; w++) {
+        for (int w = 0; w < MASK_WORDS; w++) {
             uint32_t v = smask[w];
             while (v) { const int b = __ffs(v) - 1; v &= v - 1; if (n < stride) out[n] = 32 * w + b; n++; }
         }

@@ -31,6 +31,7 @@ struct Scout {
                                                   // measured 5 / 6 / 7 / 8 blocks: 1.175 / 1.139 / 1.050 / 1.043 ms, 8 spills)
     static constexpr int kScratchBytes = 48 + 64;   // reset: 45-card deck | the four hands (tops, bottoms)
     static constexpr bool kRowFlushFull = true;   // 2752-byte rows: batched compile-time flush (1.235 -> 1.212 ms)
+    static constexpr bool kMaskBulk = false;      // 204-byte mask rows are not whole 16-byte units
     uint64_t *hands;       // shared memory of the warp: [0..3] hand tops p0..p3, [4..7] hand bottoms.  Every lane writes the
                            // same values (the state is replicated), so no barrier is needed around these accesses; keeping
                            // them out of the registers drops the 64-bit four-way select chains and 16 registers per thread

@@ -213,6 +213,33 @@ __global__ void __launch_bounds__(BLOCK) k_env(const KParams p) {
                         reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
 }
 
+// one env's dense mask row into the warp's mask tile (rows of a warp are contiguous in global memory)
+template <class G, int EPW>
+__device__ __forceinline__ void stage_mask_row(uint8_t *mtile, int lane, const uint32_t (&m)[G::MASK_WORDS]) {
+    if constexpr (G::MASK_WORDS == 2 && G::A <= 61 && (EPW * G::A) % 4 == 0) {
+        // 4 mask bits -> 4 bytes per 32-bit store instead of one byte store per action: the row starts at byte
+        // lane * A, o = (lane * A) & 3 bytes past a word boundary, so the bits are shifted up by o and expanded
+        // on the word grid; the first and the last word are shared with the neighbouring rows and OR-ed in
+        // (the tile is zero between steps), the words in between are this lane's alone
+        const int o = (lane * G::A) & 3;
+        const uint64_t mm = ((uint64_t)m[0] | ((uint64_t)m[1] << 32)) << o;
+        const uint32_t lo = (uint32_t)mm, hi = (uint32_t)(mm >> 32);
+        uint32_t *w = reinterpret_cast<uint32_t *>(mtile + lane * G::A - o);
+        constexpr int kW = (G::A + 3 + 3) / 4;
+#pragma unroll
+        for (int j = 0; j < kW; j++) {
+            const uint32_t nibble = ((j < 8 ? lo : hi) >> (4 * (j & 7))) & 15u;
+            const uint32_t v = (nibble * 0x00204081u) & 0x01010101u;          // bit a -> byte a
+            if (j == 0 || j == kW - 1) atomicOr(w + j, v);
+            else w[j] = v;
+        }
+    } else {
+        uint8_t *mr = mtile + lane * G::A;
+#pragma unroll
+        for (int a = 0; a < G::A; a++) mr[a] = (m[a >> 5] >> (a & 31)) & 1u;
+    }
+}
+
 // Fused random rollout: T env-steps per env, state in registers for the whole launch; per step the
 // warp emits one coalesced obs tile plus mask/action/player/done/payoff rows of the trajectory.
 // ALL = every trajectory pointer is present and the obs rows of a full warp are 16-byte aligned (the
@@ -276,28 +303,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
             g.legal(m);
             if constexpr (kStageMask) {
                 if (ALL || p.t_mask) {
-                    if constexpr (G::MASK_WORDS == 2 && G::A <= 61 && (EPW * G::A) % 4 == 0) {
-                        // 4 mask bits -> 4 bytes per 32-bit store instead of one byte store per action: the row starts at byte
-                        // lane * A, o = (lane * A) & 3 bytes past a word boundary, so the bits are shifted up by o and expanded
-                        // on the word grid; the first and the last word are shared with the neighbouring rows and OR-ed in
-                        // (the tile is zero between steps), the words in between are this lane's alone
-                        const int o = (lane * G::A) & 3;
-                        const uint64_t mm = ((uint64_t)m[0] | ((uint64_t)m[1] << 32)) << o;
-                        const uint32_t lo = (uint32_t)mm, hi = (uint32_t)(mm >> 32);
-                        uint32_t *w = reinterpret_cast<uint32_t *>(mtile + lane * G::A - o);
-                        constexpr int kW = (G::A + 3 + 3) / 4;
-#pragma unroll
-                        for (int j = 0; j < kW; j++) {
-                            const uint32_t nibble = ((j < 8 ? lo : hi) >> (4 * (j & 7))) & 15u;
-                            const uint32_t v = (nibble * 0x00204081u) & 0x01010101u;          // bit a -> byte a
-                            if (j == 0 || j == kW - 1) atomicOr(w + j, v);
-                            else w[j] = v;
-                        }
-                    } else {
-                        uint8_t *mr = mtile + lane * G::A;
-#pragma unroll
-                        for (int a = 0; a < G::A; a++) mr[a] = (m[a >> 5] >> (a & 31)) & 1u;
-                    }
+                    stage_mask_row<G, EPW>(mtile, lane, m);
                 }
             }
         }

@@ -194,7 +194,11 @@ __global__ void __launch_bounds__(BLOCK) k_wenv(const KParams p) {
 
 // EXT = the rlc_trajectory extensions are in use (recorded actions instead of the random policy, terminal-state pool);
 // the plain instantiation is the throughput kernel and carries none of that code.
-template <class G, class Ch, class ObsT, int BLOCK, bool EXT>
+// BULK (throughput kernel only; RLC_WROLLOUT_BULK picks it at launch, default per game from the B200 measurements in
+// profiles/): bit 0 = the bit-packed mask row leaves shared memory as ONE cp.async.bulk copy (UBLKCP) instead of 27 LDS + STG
+// per lane, bit 1 = the obs row too.  The warp-per-env kernels are issue-bound, so every instruction the copy engine takes
+// over counts; the mask row is only rewritten by the next legal(), ~300 instructions later, so the wait is free.
+template <class G, class Ch, class ObsT, int BLOCK, bool EXT, int BULK = 0>
 __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams p) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -221,12 +225,21 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     size_t rowi = env;
     for (int t = 0; t < p.T; t++, rowi += p.n) {
         bool row_pending = false;
+        constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT), kMaskBytes = G::MASK_WORDS * 4;
+        constexpr bool kBulkMask = (BULK & 1) != 0 && G::kMaskBitpacked && kMaskBytes % 16 == 0;
+        constexpr bool kBulkObs = (BULK & 2) != 0 && kObsBytes % 16 == 0;
         if (p.t_obs) {
             g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
             __syncwarp();
-            row_pending = warp_row_store_begin<G, ObsT>(p.t_obs, rowi, srow, lane);
+            if constexpr (kBulkObs) {
+                tile_store_begin<kObsBytes, true>(reinterpret_cast<uint8_t *>(p.t_obs) + rowi * (size_t)kObsBytes, reinterpret_cast<uint8_t *>(srow), lane);
+            } else row_pending = warp_row_store_begin<G, ObsT>(p.t_obs, rowi, srow, lane);
         }
-        if (p.t_mask) warp_write_mask<G>(p.t_mask, rowi, smask, lane);
+        if (p.t_mask) {
+            if constexpr (kBulkMask) {
+                tile_store_begin<kMaskBytes, true>(reinterpret_cast<uint8_t *>(p.t_mask) + rowi * (size_t)kMaskBytes, reinterpret_cast<uint8_t *>(smask), lane);
+            } else warp_write_mask<G>(p.t_mask, rowi, smask, lane);
+        }
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
         int a;
@@ -269,6 +282,8 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
             }
         }
         if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
+        if constexpr (kBulkObs) { if (p.t_obs) tile_store_end<kObsBytes, true>(reinterpret_cast<uint8_t *>(srow), lane); }   // wait + re-zero
+        else if constexpr (kBulkMask) { if (p.t_mask) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } }
         __syncwarp();
         if (!EXT || a >= 0) cnt = g.legal(smask, scratch, lane);  // legal set of the state the next iteration emits
         __syncwarp();
@@ -310,7 +325,21 @@ cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
     case kOpObserve: RLC_WLAUNCH((k_wenv<G, Ch, ObsT, kModeObserve, BLOCK>)); break;
     case kOpRollout:
         if (p.t_forced || p.tm_row) RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, true>));
-        else RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, false>));
+        else {
+            int bulk = 0;
+            if constexpr (Ch::kKind == 0 && G::kMaskBulk) {
+                constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT), kMaskBytes = G::MASK_WORDS * 4;
+                const char *envv = getenv("RLC_WROLLOUT_BULK");
+                bulk = envv ? atoi(envv) : G::kBulkDefault;
+                if ((reinterpret_cast<uintptr_t>(p.t_mask) & 15u) || kMaskBytes % 16) bulk &= ~1;
+                if ((reinterpret_cast<uintptr_t>(p.t_obs) & 15u) || kObsBytes % 16) bulk &= ~2;
+                if (!p.t_mask) bulk &= ~1;
+                if (!p.t_obs) bulk &= ~2;
+                if (bulk == 1) { RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, false, 1>)); break; }
+                if (bulk == 3) { RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, false, 3>)); break; }
+            }
+            RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, false>));
+        }
         break;
     default: e = cudaErrorInvalidValue;
     }

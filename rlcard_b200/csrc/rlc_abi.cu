@@ -55,7 +55,7 @@ static const rlc_info kInfo[RLC_NUM_GAMES] = {
     { RLC_LEDUC, 2, 4, {36, 36, 0, 0}, 36, RLC_U8, 0, 1, rlc::kHeaderWords + 1, 6, 1, RLC_STATE_SOA, rlc::kHeaderWords + 1, {0, 0} },
     { RLC_LIMIT, 2, 4, {72, 72, 0, 0}, 72, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 52, 1, RLC_STATE_SOA, rlc::kHeaderWords + 4, {0, 0} },
     { RLC_UNO, 2, 61, {240, 240, 0, 0}, 240, RLC_U8, 0, 2, rlc::kHeaderWords + 66, 256, 1, RLC_STATE_SOA, rlc::kHeaderWords + 19, {0, 0} },
-    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 859, rlc::kHeaderWords + 20, 54, 32, RLC_STATE_ROWS, rlc::kHeaderWords + 20, {0, 0} },
+    { RLC_DOUDIZHU, 3, 27472, {790, 901, 901, 0}, 912, RLC_U8, 1, 860, rlc::kHeaderWords + 20, 54, 32, RLC_STATE_ROWS, rlc::kHeaderWords + 20, {0, 0} },
     { RLC_SCOUT, 4, 204, {688, 688, 688, 688}, 688, RLC_F32, 0, 7, rlc::kHeaderWords + 23, 90, 32, RLC_STATE_ROWS, rlc::kHeaderWords + 23, {0, 0} },
 #ifdef RLC_HAVE_NOLIMIT
     { RLC_NOLIMIT, 2, 5, {54, 54, 0, 0}, 54, RLC_U8, 0, 1, rlc::kHeaderWords + 4, 53, 1, RLC_STATE_SOA, rlc::kHeaderWords + 4, {0, 0} },

@@ -9,7 +9,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import GAME_IDS, check, lib
+from ._lib import GAME_IDS, check, game_info, lib
 
 
 def _p(t):
@@ -48,13 +48,13 @@ def judge_leduc(cases):
 
 def doudizhu_playable(hands, targets=None):
     """hands uint8 [n, 15] rank counts, targets int32 [n] (action id to beat, < 0 = lead) -> bit-packed legal sets
-    int32 [n, 859] (bit a % 32 of word a // 32)."""
+    int32 [n, mask_words = 860] (bit a % 32 of word a // 32)."""
     from .vec_env import _upload_doudizhu_tables
     hands = _dev(hands, torch.uint8)
     _upload_doudizhu_tables(lib(), hands.device)
     if targets is not None:
         targets = _dev(targets, torch.int32)
-    out = torch.empty((hands.shape[0], 859), dtype=torch.int32, device=hands.device)
+    out = torch.empty((hands.shape[0], game_info('doudizhu').mask_words), dtype=torch.int32, device=hands.device)
     with torch.cuda.device(hands.device):
         check(lib().rlc_judge_doudizhu(_p(hands), _p(targets), hands.shape[0], _p(out), _stream(hands.device)))
     return out

@@ -465,6 +465,48 @@ def test_limit_warp_specialised_rollout_equals_oracle(monkeypatch):
     env.check_errors()
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('epw', [16, 32])
+def test_uno_env_emit_rollout_equals_oracle(epw, monkeypatch):
+    """RLC_UNO_EE=16|32: the two-warp UNO rollout (ENV transition warp + EMIT row warp, tu_uno.cu) gives the oracle's
+    trajectory over two launches (episodes under way at the launch boundary)."""
+    monkeypatch.setenv('RLC_UNO_EE', str(epw))
+    n, T, seed = 1024, 60, 707
+    env = rlcard_b200.VecEnv('uno', n, seed=seed)
+    orc = oracle.OracleVec('uno', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (launch, k)
+    env.check_errors()
+
+
+@pytest.mark.parametrize('bulk', [0, 1, 3])
+def test_doudizhu_bulk_row_variants_equal_oracle(bulk, monkeypatch):
+    """RLC_WROLLOUT_BULK: the DouDizhu rollout with its mask row (1) or mask + obs rows (3) leaving shared memory as
+    cp.async.bulk copies must equal the LDS + STG variant (0) and the oracle."""
+    monkeypatch.setenv('RLC_WROLLOUT_BULK', str(bulk))
+    n, T, seed = 600, 30, 808
+    env = rlcard_b200.VecEnv('doudizhu', n, seed=seed)
+    orc = oracle.OracleVec('doudizhu', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            got, want = to_np(tr[k]), ref[k]
+            if k == 'mask':
+                want = np.packbits(want, axis=-1, bitorder='little')
+                assert not got.view(np.uint8)[..., want.shape[-1]:].any()            # pad bits / pad word stay zero
+                got = got.view(np.uint8)[..., :want.shape[-1]]
+            if k == 'obs':
+                got = got[..., :want.shape[-1]]
+            assert np.array_equal(got.astype(np.float64), want.astype(np.float64)), (bulk, launch, k)
+    env.check_errors()
+
+
 THREAD_GAMES = [g for g in GAMES if g not in ('doudizhu', 'scout')]
 
 
