@@ -288,6 +288,20 @@ __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *til
 #define RLC_TMA_FLUSH 0
 #endif
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the pieces of a bulk store, for kernels that issue several rows under one fence / one commit group
+__device__ __forceinline__ uint64_t bulk_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // every writer lane
+__device__ __forceinline__ void bulk_issue(void *gdst, const void *tile, uint32_t bytes, uint64_t pol) {           // one lane
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(smem_u32(tile)), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 template <int TILE_BYTES, bool TMA = (RLC_TMA_FLUSH != 0)>
 __device__ __forceinline__ void tile_store_begin(uint8_t *gdst, uint8_t *tile, int lane) {
   if constexpr (TMA) {

@@ -54,9 +54,10 @@ __device__ __forceinline__ bool ddz_type_ok(uint64_t hand, int t) {
     }
     return g != 0;
 }
-__device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of cards = sum of nibbles
-    c = (c & 0x0f0f0f0f0f0f0f0full) + ((c >> 4) & 0x0f0f0f0f0f0f0f0full);
-    return (int)((c * 0x0101010101010101ull) >> 56);
+__device__ __forceinline__ int ddz_cards(uint64_t c) {           // number of cards = sum of the 15 nibbles
+    const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+    const uint32_t s = (lo & 0x0f0f0f0fu) + ((lo >> 4) & 0x0f0f0f0fu) + (hi & 0x0f0f0f0fu) + ((hi >> 4) & 0x0f0f0f0fu);   // four byte sums <= 16
+    return (int)__dp4a(s, 0x01010101u, 0u);
 }
 
 struct Doudizhu {

@@ -223,22 +223,33 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     int cnt = g.legal(smask, scratch, lane);
     __syncwarp();
     size_t rowi = env;
+    constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT), kMaskBytes = G::MASK_WORDS * 4;
+    constexpr bool kBulkMask = (BULK & 1) != 0 && G::kMaskBitpacked && kMaskBytes % 16 == 0;
+    constexpr bool kBulkObs = (BULK & 2) != 0 && kBulkMask && kObsBytes % 16 == 0;          // the obs row only together with the mask row
+    uint64_t bulk_pol = 0;
+    if constexpr (kBulkMask) bulk_pol = bulk_evict_first_policy();
     for (int t = 0; t < p.T; t++, rowi += p.n) {
         bool row_pending = false;
-        constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT), kMaskBytes = G::MASK_WORDS * 4;
-        constexpr bool kBulkMask = (BULK & 1) != 0 && G::kMaskBitpacked && kMaskBytes % 16 == 0;
-        constexpr bool kBulkObs = (BULK & 2) != 0 && kObsBytes % 16 == 0;
-        if (p.t_obs) {
+        if constexpr (kBulkObs && kBulkMask) {                    // launcher: both streams present and aligned
             g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
+            bulk_fence();                                         // one fence, one barrier, one commit group for both rows
             __syncwarp();
-            if constexpr (kBulkObs) {
-                tile_store_begin<kObsBytes, true>(reinterpret_cast<uint8_t *>(p.t_obs) + rowi * (size_t)kObsBytes, reinterpret_cast<uint8_t *>(srow), lane);
-            } else row_pending = warp_row_store_begin<G, ObsT>(p.t_obs, rowi, srow, lane);
-        }
-        if (p.t_mask) {
-            if constexpr (kBulkMask) {
-                tile_store_begin<kMaskBytes, true>(reinterpret_cast<uint8_t *>(p.t_mask) + rowi * (size_t)kMaskBytes, reinterpret_cast<uint8_t *>(smask), lane);
-            } else warp_write_mask<G>(p.t_mask, rowi, smask, lane);
+            if (lane == 0) {
+                bulk_issue(reinterpret_cast<uint8_t *>(p.t_obs) + rowi * (size_t)kObsBytes, srow, kObsBytes, bulk_pol);
+                bulk_issue(reinterpret_cast<uint8_t *>(p.t_mask) + rowi * (size_t)kMaskBytes, smask, kMaskBytes, bulk_pol);
+                bulk_commit();
+            }
+        } else {
+            if (p.t_obs) {
+                g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
+                __syncwarp();
+                row_pending = warp_row_store_begin<G, ObsT>(p.t_obs, rowi, srow, lane);
+            }
+            if (p.t_mask) {
+                if constexpr (kBulkMask) {
+                    tile_store_begin<kMaskBytes, true>(reinterpret_cast<uint8_t *>(p.t_mask) + rowi * (size_t)kMaskBytes, reinterpret_cast<uint8_t *>(smask), lane);
+                } else warp_write_mask<G>(p.t_mask, rowi, smask, lane);
+            }
         }
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
@@ -282,8 +293,8 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
             }
         }
         if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
-        if constexpr (kBulkObs) { if (p.t_obs) tile_store_end<kObsBytes, true>(reinterpret_cast<uint8_t *>(srow), lane); }   // wait + re-zero
-        else if constexpr (kBulkMask) { if (p.t_mask) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } }
+        if constexpr (kBulkObs && kBulkMask) tile_store_end<kObsBytes, true>(reinterpret_cast<uint8_t *>(srow), lane);   // wait + re-zero the obs row
+        else if constexpr (kBulkMask) { if (p.t_mask) { if (lane == 0) bulk_wait_read(); } }
         __syncwarp();
         if (!EXT || a >= 0) cnt = g.legal(smask, scratch, lane);  // legal set of the state the next iteration emits
         __syncwarp();
