@@ -222,21 +222,24 @@ __device__ __forceinline__ void st_stream(T *p, T v) {
 // by this kernel) and re-zeroes the tile on the way.  Falls back to byte stores when the
 // destination or the length is not 16-byte aligned (ragged last warp).
 // ------------------------------------------------------------------------------------------
+// LANES = lanes that share the tile (32: the whole warp; 16: a half-warp that hosts its own env, kernels_warp.cuh)
+template <int LANES = kWarp>
 __device__ __forceinline__ void warp_tile_zero(uint8_t *tile, int nbytes, int lane) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int c = lane; c < (nbytes >> 4); c += kWarp) reinterpret_cast<uint4 *>(tile)[c] = z;
-    for (int c = (nbytes & ~15) + lane; c < nbytes; c += kWarp) tile[c] = 0;
+    for (int c = lane; c < (nbytes >> 4); c += LANES) reinterpret_cast<uint4 *>(tile)[c] = z;
+    for (int c = (nbytes & ~15) + lane; c < nbytes; c += LANES) tile[c] = 0;
 }
+template <int LANES = kWarp>
 __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, int nbytes, int lane) {
     if (((reinterpret_cast<uintptr_t>(gdst) | (uintptr_t)nbytes) & 15u) == 0) {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int c = lane; c < (nbytes >> 4); c += kWarp) {
+        for (int c = lane; c < (nbytes >> 4); c += LANES) {
             const uint4 v = reinterpret_cast<uint4 *>(tile)[c];
             st_stream(reinterpret_cast<uint4 *>(gdst) + c, v);
             reinterpret_cast<uint4 *>(tile)[c] = z;
         }
     } else {
-        for (int c = lane; c < nbytes; c += kWarp) { gdst[c] = tile[c]; tile[c] = 0; }
+        for (int c = lane; c < nbytes; c += LANES) { gdst[c] = tile[c]; tile[c] = 0; }
     }
 }
 
@@ -244,9 +247,10 @@ __device__ __forceinline__ void warp_tile_flush(uint8_t *gdst, uint8_t *tile, in
 // count and every guard are compile-time.  Chunks move in batches of up to four per lane: all 128-bit LDS of a batch
 // first, then the zeroing STS, then the STG.cs -- distinct registers per chunk, so no load waits for a store to
 // release its source registers and the shared-memory latency is paid once per batch.
-template <int TILE_BYTES>
+template <int TILE_BYTES, int LANES = kWarp>
 __device__ __forceinline__ void warp_tile_flush_full(uint8_t *gdst, uint8_t *tile, int lane) {
     static_assert(TILE_BYTES % 16 == 0, "tile must be a whole number of 128-bit chunks");
+    constexpr int kWarp = LANES;           // lanes that share the tile (shadows rlc::kWarp in this function)
     constexpr int kChunks = TILE_BYTES / 16, kBatch = 4;
     const uint4 z = make_uint4(0, 0, 0, 0);
     uint4 *t4 = reinterpret_cast<uint4 *>(tile), *g4 = reinterpret_cast<uint4 *>(gdst);

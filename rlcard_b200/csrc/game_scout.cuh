@@ -24,7 +24,24 @@ __device__ __forceinline__ uint64_t shr64(uint64_t x, int bits) { return bits >=
 __device__ __forceinline__ uint64_t shl64(uint64_t x, int bits) { return bits >= 64 ? 0ull : (x << bits); }
 __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * k)) & 15ull); }
 
-struct Scout {
+// LPE = lanes per env: 32 (a warp per env: replay modes, per-step kernels) or 16 (the fused throughput rollout hosts two
+// envs per warp, one per half-warp: the scalar transition every lane replicates is then paid once per TWO envs, and the
+// lane-parallel parts -- 16 starts, 16 hand / table slots -- are 16 wide anyway).  `lane` is always the lane within the
+// env's group; ballots are shifted down to group-relative bits.
+template <int LPE>
+struct ScoutT {
+    static_assert(LPE == 32 || LPE == 16, "a warp or a half-warp per env");
+    static constexpr int kLanes = LPE;
+    template <int L> using WithLanes = ScoutT<L>;
+    static constexpr int kRolloutLanes = 16;      // lanes per env of the fused throughput rollout (RLC_WROLLOUT_LPE=32: a warp per env)
+    uint32_t gm; int gsh;                         // LPE == 16: lane mask of this env's half-warp and its first lane
+    __device__ __forceinline__ void bind_group(uint32_t mask, int shift) { gm = mask; gsh = shift; }
+    __device__ __forceinline__ uint32_t ballot(bool pred) const {
+        if constexpr (LPE == 32) return __ballot_sync(kFull, pred);
+        else return __ballot_sync(gm, pred) >> gsh;
+    }
+    __device__ __forceinline__ uint32_t red_or(uint32_t v) const { return __reduce_or_sync(LPE == 32 ? kFull : gm, v); }
+    __device__ __forceinline__ void gsync() const { __syncwarp(LPE == 32 ? kFull : gm); }
     static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
     static constexpr bool kMaskBitpacked = false;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for (71 registers, no spills;
@@ -96,9 +113,9 @@ struct Scout {
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
         const int a = nib(T, lane & 15), b = nib(T, (lane + 1) & 15);
         const bool adj = lane < 15 && lane + 1 < n;
-        const uint32_t eqm = __ballot_sync(kFull, adj && b == a);
-        const uint32_t upm = __ballot_sync(kFull, adj && b == a + 1);
-        const uint32_t dnm = __ballot_sync(kFull, adj && b == a - 1);
+        const uint32_t eqm = ballot(adj && b == a);
+        const uint32_t upm = ballot(adj && b == a + 1);
+        const uint32_t dnm = ballot(adj && b == a - 1);
         int lo_id = 1, hi_id = 0;                                          // empty
         if (lane < n && lane < 16) {
             const int s = lane;
@@ -118,7 +135,7 @@ struct Scout {
         for (int r = 0; r < 5; r++) {
             const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
             const uint32_t bits = x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
-            m[r] = __reduce_or_sync(kFull, bits);
+            m[r] = red_or(bits);
         }
         forced = (m[0] | m[1] | m[2] | m[3] | m[4]) == 0;
         m[5] = m[6] = 0;
@@ -166,13 +183,13 @@ struct Scout {
             int n = 0;
             for (int top = 1; top <= 10; top++) for (int bot = top + 1; bot <= 10; bot++) deck[n++] = (uint8_t)((top << 4) | bot);
         }
-        __syncwarp();
+        gsync();
         for (int pass = 0; pass < 2; pass++)
             for (int i = 44; i >= 1; i--) {
                 const uint32_t j = ch.below((uint32_t)i + 1u);
                 if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
             }
-        __syncwarp();
+        gsync();
         uint64_t nt[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 45; k++) {                   // deck.pop() = position 44-k -> player k%4, slot k/4
@@ -182,7 +199,7 @@ struct Scout {
         }
 #pragma unroll
         for (int p = 0; p < 4; p++) { hands[p] = nt[p]; hands[4 + p] = nb[p]; hl[p] = p == 0 ? 12 : 11; score[p] = 0; }
-        __syncwarp();
+        gsync();
         tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
         cur = (int)ch.below(4u);
         forced = false; lm_valid = false;
@@ -229,9 +246,9 @@ struct Scout {
             if (tl == 0) { owner = 4; consec = 0; }
             if (consec == 3 && owner < 4) over_ = 1;
         }
-        __syncwarp();                                                       // every lane has read the old hand
+        gsync();                                                            // every lane has read the old hand
         hands[p] = T; hands[4 + p] = B; puti(hl, p, n);
-        __syncwarp();
+        gsync();
         cur = (p + 1) & 3;
         legal_words(lm, lane);                                              // next player cannot move -> round ends
         lm_valid = true;
@@ -250,8 +267,9 @@ struct Scout {
                 row[160 + s * 10 + nib(bot_of(seat), s) - 1] = (T)1;
                 row[640 + s] = (T)1;
             }
-        } else {
-            const int j = lane - 16;
+        }
+        if (LPE == 16 || lane >= 16) {                                      // half-warp: the same 16 lanes write the table slots
+            const int j = lane & 15;
             if (j < tl) {
                 row[320 + j * 10 + nib(tt, j) - 1] = (T)1;
                 row[480 + j * 10 + nib(tb, j) - 1] = (T)1;
@@ -276,5 +294,6 @@ struct Scout {
         }
     }
 };
+using Scout = ScoutT<32>;
 
 }  // namespace rlc

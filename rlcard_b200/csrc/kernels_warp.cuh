@@ -18,50 +18,53 @@ namespace rlc {
 constexpr uint32_t kFull = 0xffffffffu;
 
 // lane 0 owns the chance source; results are broadcast so that all lanes stay in lock step
-template <class Ch>
+// LPE = lanes per env (32, or 16 when a half-warp hosts the env: `lane` is then the lane within the half and gm its mask)
+template <class Ch, int LPE = 32>
 struct WarpChance {
     static constexpr int kKind = Ch::kKind;
-    Ch ch; int lane;
+    Ch ch; int lane; uint32_t gm;
+    __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(LPE == 32 ? kFull : gm, v, 0, LPE); }
     __device__ __forceinline__ uint32_t below(uint32_t n) {
         uint32_t v = 0;
         if (lane == 0) v = ch.below(n);
-        return __shfl_sync(kFull, v, 0);
+        return bcast(v);
     }
     __device__ __forceinline__ void skip_fy(int a, int b) { if (lane == 0) ch.skip_fy(a, b); }
     __device__ __forceinline__ void begin_step(uint32_t k) { if (lane == 0) (void)ch.begin_step(k); }
     __device__ __forceinline__ void begin_reset(uint32_t k) { if (lane == 0) ch.begin_reset(k); }
     __device__ __forceinline__ void begin_episode(uint32_t e) { if (lane == 0) ch.begin_episode(e); }
-    __device__ __forceinline__ int err() { return __shfl_sync(kFull, ch.err, 0); }
+    __device__ __forceinline__ int err() { return (int)bcast((uint32_t)ch.err); }
 };
-template <class Ch>
-__device__ __forceinline__ void wchance_open(WarpChance<Ch> &w, const KParams &p, size_t env, int lane) {
-    w.lane = lane;
+template <class Ch, int LPE>
+__device__ __forceinline__ void wchance_open(WarpChance<Ch, LPE> &w, const KParams &p, size_t env, int lane, uint32_t gm = kFull) {
+    w.lane = lane; w.gm = gm;
     ChanceIO<Ch>::open(w.ch, p, env);     // every lane builds the (cheap) handle; only lane 0 draws/commits
 }
-template <class Ch>
-__device__ __forceinline__ void wchance_close(WarpChance<Ch> &w, const KParams &p, size_t env) {
+template <class Ch, int LPE>
+__device__ __forceinline__ void wchance_close(WarpChance<Ch, LPE> &w, const KParams &p, size_t env) {
     if (w.lane == 0) ChanceIO<Ch>::close(w.ch, p, env);
 }
-template <class Ch>
-__device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch> &w, const KParams &p, size_t env, uint32_t k) {
+template <class Ch, int LPE>
+__device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch, LPE> &w, const KParams &p, size_t env, uint32_t k) {
     uint32_t word = 0;
     if (w.lane == 0) {
         if constexpr (Ch::kKind == 0) word = w.ch.begin_step(k);
         else word = policy_word_only(p, env, k);
     }
-    return __shfl_sync(kFull, word, 0);
+    return w.bcast(word);
 }
 
 // mask row of one env: dense uint8 [A] (4 ids per 32-bit store) or bit-packed uint32 [W]
-template <class G>
+template <class G, int LANES = 32>
 __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const uint32_t *sm, int lane) {
     if constexpr (G::kMaskBitpacked) {
         uint32_t *dst = reinterpret_cast<uint32_t *>(gmask) + row * (size_t)G::MASK_WORDS;
-        for (int wi = lane; wi < G::MASK_WORDS; wi += 32) st_stream(dst + wi, sm[wi]);
+        for (int wi = lane; wi < G::MASK_WORDS; wi += LANES) st_stream(dst + wi, sm[wi]);
     } else {
         static_assert(G::A % 4 == 0, "dense mask rows are written as 32-bit words");
         uint32_t *dst = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gmask) + row * (size_t)G::A);
-        for (int q = lane; q < G::A / 4; q += 32) {
+#pragma unroll
+        for (int q = lane; q < G::A / 4; q += LANES) {
             const uint32_t b = (sm[q >> 3] >> ((q & 7) * 4)) & 15u;
             st_stream(dst + q, (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
         }
@@ -318,6 +321,92 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
     if (err && p.err && lane == 0) p.err[env] |= err;
 }
 
+// Throughput rollout with LPE < 32 lanes per env: a warp hosts 32 / LPE envs, one per lane group.  The transition is scalar
+// code that every lane of an env replicates, so a warp-instruction of it now serves 32 / LPE envs instead of one; the
+// lane-parallel parts (legal-set ballots, obs slots, row flush) run on the group's lanes.  Groups diverge where their envs do
+// (play vs scout, an episode ending), so every barrier and collective names the group's own lane mask.  Philox mode, every
+// trajectory stream optional, no ABI-2 extensions (those run on k_wrollout).
+template <class G, class Ch, class ObsT, int BLOCK, int LPE>
+__global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const KParams p) {
+    static_assert(LPE == 16 && G::kLanes == LPE, "half-warp groups");
+    extern __shared__ uint4 smem_raw[];
+    constexpr int kGroups = 32 / LPE;
+    const int lane_abs = threadIdx.x & 31, sub = lane_abs / LPE, lane = lane_abs % LPE;
+    const int slot = (threadIdx.x >> 5) * kGroups + sub;
+    const size_t env = (size_t)blockIdx.x * (BLOCK / LPE) + slot;
+    if (env >= p.n) return;
+    const int gsh = sub * LPE;
+    const uint32_t gm = ((LPE == 32) ? kFull : ((1u << LPE) - 1u)) << gsh;
+    constexpr int kRowBytes = (G::OBS * (int)sizeof(ObsT) + 15) & ~15;
+    constexpr int kEnvBytes = kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15) + G::kScratchBytes;
+    uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot * kEnvBytes;
+    ObsT *srow = reinterpret_cast<ObsT *>(base);
+    uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
+    uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
+    warp_tile_zero<LPE>(base, kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15), lane);
+    __syncwarp(gm);
+
+    uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
+    EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
+    G g; g.bind(p, scratch); g.bind_group(gm, gsh); g.load(row + kHeaderWords, lane);
+    WarpChance<Ch, LPE> ch; wchance_open(ch, p, env, lane, gm);
+    int err = 0;
+    if (h.episode == 0 || g.over()) { ch.begin_reset(h.k); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
+    __syncwarp(gm);
+    int cnt = g.legal(smask, scratch, lane);
+    __syncwarp(gm);
+    size_t rowi = env;
+    constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT);
+    const bool obs_fast = p.t_obs && kObsBytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0;
+    for (int t = 0; t < p.T; t++, rowi += p.n) {
+        if (p.t_obs) {
+            g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
+            __syncwarp(gm);
+            uint8_t *dst = reinterpret_cast<uint8_t *>(p.t_obs) + rowi * (size_t)kObsBytes;
+            if constexpr (kObsBytes % 16 == 0) {
+                if (obs_fast) warp_tile_flush_full<kObsBytes, LPE>(dst, reinterpret_cast<uint8_t *>(srow), lane);
+                else warp_tile_flush<LPE>(dst, reinterpret_cast<uint8_t *>(srow), kObsBytes, lane);
+            } else warp_tile_flush<LPE>(dst, reinterpret_cast<uint8_t *>(srow), kObsBytes, lane);
+        }
+        if (p.t_mask) warp_write_mask<G, LPE>(p.t_mask, rowi, smask, lane);
+        const uint32_t word = wpolicy_word(ch, p, env, h.k);
+        const int k = (int)__umulhi(word, (uint32_t)cnt);
+        const int a = g.pick(smask, scratch, k, lane);
+        const int pl = g.player();
+        __syncwarp(gm);
+        float pay[G::P];
+#pragma unroll
+        for (int q = 0; q < G::P; q++) pay[q] = 0.f;
+        g.step(a, ch, smask, scratch, lane, err);
+        h.t++; h.k++;
+        const bool over = g.over();
+        if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
+        __syncwarp(gm);
+        cnt = g.legal(smask, scratch, lane);                      // legal set of the state the next iteration emits
+        __syncwarp(gm);
+        if (lane == 0) {
+            if (p.t_player) st_stream(p.t_player + rowi, pl);
+            if (p.t_action) st_stream(p.t_action + rowi, a);
+            if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
+        }
+        if (p.t_payoffs && lane < G::P) {
+            float v = pay[0];
+#pragma unroll
+            for (int q = 1; q < G::P; q++) v = lane == q ? pay[q] : v;
+            p.t_payoffs[rowi * G::P + lane] = v;
+        }
+    }
+    wchance_close(ch, p, env);
+    if (lane == 0) { row[0] = h.episode; row[1] = h.t; row[2] = h.k; }
+    g.store(row + kHeaderWords, lane);
+    err |= ch.err();
+    if (err && p.err && lane == 0) p.err[env] |= err;
+}
+
+// lanes per env of the fused throughput rollout, if the game asks for fewer than a warp (G::kRolloutLanes)
+template <class G, class = void> struct RolloutLanes { static constexpr int value = 32; };
+template <class G> struct RolloutLanes<G, std::void_t<decltype(G::kRolloutLanes)>> { static constexpr int value = G::kRolloutLanes; };
+
 template <class G, class Ch, class ObsT>
 cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
     constexpr int BLOCK = 128;
@@ -337,6 +426,19 @@ cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
     case kOpRollout:
         if (p.t_forced || p.tm_row) RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, true>));
         else {
+            if constexpr (Ch::kKind == 0 && RolloutLanes<G>::value < 32) {          // several envs per warp (throughput mode)
+                constexpr int LPE = RolloutLanes<G>::value;
+                const char *lv = getenv("RLC_WROLLOUT_LPE");
+                if (!lv || atoi(lv) != 32) {
+                    using GL = typename G::template WithLanes<LPE>;
+                    const unsigned mgrid = (unsigned)((p.n + BLOCK / LPE - 1) / (BLOCK / LPE));
+                    const size_t msmem = smem * (32 / LPE);
+                    auto kk = k_wrollout_multi<GL, Ch, ObsT, BLOCK, LPE>;
+                    if (msmem > 48 * 1024) e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+                    if (e == cudaSuccess) { kk<<<mgrid, BLOCK, msmem, stream>>>(p); e = cudaGetLastError(); }
+                    break;
+                }
+            }
             int bulk = 0;
             if constexpr (Ch::kKind == 0 && G::kMaskBulk) {
                 constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT), kMaskBytes = G::MASK_WORDS * 4;
