@@ -27,7 +27,10 @@ __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * 
 // LPE = lanes per env: 32 (a warp per env: replay modes, per-step kernels) or 16 (the fused throughput rollout hosts two
 // envs per warp, one per half-warp: the scalar transition every lane replicates is then paid once per TWO envs, and the
 // lane-parallel parts -- 16 starts, 16 hand / table slots -- are 16 wide anyway).  `lane` is always the lane within the
-// env's group; ballots are shifted down to group-relative bits.
+// env's group.  With LPE = 16 legal_words() and step() must be called by ALL 32 lanes together (k_wrollout_multi does):
+// their collectives name the whole warp with a compile-time mask -- a per-lane group mask would make the compiler wrap
+// every ballot / reduction in a MATCH.ANY + WARPSYNC loop -- and each half picks its own part of the result.  reset()
+// may run in one half only: it has no collective, only barriers on the group's own mask.
 template <int LPE>
 struct ScoutT {
     static_assert(LPE == 32 || LPE == 16, "a warp or a half-warp per env");
@@ -38,10 +41,17 @@ struct ScoutT {
     __device__ __forceinline__ void bind_group(uint32_t mask, int shift) { gm = mask; gsh = shift; }
     __device__ __forceinline__ uint32_t ballot(bool pred) const {
         if constexpr (LPE == 32) return __ballot_sync(kFull, pred);
-        else return __ballot_sync(gm, pred) >> gsh;
+        else return (__ballot_sync(kFull, pred) >> gsh) & 0xffffu;
     }
-    __device__ __forceinline__ uint32_t red_or(uint32_t v) const { return __reduce_or_sync(LPE == 32 ? kFull : gm, v); }
-    __device__ __forceinline__ void gsync() const { __syncwarp(LPE == 32 ? kFull : gm); }
+    __device__ __forceinline__ uint32_t red_or(uint32_t v) const {
+        if constexpr (LPE == 32) return __reduce_or_sync(kFull, v);
+        else {
+            const uint32_t lo = __reduce_or_sync(kFull, gsh ? 0u : v), hi = __reduce_or_sync(kFull, gsh ? v : 0u);
+            return gsh ? hi : lo;
+        }
+    }
+    __device__ __forceinline__ void wsync() const { __syncwarp(); }                          // all 32 lanes are here
+    __device__ __forceinline__ void gsync() const { __syncwarp(LPE == 32 ? kFull : gm); }    // only this env's lanes may be
     static constexpr int kGameId = 5, P = 4, A = 204, OBS = 688, GAME_WORDS = 23, MASK_WORDS = 7;
     static constexpr bool kMaskBitpacked = false;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for (71 registers, no spills;
@@ -148,7 +158,8 @@ struct ScoutT {
     uint32_t lm[7];        // the last legal() set, identical in all lanes
     bool lm_valid;         // lm / forced already describe the current state (step() computed them)
     __device__ __forceinline__ int legal(uint32_t *smask, uint8_t *, int lane) {
-        if (!lm_valid) legal_words(lm, lane);
+        if constexpr (LPE == 32) { if (!lm_valid) legal_words(lm, lane); }
+        else { if (__any_sync(kFull, !lm_valid)) legal_words(lm, lane); }   // warp-wide decision: the collectives need both halves
         lm_valid = true;
         if (lane == 0) {
 #pragma unroll
@@ -179,16 +190,16 @@ struct ScoutT {
     }
     // games/scout/game.py:37-65, dealer.py:12-22, round.py:22-50: two shuffles (Q-SC1), round-robin deal
     template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
-        if (lane == 0) {
+        if (lane == 0) {                                 // lane 0 owns the chance source: it shuffles alone, nothing is broadcast
             int n = 0;
             for (int top = 1; top <= 10; top++) for (int bot = top + 1; bot <= 10; bot++) deck[n++] = (uint8_t)((top << 4) | bot);
+            for (int pass = 0; pass < 2; pass++)
+                for (int i = 44; i >= 1; i--) {
+                    const uint32_t j = ch.ch.below((uint32_t)i + 1u);
+                    const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t;
+                }
+            deck[45] = (uint8_t)ch.ch.below(4u);         // first player (round.py:22-50), read by every lane below
         }
-        gsync();
-        for (int pass = 0; pass < 2; pass++)
-            for (int i = 44; i >= 1; i--) {
-                const uint32_t j = ch.below((uint32_t)i + 1u);
-                if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
-            }
         gsync();
         uint64_t nt[4] = {0, 0, 0, 0}, nb[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -197,11 +208,11 @@ struct ScoutT {
             nt[k & 3] |= (uint64_t)(c >> 4) << (4 * (k >> 2));
             nb[k & 3] |= (uint64_t)(c & 15) << (4 * (k >> 2));
         }
+        cur = deck[45];
 #pragma unroll
         for (int p = 0; p < 4; p++) { hands[p] = nt[p]; hands[4 + p] = nb[p]; hl[p] = p == 0 ? 12 : 11; score[p] = 0; }
         gsync();
         tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
-        cur = (int)ch.below(4u);
         forced = false; lm_valid = false;
     }
     __device__ __forceinline__ int player() const { return cur; }
@@ -246,9 +257,9 @@ struct ScoutT {
             if (tl == 0) { owner = 4; consec = 0; }
             if (consec == 3 && owner < 4) over_ = 1;
         }
-        gsync();                                                            // every lane has read the old hand
+        wsync();                                                            // every lane has read the old hand
         hands[p] = T; hands[4 + p] = B; puti(hl, p, n);
-        gsync();
+        wsync();
         cur = (p + 1) & 3;
         legal_words(lm, lane);                                              // next player cannot move -> round ends
         lm_valid = true;

@@ -24,6 +24,8 @@ struct WarpChance {
     static constexpr int kKind = Ch::kKind;
     Ch ch; int lane; uint32_t gm;
     __device__ __forceinline__ uint32_t bcast(uint32_t v) const { return __shfl_sync(LPE == 32 ? kFull : gm, v, 0, LPE); }
+    // the same from a point all 32 lanes reach together: compile-time mask (a per-lane mask costs a MATCH.ANY loop per call)
+    __device__ __forceinline__ uint32_t bcast_all(uint32_t v) const { return __shfl_sync(kFull, v, 0, LPE); }
     __device__ __forceinline__ uint32_t below(uint32_t n) {
         uint32_t v = 0;
         if (lane == 0) v = ch.below(n);
@@ -33,7 +35,7 @@ struct WarpChance {
     __device__ __forceinline__ void begin_step(uint32_t k) { if (lane == 0) (void)ch.begin_step(k); }
     __device__ __forceinline__ void begin_reset(uint32_t k) { if (lane == 0) ch.begin_reset(k); }
     __device__ __forceinline__ void begin_episode(uint32_t e) { if (lane == 0) ch.begin_episode(e); }
-    __device__ __forceinline__ int err() { return (int)bcast((uint32_t)ch.err); }
+    __device__ __forceinline__ int err() { return (int)bcast_all((uint32_t)ch.err); }
 };
 template <class Ch, int LPE>
 __device__ __forceinline__ void wchance_open(WarpChance<Ch, LPE> &w, const KParams &p, size_t env, int lane, uint32_t gm = kFull) {
@@ -51,7 +53,7 @@ __device__ __forceinline__ uint32_t wpolicy_word(WarpChance<Ch, LPE> &w, const K
         if constexpr (Ch::kKind == 0) word = w.ch.begin_step(k);
         else word = policy_word_only(p, env, k);
     }
-    return w.bcast(word);
+    return w.bcast_all(word);
 }
 
 // mask row of one env: dense uint8 [A] (4 ids per 32-bit store) or bit-packed uint32 [W]
@@ -333,10 +335,14 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const K
     constexpr int kGroups = 32 / LPE;
     const int lane_abs = threadIdx.x & 31, sub = lane_abs / LPE, lane = lane_abs % LPE;
     const int slot = (threadIdx.x >> 5) * kGroups + sub;
-    const size_t env = (size_t)blockIdx.x * (BLOCK / LPE) + slot;
-    if (env >= p.n) return;
+    const size_t env0 = (size_t)blockIdx.x * (BLOCK / LPE) + slot;
+    if (env0 - sub >= p.n) return;                                // whole warp past the batch
+    // the collectives of the transition name all 32 lanes, so a group past the end of a ragged batch stays: it replays the
+    // last env in its own shared memory and stores nothing
+    const bool live = env0 < p.n;
+    const size_t env = live ? env0 : p.n - 1;
     const int gsh = sub * LPE;
-    const uint32_t gm = ((LPE == 32) ? kFull : ((1u << LPE) - 1u)) << gsh;
+    const uint32_t gm = ((1u << LPE) - 1u) << gsh;
     constexpr int kRowBytes = (G::OBS * (int)sizeof(ObsT) + 15) & ~15;
     constexpr int kEnvBytes = kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15) + G::kScratchBytes;
     uint8_t *base = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot * kEnvBytes;
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const K
     uint32_t *smask = reinterpret_cast<uint32_t *>(base + kRowBytes);
     uint8_t *scratch = base + kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15);
     warp_tile_zero<LPE>(base, kRowBytes + ((G::MASK_WORDS * 4 + 15) & ~15), lane);
-    __syncwarp(gm);
+    __syncwarp();
 
     uint32_t *row = p.state + env * (size_t)(kHeaderWords + G::GAME_WORDS);
     EnvHeader h; h.episode = row[0]; h.t = row[1]; h.k = row[2];
@@ -352,28 +358,29 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const K
     WarpChance<Ch, LPE> ch; wchance_open(ch, p, env, lane, gm);
     int err = 0;
     if (h.episode == 0 || g.over()) { ch.begin_reset(h.k); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
-    __syncwarp(gm);
+    __syncwarp();
     int cnt = g.legal(smask, scratch, lane);
-    __syncwarp(gm);
+    __syncwarp();
     size_t rowi = env;
     constexpr int kObsBytes = G::OBS * (int)sizeof(ObsT);
-    const bool obs_fast = p.t_obs && kObsBytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0;
+    const bool obs_fast = kObsBytes % 16 == 0 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0;
     for (int t = 0; t < p.T; t++, rowi += p.n) {
         if (p.t_obs) {
             g.encode_obs(g.player(), h.t == 0, srow, scratch, lane);
-            __syncwarp(gm);
+            __syncwarp();
             uint8_t *dst = reinterpret_cast<uint8_t *>(p.t_obs) + rowi * (size_t)kObsBytes;
-            if constexpr (kObsBytes % 16 == 0) {
+            if (!live) warp_tile_zero<LPE>(reinterpret_cast<uint8_t *>(srow), kRowBytes, lane);
+            else if constexpr (kObsBytes % 16 == 0) {
                 if (obs_fast) warp_tile_flush_full<kObsBytes, LPE>(dst, reinterpret_cast<uint8_t *>(srow), lane);
                 else warp_tile_flush<LPE>(dst, reinterpret_cast<uint8_t *>(srow), kObsBytes, lane);
             } else warp_tile_flush<LPE>(dst, reinterpret_cast<uint8_t *>(srow), kObsBytes, lane);
         }
-        if (p.t_mask) warp_write_mask<G, LPE>(p.t_mask, rowi, smask, lane);
+        if (p.t_mask && live) warp_write_mask<G, LPE>(p.t_mask, rowi, smask, lane);
         const uint32_t word = wpolicy_word(ch, p, env, h.k);
         const int k = (int)__umulhi(word, (uint32_t)cnt);
         const int a = g.pick(smask, scratch, k, lane);
         const int pl = g.player();
-        __syncwarp(gm);
+        __syncwarp();
         float pay[G::P];
 #pragma unroll
         for (int q = 0; q < G::P; q++) pay[q] = 0.f;
@@ -381,25 +388,26 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const K
         h.t++; h.k++;
         const bool over = g.over();
         if (over) { g.payoffs(pay); h.episode++; h.t = 0; g.reset(ch, scratch, lane); }
-        __syncwarp(gm);
+        __syncwarp();
         cnt = g.legal(smask, scratch, lane);                      // legal set of the state the next iteration emits
-        __syncwarp(gm);
-        if (lane == 0) {
+        __syncwarp();
+        if (lane == 0 && live) {
             if (p.t_player) st_stream(p.t_player + rowi, pl);
             if (p.t_action) st_stream(p.t_action + rowi, a);
             if (p.t_done) p.t_done[rowi] = over ? 1 : 0;
         }
-        if (p.t_payoffs && lane < G::P) {
+        if (p.t_payoffs && lane < G::P && live) {
             float v = pay[0];
 #pragma unroll
             for (int q = 1; q < G::P; q++) v = lane == q ? pay[q] : v;
             p.t_payoffs[rowi * G::P + lane] = v;
         }
     }
+    err |= ch.err();
+    if (!live) return;
     wchance_close(ch, p, env);
     if (lane == 0) { row[0] = h.episode; row[1] = h.t; row[2] = h.k; }
     g.store(row + kHeaderWords, lane);
-    err |= ch.err();
     if (err && p.err && lane == 0) p.err[env] |= err;
 }
 
