@@ -63,13 +63,19 @@ struct ScoutT {
                            // same values (the state is replicated), so no barrier is needed around these accesses; keeping
                            // them out of the registers drops the 64-bit four-way select chains and 16 registers per thread
     uint64_t tt, tb;
-    int hl[4], score[4], tl, owner, consec, cur, over_;
+    uint32_t hlw, sc01, sc23;     // hand lengths, one byte per seat | scores, 16 bits per seat: a run-time seat is a shift, not a select chain
+    int tl, owner, consec, cur, over_;
     bool forced;           // current_player_forced_scout: recomputed by every legal() (round.py:246)
 
     __device__ __forceinline__ uint64_t top_of(int p) const { return hands[p]; }
     __device__ __forceinline__ uint64_t bot_of(int p) const { return hands[4 + p]; }
-    __device__ __forceinline__ int seli(const int (&a)[4], int p) const { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
-    __device__ __forceinline__ void puti(int (&a)[4], int p, int v) { a[0] = p == 0 ? v : a[0]; a[1] = p == 1 ? v : a[1]; a[2] = p == 2 ? v : a[2]; a[3] = p == 3 ? v : a[3]; }
+    __device__ __forceinline__ int hl_of(int p) const { return (int)((hlw >> (8 * p)) & 255u); }
+    __device__ __forceinline__ void hl_set(int p, int v) { hlw = (hlw & ~(255u << (8 * p))) | ((uint32_t)v << (8 * p)); }
+    __device__ __forceinline__ int score_of(int p) const { return (int)(((p & 2) ? sc23 : sc01) >> (16 * (p & 1)) & 0xffffu); }
+    __device__ __forceinline__ void score_add(int p, int v) {
+        const uint32_t d = (uint32_t)v << (16 * (p & 1));
+        sc01 += (p & 2) ? 0u : d; sc23 += (p & 2) ? d : 0u;
+    }
 
     __device__ __forceinline__ void bind(const KParams &, uint8_t *scratch) { hands = reinterpret_cast<uint64_t *>(scratch + 48); }
     __device__ void load(const uint32_t *w, int lane) {
@@ -81,9 +87,11 @@ struct ScoutT {
         tt = (uint64_t)w[16] | ((uint64_t)w[17] << 32); tb = (uint64_t)w[18] | ((uint64_t)w[19] << 32);
         const uint32_t m = w[20], s0 = w[21], s1 = w[22];
 #pragma unroll
-        for (int p = 0; p < 4; p++) hl[p] = (m >> (5 * p)) & 31;
+        hlw = 0;
+#pragma unroll
+        for (int p = 0; p < 4; p++) hlw |= ((m >> (5 * p)) & 31u) << (8 * p);
         tl = (m >> 20) & 31; owner = (m >> 25) & 7; consec = (m >> 28) & 3; cur = (m >> 30) & 3;
-        score[0] = s0 & 0xffff; score[1] = s0 >> 16; score[2] = s1 & 0xffff; score[3] = (s1 >> 16) & 0x7fff; over_ = s1 >> 31;
+        sc01 = s0; sc23 = s1 & 0x7fffffffu; over_ = s1 >> 31;
         forced = false; lm_valid = false;
     }
     __device__ void store(uint32_t *w, int lane) const {
@@ -94,9 +102,9 @@ struct ScoutT {
             w[8 + 2 * p] = (uint32_t)hands[4 + p]; w[9 + 2 * p] = (uint32_t)(hands[4 + p] >> 32);
         }
         w[16] = (uint32_t)tt; w[17] = (uint32_t)(tt >> 32); w[18] = (uint32_t)tb; w[19] = (uint32_t)(tb >> 32);
-        w[20] = hl[0] | (hl[1] << 5) | (hl[2] << 10) | (hl[3] << 15) | (tl << 20) | (owner << 25) | (consec << 28) | ((uint32_t)cur << 30);
-        w[21] = (uint32_t)score[0] | ((uint32_t)score[1] << 16);
-        w[22] = (uint32_t)score[2] | ((uint32_t)(score[3] & 0x7fff) << 16) | ((uint32_t)over_ << 31);
+        w[20] = hl_of(0) | (hl_of(1) << 5) | (hl_of(2) << 10) | (hl_of(3) << 15) | (tl << 20) | (owner << 25) | (consec << 28) | ((uint32_t)cur << 30);
+        w[21] = sc01;
+        w[22] = (sc23 & 0x7fffffffu) | ((uint32_t)over_ << 31);
     }
 
     // utils/utils.py:17-67 + 144-184 on a nibble slice: valid?, (type 2 group / 1 run / 0 single, rank)
@@ -118,7 +126,7 @@ struct ScoutT {
     // lanes' ranges; the scout ids 136 + 4 ins + {front, front flipped, back, back flipped} are a closed-form pattern.
     __device__ void legal_words(uint32_t (&m)[7], int lane) {
         const uint64_t T = top_of(cur);
-        const int n = seli(hl, cur);
+        const int n = hl_of(cur);
         int ttype = 0, trank = 0;
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
         const int a = nib(T, lane & 15), b = nib(T, (lane + 1) & 15);
@@ -210,7 +218,8 @@ struct ScoutT {
         }
         cur = deck[45];
 #pragma unroll
-        for (int p = 0; p < 4; p++) { hands[p] = nt[p]; hands[4 + p] = nb[p]; hl[p] = p == 0 ? 12 : 11; score[p] = 0; }
+        for (int p = 0; p < 4; p++) { hands[p] = nt[p]; hands[4 + p] = nb[p]; }
+        hlw = 0x0b0b0b0cu; sc01 = sc23 = 0;                                 // 12 cards to seat 0, 11 to the others
         gsync();
         tt = tb = 0; tl = 0; owner = 4; consec = 0; over_ = 0;
         forced = false; lm_valid = false;
@@ -227,7 +236,7 @@ struct ScoutT {
         const int p = cur;
         const bool was_forced = forced;
         uint64_t T = top_of(p), B = bot_of(p);
-        int n = seli(hl, p);
+        int n = hl_of(p);
         if (id < 136) {
             int s = 0, k = id;
             while (k >= 16 - s) { k -= 16 - s; s++; }
@@ -237,7 +246,7 @@ struct ScoutT {
             T = (T & lo) | shl64(shr64(T, 4 * e), 4 * s);
             B = (B & lo) | shl64(shr64(B, 4 * e), 4 * s);
             n -= len;
-            if (tl > 0) puti(score, p, seli(score, p) + tl);
+            score_add(p, tl);
             tt = st; tb = sb; tl = len; owner = p; consec = 0;
         } else {
             const int k = id - 136, front = (k & 3) < 2, flip = k & 1;
@@ -252,13 +261,13 @@ struct ScoutT {
             T = (T & lo) | ((uint64_t)ctop << (4 * ins)) | shl64(T & ~lo, 4);
             B = (B & lo) | ((uint64_t)cbot << (4 * ins)) | shl64(B & ~lo, 4);
             n++;
-            if (was_forced && owner < 4) puti(score, owner, seli(score, owner) + 1);   // Q-SC2
+            if (was_forced && owner < 4) score_add(owner, 1);              // Q-SC2
             consec++;
             if (tl == 0) { owner = 4; consec = 0; }
             if (consec == 3 && owner < 4) over_ = 1;
         }
         wsync();                                                            // every lane has read the old hand
-        hands[p] = T; hands[4 + p] = B; puti(hl, p, n);
+        hands[p] = T; hands[4 + p] = B; hl_set(p, n);
         wsync();
         cur = (p + 1) & 3;
         legal_words(lm, lane);                                              // next player cannot move -> round ends
@@ -267,13 +276,13 @@ struct ScoutT {
     }
     __device__ __forceinline__ void payoffs(float *out) const {             // judger.py:15-30
 #pragma unroll
-        for (int p = 0; p < 4; p++) out[p] = (float)(score[p] - hl[p]);
+        for (int p = 0; p < 4; p++) out[p] = (float)(score_of(p) - hl_of(p));
     }
     // envs/scout.py:171-235 (row pre-zeroed).  Scalars are float32(python float64 expression).
     template <class T> __device__ void encode_obs(int seat, bool, T *row, uint8_t *, int lane) const {
         if (lane < 16) {
             const int s = lane;
-            if (s < seli(hl, seat)) {
+            if (s < hl_of(seat)) {
                 row[s * 10 + nib(top_of(seat), s) - 1] = (T)1;
                 row[160 + s * 10 + nib(bot_of(seat), s) - 1] = (T)1;
                 row[640 + s] = (T)1;
@@ -291,8 +300,8 @@ struct ScoutT {
             float v = 0.f;
             if (lane < 5) v = owner == lane ? 1.f : 0.f;
             else if (lane == 5) v = consec == 0 ? 0.f : (consec == 1 ? (float)(1.0 / 3.0) : (consec == 2 ? (float)(2.0 / 3.0) : 1.f));
-            else if (lane < 10) v = (float)seli(hl, lane - 6) * 0.0625f;
-            else if (lane == 10) v = (float)seli(score, seat) * 0.0625f;
+            else if (lane < 10) v = (float)hl_of(lane - 6) * 0.0625f;
+            else if (lane == 10) v = (float)score_of(seat) * 0.0625f;
             else if (lane == 11) v = (float)tl * 0.0625f;
             else if (lane == 13) v = forced ? 1.f : 0.f;
             else if (lane >= 14) {
