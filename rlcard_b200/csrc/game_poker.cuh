@@ -277,10 +277,11 @@ struct Limit {
             uint32_t d0, d1, d2, d3;                           // common.cuh) give nine cards + blind
             ch.deal_words(d0, d1, d2, d3);
             const uint32_t x1 = __umulhi(d0, 52u * 51u * 50u), x2 = __umulhi(d1, 49u * 48u * 47u), x3 = __umulhi(d2, 46u * 45u * 44u * 2u);
-            j[0] = (int)(x1 / 2550u); j[1] = (int)((x1 / 50u) % 51u); j[2] = (int)(x1 % 50u);
-            j[3] = (int)(x2 / 2256u); j[4] = (int)((x2 / 47u) % 48u); j[5] = (int)(x2 % 47u);
-            const uint32_t z = x3 >> 1;
-            j[6] = (int)(z / 1980u); j[7] = (int)((z / 44u) % 45u); j[8] = (int)(z % 44u);
+            // mixed-radix digits, two divisions per word: x / (a * b) == (x / b) / a
+            const uint32_t q1 = x1 / 50u, q2 = x2 / 47u, z = x3 >> 1, q3 = z / 44u;
+            j[2] = (int)(x1 - 50u * q1); j[0] = (int)(q1 / 51u); j[1] = (int)(q1 - 51u * (uint32_t)j[0]);
+            j[5] = (int)(x2 - 47u * q2); j[3] = (int)(q2 / 48u); j[4] = (int)(q2 - 48u * (uint32_t)j[3]);
+            j[8] = (int)(z - 44u * q3); j[6] = (int)(q3 / 45u); j[7] = (int)(q3 - 45u * (uint32_t)j[6]);
             sb = (int)(x3 & 1u);
         } else {                                               // replay: the reference's 51 shuffle draws + randint
 #pragma unroll

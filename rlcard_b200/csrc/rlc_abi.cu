@@ -10,6 +10,7 @@ namespace rlc {
 cudaError_t dispatch_blackjack(int, int, int, const KParams &, cudaStream_t);
 cudaError_t dispatch_leduc(int, int, int, const KParams &, cudaStream_t);
 cudaError_t leduc_init(int device);
+cudaError_t limit_init(int device);
 cudaError_t dispatch_limit(int, int, int, const KParams &, cudaStream_t);
 cudaError_t judge_holdem(const uint8_t *, int, int, uint8_t *, cudaStream_t);
 cudaError_t judge_leduc(const int32_t *, int, float *, cudaStream_t);
@@ -137,6 +138,12 @@ int rlc_upload_tables(int game_id, int device, const void *blob, size_t nbytes) 
         cudaError_t e = rlc::leduc_init(device);
         return e == cudaSuccess ? RLC_OK : fail(RLC_ECUDA, "leduc table build: %s", cudaGetErrorString(e));
     }
+#ifdef RLC_HAVE_LIMIT
+    if (game_id == RLC_LIMIT) {      /* likewise: the 98 betting states of Limit Hold'em */
+        cudaError_t e = rlc::limit_init(device);
+        return e == cudaSuccess ? RLC_OK : fail(RLC_ECUDA, "limit hold'em table build: %s", cudaGetErrorString(e));
+    }
+#endif
     (void)device; (void)blob; (void)nbytes;
     if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);
     return RLC_OK;   /* the other games have no uploaded tables */

@@ -1,6 +1,8 @@
 // tu_limit.cu -- kernel instantiations for Limit (one translation unit per game: parallel nvcc)
 #include "game_poker.cuh"
 #include "kernels.cuh"
+#include <mutex>
+#include <type_traits>
 namespace rlc {
 
 // ==========================================================================================
@@ -247,6 +249,272 @@ __global__ void __launch_bounds__(32 * kWsWarps) k_rollout_limit_ws(const KParam
     if (err && p.err) p.err[i] |= err;
 }
 
+// ==========================================================================================
+// Table-driven Limit Hold'em rollout (throughput mode, every trajectory stream): the default for the bench / training case.
+//
+// With a thread per env the kernel is bound by the number of dependent instructions one warp issues per env-step (ncu:
+// 495 warp-instructions per warp-step at one warp per scheduler, IPC 0.34; the alu pipe takes one warp-instruction per two
+// cycles).  Three things are taken off that chain:
+//   * betting: everything about a Limit state except the cards, the chips and the raise history is one of 98 "betting
+//     states" (round, pointer, raised amounts, raise / check counters, folds).  Their transition function is tabulated ONCE
+//     per device by running the register engine (Limit::step / legal / over / n_public, game_poker.cuh) over every reachable
+//     state -- table == engine by construction, like the Leduc automaton (tu_leduc.cu).  One uint4 per state:
+//       .x  legal mask [0:4) | is_over [4] | public cards shown [5:8) | state key [11:32) (have_raised 3, not_raise_num 2,
+//           pointer 1, fold0, fold1, raised0 5, raised1 5, round 3 -- the bit fields of the packed state words)
+//       .y  id of the next state after the k-th legal action (ascending id order, a byte each)
+//       .z  id of the k-th legal action (a byte each)      .w  chips the actor adds with it (a byte each)
+//     State ids 0 / 1 open an episode with seat 0 / 1 as small blind.  Chips (one byte per seat) and the raise history
+//     (4 x 3 bits) ride in two registers and are updated from the entry.
+//   * deals: the deal of episode E is a pure function of (seed, env, E) (deal words, common.cuh), so every lane keeps a ring
+//     of prepared deals in shared memory and the warp tops the rings up TOGETHER whenever one runs dry: the Philox block,
+//     the mixed-radix decode and the nine-card Fisher-Yates traceback then run with most lanes active instead of for the
+//     ~10 lanes of 32 that end an episode in any given step (the generic kernel pays a diverged deal in nearly every
+//     warp-step).  A new episode is one 64-bit shared-memory read.
+//   * the showdown (7-card evaluator, Limit::showdown_outcome) stays behind a branch: random play folds 96 % of the time.
+// Same trajectory, state words and Philox draws as k_rollout<Limit, ChancePhilox, ObsT, 64, true, 32>.
+// ==========================================================================================
+constexpr int kLimFsmMax = 128;
+static uint4 *g_lfsm[64];
+static int g_lfsm_n[64];
+static std::mutex g_lfsm_mu;
+
+__device__ __forceinline__ uint32_t lim_key(const Limit &g) {
+    return (uint32_t)g.r.have_raised | ((uint32_t)g.r.not_raise_num << 3) | ((uint32_t)g.r.pointer << 5) | ((uint32_t)g.fold0 << 6) |
+           ((uint32_t)g.fold1 << 7) | ((uint32_t)g.r.raised0 << 8) | ((uint32_t)g.r.raised1 << 13) | ((uint32_t)g.rc << 18);
+}
+__device__ __forceinline__ void lim_unkey(Limit &g, uint32_t k) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) g.card[c] = c;
+    g.chips0 = g.chips1 = 0; g.rn = g.rn_shown = 0;
+    g.r.have_raised = bf_get(k, 0, 3); g.r.not_raise_num = bf_get(k, 3, 2); g.r.pointer = bf_get(k, 5, 1);
+    g.fold0 = bf_get(k, 6, 1); g.fold1 = bf_get(k, 7, 1); g.r.raised0 = bf_get(k, 8, 5); g.r.raised1 = bf_get(k, 13, 5);
+    g.rc = bf_get(k, 18, 3);
+}
+// single thread: breadth-first closure of the two opening states under Limit::step
+__global__ void k_limit_build_fsm(uint4 *tab, int *count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ uint32_t keys[kLimFsmMax];
+    int n = 0;
+    for (int sb = 0; sb < 2; sb++) {                         // game.py:71-103 with the blind draw fixed
+        Limit g; lim_unkey(g, 0);
+        g.r.start(sb, sb == 0 ? 1 : 2, sb == 0 ? 2 : 1);
+        keys[n++] = lim_key(g);
+    }
+    ChancePhilox none; none.init(0, 0);
+    for (int i = 0; i < n; i++) {
+        Limit g; lim_unkey(g, keys[i]);
+        uint32_t m[1]; g.legal(m);
+        const bool over = g.over();
+        uint32_t x = (m[0] & 15u) | (over ? 16u : 0u) | ((uint32_t)g.n_public() << 5) | (keys[i] << 11), y = 0, z = 0, w = 0;
+        if (!over) {
+            int kth = 0;
+            for (int a = 0; a < 4; a++) {
+                if (!((m[0] >> a) & 1u)) continue;
+                Limit h; lim_unkey(h, keys[i]);
+                int err = 0;
+                const int actor = h.player();
+                h.step(a, none, err);
+                const int diff = actor ? h.chips1 : h.chips0;
+                if (err || diff < 0 || diff > 255 || (actor ? h.chips0 : h.chips1) != 0) { *count = -2; return; }
+                // the raise history moves exactly as the rollout kernel assumes: +1 in the field of the acting round on a raise
+                const uint32_t rc = (uint32_t)g.rc;
+                if (h.rn != (((uint32_t)g.r.have_raised + (a == kRaise ? 1u : 0u)) << (3u * rc))) { *count = -3; return; }
+                const uint32_t k2 = lim_key(h);
+                int j = 0;
+                while (j < n && keys[j] != k2) j++;
+                if (j == n) { if (n >= kLimFsmMax) { *count = -1; return; } keys[n++] = k2; }
+                y |= (uint32_t)j << (8 * kth);
+                z |= (uint32_t)a << (8 * kth);
+                w |= (uint32_t)diff << (8 * kth);
+                kth++;
+            }
+        }
+        tab[i] = make_uint4(x, y, z, w);
+    }
+    *count = n;
+}
+// Built once per device by rlc_upload_tables(RLC_LIMIT, device, NULL, 0) (VecEnv does it at construction); until then the
+// rollout runs the generic register engine (same results).
+cudaError_t limit_init(int device) {
+    if (device < 0 || device >= 64) return cudaErrorInvalidValue;
+    std::lock_guard<std::mutex> lock(g_lfsm_mu);
+    if (g_lfsm[device]) return cudaSuccess;
+    int prev = 0; cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    uint4 *tab = nullptr; int *cnt = nullptr, h = 0;
+    e = cudaMalloc(&tab, sizeof(uint4) * kLimFsmMax);
+    if (e == cudaSuccess) e = cudaMalloc(&cnt, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(tab, 0, sizeof(uint4) * kLimFsmMax);
+    if (e == cudaSuccess) { k_limit_build_fsm<<<1, 32>>>(tab, cnt); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && h <= 0) e = cudaErrorUnknown;
+    if (cnt) cudaFree(cnt);
+    if (e == cudaSuccess) { g_lfsm[device] = tab; g_lfsm_n[device] = h; }
+    else if (tab) cudaFree(tab);
+    cudaSetDevice(prev);
+    return e;
+}
+static const uint4 *limit_fsm_on_device(int &n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lfsm_mu);
+    n = g_lfsm_n[dev];
+    return g_lfsm[dev];
+}
+__device__ __forceinline__ uint32_t lim_byte(uint32_t w, uint32_t k) { return __byte_perm(w, 0u, 0x4440u | k); }
+
+template <class ObsT, int BLOCK, int RING>
+__global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, const uint4 *__restrict__ gtab, int nstates) {
+    extern __shared__ uint4 smem_raw[];
+    constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = BLOCK * kRowBytes;
+    uint4 *stab = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
+    uint2 *ring_all = reinterpret_cast<uint2 *>(stab + kLimFsmMax);          // [BLOCK / 32][RING][32]
+    for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
+    if (warp_env0 >= p.n) return;
+    const size_t i = warp_env0 + lane;
+    const bool valid = i < p.n;
+    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * Limit::OBS;
+    ObsT *row = tile + lane * Limit::OBS;
+    uint2 *ring = ring_all + (size_t)wib * RING * 32 + lane;                 // deal of episode E: ring[(E % RING) * 32]
+    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    __syncwarp();
+
+    EnvHeader h; h.episode = 0; h.t = 0; h.k = 0;
+    ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
+    uint32_t c_lo = 0, c_hi = 0, sid = 0;      // cards 0..4 / 5..8, six bits each (state words 0 / 1) ; betting-state id
+    uint32_t chips = 0, rn = 0, rn_shown = 0;  // chips0 | chips1 << 8 ; raise counters of the four rounds, 3 bits each (Q-LH1: + the list the reset() state shows)
+    bool fresh = false;                        // the env starts a new episode before its first step
+    if (valid) {
+        h.load(p.state, p.n, i);
+        const uint32_t *gw = p.state + kHeaderWords * p.n;
+        const uint32_t w0 = gw[i], w1 = gw[p.n + i], w2 = gw[2 * p.n + i], w3 = gw[3 * p.n + i];
+        c_lo = w0 & 0x3fffffffu; c_hi = w1 & 0xffffffu;
+        chips = bf_get(w2, 0, 6) | (bf_get(w2, 6, 6) << 8);
+        rn = w3 & 0xfffu; rn_shown = (w3 >> 12) & 0xfffu;
+        const uint32_t key = bf_get(w1, 24, 3) | (bf_get(w1, 27, 2) << 3) | (bf_get(w1, 29, 1) << 5) | (bf_get(w1, 30, 1) << 6) |
+                             (bf_get(w1, 31, 1) << 7) | (bf_get(w2, 12, 5) << 8) | (bf_get(w2, 17, 5) << 13) | (bf_get(w2, 22, 3) << 18);
+        int found = -1;
+        for (int j = 0; j < nstates; j++) if ((stab[j].x >> 11) == key) { found = j; break; }
+        // never dealt, a finished episode left by rlc_step without auto reset (or a state outside the table): deal first
+        fresh = h.episode == 0 || found < 0 || ((stab[found].x >> 4) & 1u);
+        sid = found < 0 ? 0u : (uint32_t)found;
+    }
+    uint32_t filled = h.episode;               // deals prepared for every episode ordinal <= filled
+    // top the deal rings up: every lane short of `cap` prepared deals makes one per round, all such lanes together
+    auto refill = [&](uint32_t cap) {
+        for (;;) {
+            const bool need = valid && filled - h.episode < cap;
+            if (!__any_sync(0xffffffffu, need)) break;
+            if (need) {
+                Limit g; g.rn = 0;
+                ChancePhilox dc = ch;
+                dc.begin_episode(filled + 1u);
+                g.reset(dc);                                   // deal words (episode-keyed) -> nine cards + small blind
+                const uint2 d = limit_pack_cards(g);
+                filled++;
+                ring[(filled % RING) * 32] = make_uint2(d.x | ((uint32_t)g.r.pointer << 30), d.y);
+            }
+        }
+    };
+    auto open_episode = [&]() {                // game.py:46-103 once the deal is known
+        h.episode++; h.t = 0;
+        const uint2 d = ring[(h.episode % RING) * 32];
+        c_lo = d.x & 0x3fffffffu; c_hi = d.y;
+        sid = d.x >> 30;                                       // states 0 / 1: seat 0 / 1 is the small blind
+        chips = sid ? (2u | (1u << 8)) : (1u | (2u << 8));
+        rn_shown = rn; rn = 0;                                 // Q-LH1
+    };
+    refill((uint32_t)min(RING, p.T + 1));
+    __syncwarp();
+    if (fresh) open_episode();
+    uint4 e = stab[sid];
+    uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
+    const size_t obs_step = p.n * (size_t)kRowBytes;
+    const bool full_warp = nvalid == 32;
+    size_t rowi = i;
+    auto run = [&](auto full_c) {
+    constexpr bool kFullWarp = decltype(full_c)::value;
+    const bool live = kFullWarp || valid;
+    for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
+        if (__any_sync(0xffffffffu, live && filled == h.episode)) {       // some lane could not open its next episode
+            refill((uint32_t)min(RING, p.T - t));
+            __syncwarp();
+        }
+        const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
+        if (live) {                            // envs/limitholdem.py:40-71 (Limit::encode_obs): hole cards of the acting seat,
+            const uint32_t sh = 6u * ptr;      // the public cards shown in this round, the four raise counters one-hot
+            row[(c_lo >> sh) & 63u] = (ObsT)1; row[(c_lo >> (sh + 12u)) & 63u] = (ObsT)1;
+            const uint32_t np_ = (e.x >> 5) & 7u;
+            if (np_ >= 3u) { row[(c_lo >> 24) & 63u] = (ObsT)1; row[c_hi & 63u] = (ObsT)1; row[(c_hi >> 6) & 63u] = (ObsT)1; }
+            if (np_ >= 4u) row[(c_hi >> 12) & 63u] = (ObsT)1;
+            if (np_ >= 5u) row[(c_hi >> 18) & 63u] = (ObsT)1;
+            const uint32_t shown = h.t == 0 ? rn_shown : rn;
+            row[52 + (shown & 7u)] = (ObsT)1; row[57 + ((shown >> 3) & 7u)] = (ObsT)1;
+            row[62 + ((shown >> 6) & 7u)] = (ObsT)1; row[67 + ((shown >> 9) & 7u)] = (ObsT)1;
+        }
+        __syncwarp();
+        if constexpr (kFullWarp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+        else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+        if (live) {
+            st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
+            st_stream(p.t_player + rowi, (int)ptr);
+            const uint32_t word = ch.begin_step(h.k);
+            const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
+            const uint32_t a = lim_byte(e.z, kth);
+            st_stream(p.t_action + rowi, (int)a);
+            chips += lim_byte(e.w, kth) << (8u * ptr);
+            rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
+            sid = lim_byte(e.y, kth);
+            e = stab[sid];
+            h.t++; h.k++;
+            const bool over = (e.x >> 4) & 1u;
+            float2 pay = make_float2(0.f, 0.f);
+            if (over) {                        // game.py:233-243, judger.py:11-108 for two players
+                const uint32_t f0 = (e.x >> 17) & 1u, f1 = (e.x >> 18) & 1u;
+                int oc = f1 ? 0 : 1;
+                if ((f0 | f1) == 0u) {         // showdown: random play rarely gets here, whole warps skip the evaluator
+                    Limit g;
+                    limit_unpack_cards(g, make_uint2(c_lo, c_hi));
+                    oc = g.showdown_outcome();
+                }
+                const float pot = (float)min(chips & 255u, chips >> 8);
+                const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * pot;
+                pay = make_float2(p0, -p0);
+                open_episode();
+                e = stab[sid];
+            }
+            p.t_done[rowi] = over ? 1 : 0;
+            st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+        }
+        __syncwarp();
+    }
+    };
+    if (full_warp) run(std::true_type{}); else run(std::false_type{});
+    if (valid) {
+        h.store(p.state, p.n, i);
+        uint32_t *gw = p.state + kHeaderWords * p.n;
+        const uint32_t k = e.x >> 11;
+        gw[i] = c_lo;
+        gw[p.n + i] = c_hi | (bf_get(k, 0, 3) << 24) | (bf_get(k, 3, 2) << 27) | (bf_get(k, 5, 1) << 29) | (bf_get(k, 6, 1) << 30) | (bf_get(k, 7, 1) << 31);
+        gw[2 * p.n + i] = (chips & 63u) | (((chips >> 8) & 63u) << 6) | (bf_get(k, 8, 5) << 12) | (bf_get(k, 13, 5) << 17) | (bf_get(k, 18, 3) << 22);
+        gw[3 * p.n + i] = rn | (rn_shown << 12);
+    }
+}
+
+template <class ObsT>
+static cudaError_t launch_limit_fsm(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
+    constexpr int BLOCK = 64, RING = 8;
+    const size_t smem = (size_t)BLOCK * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + (size_t)(BLOCK / 32) * RING * 32 * sizeof(uint2);
+    k_rollout_limit_fsm<ObsT, BLOCK, RING><<<(unsigned)((p.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(p, tab, nstates);
+    return cudaGetLastError();
+}
+
 template <class ObsT>
 static cudaError_t launch_limit_ws(const KParams &p, cudaStream_t s) {
     constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
@@ -265,6 +533,17 @@ cudaError_t dispatch_limit(int op, int chance, int obs_dtype, const KParams &p, 
         p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs) {
         if (obs_dtype == RLC_U8 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0) return launch_limit_ws<uint8_t>(p, s);
         if (obs_dtype == RLC_F32 && (reinterpret_cast<uintptr_t>(p.t_obs) & 15u) == 0) return launch_limit_ws<float>(p, s);
+    }
+    // default for the same case: the tabulated engine with per-lane deal rings (RLC_LIMIT_FSM=0 keeps the generic kernel)
+    const char *fsm = getenv("RLC_LIMIT_FSM");
+    int nstates = 0;
+    const uint4 *tab = nullptr;
+    if (!(fsm && fsm[0] == '0') && op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & kFlagNoFsm) && p.T > 0 && p.t_obs &&
+        p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs && (tab = limit_fsm_on_device(nstates)) != nullptr) {
+        if (obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS)) & 15u) == 0)
+            return launch_limit_fsm<uint8_t>(p, tab, nstates, s);
+        if (obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS * 4)) & 15u) == 0)
+            return launch_limit_fsm<float>(p, tab, nstates, s);
     }
     return dispatch_game<Limit>(op, chance, obs_dtype, p, s);
 }

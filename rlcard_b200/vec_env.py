@@ -128,7 +128,7 @@ class VecEnv:
         self.launches = 0
         if env_id == 'doudizhu':
             _upload_doudizhu_tables(self.L, self.device)
-        elif env_id == 'leduc-holdem':             # betting-state table of the tabulated rollout: explicit one-time init
+        elif env_id in ('leduc-holdem', 'limit-holdem'):   # betting-state table of the tabulated rollout: explicit one-time init
             idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
             check(self.L.rlc_upload_tables(self.gid, idx, None, 0))
 
