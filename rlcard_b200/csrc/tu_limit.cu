@@ -364,25 +364,37 @@ static const uint4 *limit_fsm_on_device(int &n) {
 }
 __device__ __forceinline__ uint32_t lim_byte(uint32_t w, uint32_t k) { return __byte_perm(w, 0u, 0x4440u | k); }
 
-template <class ObsT, int BLOCK, int RING>
+// SPLIT = 2: the env-step chain of a group of 32 envs is cut in two and run by the two warps of a 64-thread block.  The
+// automaton is so cheap (~50 instructions per step) that BOTH warps simply run it -- same table, same Philox words, same
+// deals, so they stay in step without ever exchanging a value -- and each emits half of the trajectory: warp 0 the obs rows
+// (tile, 128-bit streaming stores), warp 1 the mask / player / action / done / payoff streams, the showdowns and the final
+// state.  The deal rings are shared: the rounds of a top-up alternate between the two warps (a round = one deal for every lane that is short),
+// and one block barrier per top-up publishes them (the ring has 2 x RING slots, so a deal written in top-up r only
+// replaces one that both warps consumed before top-up r - 1).  SPLIT = 1: one warp does everything (64-thread blocks
+// then hold two groups).
+template <class ObsT, int BLOCK, int RING, int SPLIT>
 __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, const uint4 *__restrict__ gtab, int nstates) {
     extern __shared__ uint4 smem_raw[];
+    constexpr int kGroups = BLOCK / 32 / SPLIT, kSlots = SPLIT == 2 ? 2 * RING : RING;
     constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
-    constexpr int kTileBytes = BLOCK * kRowBytes;
+    constexpr int kTileBytes = kGroups * 32 * kRowBytes;
     uint4 *stab = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
-    uint2 *ring_all = reinterpret_cast<uint2 *>(stab + kLimFsmMax);          // [BLOCK / 32][RING][32]
+    uint2 *ring_all = reinterpret_cast<uint2 *>(stab + kLimFsmMax);          // [kGroups][kSlots][32]
     for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t warp_env0 = ((size_t)blockIdx.x * (BLOCK / 32) + wib) * 32;
-    if (warp_env0 >= p.n) return;
+    const int grp = SPLIT == 2 ? wib >> 1 : wib, role = SPLIT == 2 ? wib & 1 : 0;   // role 0 emits obs rows, role 1 the other streams
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" :: "r"(1 + grp) : "memory"); };   // the two warps of a group
+    const bool obs_role = SPLIT == 1 || role == 0, str_role = SPLIT == 1 || role == 1;
+    const size_t warp_env0 = ((size_t)blockIdx.x * kGroups + grp) * 32;
+    if (warp_env0 >= p.n) return;                                            // both warps of a group: no barrier is left waiting
     const size_t i = warp_env0 + lane;
     const bool valid = i < p.n;
     const int nvalid = (int)min((size_t)32, p.n - warp_env0);
-    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)wib * 32 * Limit::OBS;
+    ObsT *tile = reinterpret_cast<ObsT *>(smem_raw) + (size_t)grp * 32 * Limit::OBS;
     ObsT *row = tile + lane * Limit::OBS;
-    uint2 *ring = ring_all + (size_t)wib * RING * 32 + lane;                 // deal of episode E: ring[(E % RING) * 32]
-    warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
+    uint2 *ring = ring_all + (size_t)grp * kSlots * 32 + lane;               // deal of episode E: ring[(E % kSlots) * 32]
+    if (obs_role) warp_tile_zero(reinterpret_cast<uint8_t *>(tile), 32 * kRowBytes, lane);
     __syncwarp();
 
     EnvHeader h; h.episode = 0; h.t = 0; h.k = 0;
@@ -405,33 +417,36 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
         fresh = h.episode == 0 || found < 0 || ((stab[found].x >> 4) & 1u);
         sid = found < 0 ? 0u : (uint32_t)found;
     }
+    if constexpr (SPLIT == 2) pair_sync();                    // both warps have read the state words before either may store them
     uint32_t filled = h.episode;               // deals prepared for every episode ordinal <= filled
-    // top the deal rings up: every lane short of `cap` prepared deals makes one per round, all such lanes together
+    // top the deal rings up: every lane short of `cap` prepared deals gets one per round, all such lanes together
     auto refill = [&](uint32_t cap) {
-        for (;;) {
+        for (uint32_t round = 0;; round++) {
             const bool need = valid && filled - h.episode < cap;
             if (!__any_sync(0xffffffffu, need)) break;
             if (need) {
-                Limit g; g.rn = 0;
-                ChancePhilox dc = ch;
-                dc.begin_episode(filled + 1u);
-                g.reset(dc);                                   // deal words (episode-keyed) -> nine cards + small blind
-                const uint2 d = limit_pack_cards(g);
                 filled++;
-                ring[(filled % RING) * 32] = make_uint2(d.x | ((uint32_t)g.r.pointer << 30), d.y);
+                if (SPLIT == 1 || (round & 1u) == (uint32_t)role) {            // whole rounds alternate between the two warps
+                    Limit g; g.rn = 0;
+                    ChancePhilox dc = ch;
+                    dc.begin_episode(filled);
+                    g.reset(dc);                               // deal words (episode-keyed) -> nine cards + small blind
+                    const uint2 d = limit_pack_cards(g);
+                    ring[(filled % kSlots) * 32] = make_uint2(d.x | ((uint32_t)g.r.pointer << 30), d.y);
+                }
             }
         }
+        if constexpr (SPLIT == 2) pair_sync(); else __syncwarp();
     };
     auto open_episode = [&]() {                // game.py:46-103 once the deal is known
         h.episode++; h.t = 0;
-        const uint2 d = ring[(h.episode % RING) * 32];
+        const uint2 d = ring[(h.episode % kSlots) * 32];
         c_lo = d.x & 0x3fffffffu; c_hi = d.y;
         sid = d.x >> 30;                                       // states 0 / 1: seat 0 / 1 is the small blind
         chips = sid ? (2u | (1u << 8)) : (1u | (2u << 8));
         rn_shown = rn; rn = 0;                                 // Q-LH1
     };
     refill((uint32_t)min(RING, p.T + 1));
-    __syncwarp();
     if (fresh) open_episode();
     uint4 e = stab[sid];
     uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
@@ -442,32 +457,34 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
     constexpr bool kFullWarp = decltype(full_c)::value;
     const bool live = kFullWarp || valid;
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
-        if (__any_sync(0xffffffffu, live && filled == h.episode)) {       // some lane could not open its next episode
+        if (__any_sync(0xffffffffu, live && filled == h.episode))         // some lane could not open its next episode
             refill((uint32_t)min(RING, p.T - t));
-            __syncwarp();
-        }
         const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
-        if (live) {                            // envs/limitholdem.py:40-71 (Limit::encode_obs): hole cards of the acting seat,
-            const uint32_t sh = 6u * ptr;      // the public cards shown in this round, the four raise counters one-hot
-            row[(c_lo >> sh) & 63u] = (ObsT)1; row[(c_lo >> (sh + 12u)) & 63u] = (ObsT)1;
-            const uint32_t np_ = (e.x >> 5) & 7u;
-            if (np_ >= 3u) { row[(c_lo >> 24) & 63u] = (ObsT)1; row[c_hi & 63u] = (ObsT)1; row[(c_hi >> 6) & 63u] = (ObsT)1; }
-            if (np_ >= 4u) row[(c_hi >> 12) & 63u] = (ObsT)1;
-            if (np_ >= 5u) row[(c_hi >> 18) & 63u] = (ObsT)1;
-            const uint32_t shown = h.t == 0 ? rn_shown : rn;
-            row[52 + (shown & 7u)] = (ObsT)1; row[57 + ((shown >> 3) & 7u)] = (ObsT)1;
-            row[62 + ((shown >> 6) & 7u)] = (ObsT)1; row[67 + ((shown >> 9) & 7u)] = (ObsT)1;
+        if (obs_role) {
+            if (live) {                        // envs/limitholdem.py:40-71 (Limit::encode_obs): hole cards of the acting seat,
+                const uint32_t sh = 6u * ptr;  // the public cards shown in this round, the four raise counters one-hot
+                row[(c_lo >> sh) & 63u] = (ObsT)1; row[(c_lo >> (sh + 12u)) & 63u] = (ObsT)1;
+                const uint32_t np_ = (e.x >> 5) & 7u;
+                if (np_ >= 3u) { row[(c_lo >> 24) & 63u] = (ObsT)1; row[c_hi & 63u] = (ObsT)1; row[(c_hi >> 6) & 63u] = (ObsT)1; }
+                if (np_ >= 4u) row[(c_hi >> 12) & 63u] = (ObsT)1;
+                if (np_ >= 5u) row[(c_hi >> 18) & 63u] = (ObsT)1;
+                const uint32_t shown = h.t == 0 ? rn_shown : rn;
+                row[52 + (shown & 7u)] = (ObsT)1; row[57 + ((shown >> 3) & 7u)] = (ObsT)1;
+                row[62 + ((shown >> 6) & 7u)] = (ObsT)1; row[67 + ((shown >> 9) & 7u)] = (ObsT)1;
+            }
+            __syncwarp();
+            if constexpr (kFullWarp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+            else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         }
-        __syncwarp();
-        if constexpr (kFullWarp) warp_tile_flush_full<32 * kRowBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
-        else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
         if (live) {
-            st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
-            st_stream(p.t_player + rowi, (int)ptr);
+            if (str_role) {
+                st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
+                st_stream(p.t_player + rowi, (int)ptr);
+            }
             const uint32_t word = ch.begin_step(h.k);
             const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
             const uint32_t a = lim_byte(e.z, kth);
-            st_stream(p.t_action + rowi, (int)a);
+            if (str_role) st_stream(p.t_action + rowi, (int)a);
             chips += lim_byte(e.w, kth) << (8u * ptr);
             rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
             sid = lim_byte(e.y, kth);
@@ -476,27 +493,31 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
             const bool over = (e.x >> 4) & 1u;
             float2 pay = make_float2(0.f, 0.f);
             if (over) {                        // game.py:233-243, judger.py:11-108 for two players
-                const uint32_t f0 = (e.x >> 17) & 1u, f1 = (e.x >> 18) & 1u;
-                int oc = f1 ? 0 : 1;
-                if ((f0 | f1) == 0u) {         // showdown: random play rarely gets here, whole warps skip the evaluator
-                    Limit g;
-                    limit_unpack_cards(g, make_uint2(c_lo, c_hi));
-                    oc = g.showdown_outcome();
+                if (str_role) {
+                    const uint32_t f0 = (e.x >> 17) & 1u, f1 = (e.x >> 18) & 1u;
+                    int oc = f1 ? 0 : 1;
+                    if ((f0 | f1) == 0u) {     // showdown: random play rarely gets here, whole warps skip the evaluator
+                        Limit g;
+                        limit_unpack_cards(g, make_uint2(c_lo, c_hi));
+                        oc = g.showdown_outcome();
+                    }
+                    const float pot = (float)min(chips & 255u, chips >> 8);
+                    const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * pot;
+                    pay = make_float2(p0, -p0);
                 }
-                const float pot = (float)min(chips & 255u, chips >> 8);
-                const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * pot;
-                pay = make_float2(p0, -p0);
                 open_episode();
                 e = stab[sid];
             }
-            p.t_done[rowi] = over ? 1 : 0;
-            st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+            if (str_role) {
+                p.t_done[rowi] = over ? 1 : 0;
+                st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+            }
         }
         __syncwarp();
     }
     };
     if (full_warp) run(std::true_type{}); else run(std::false_type{});
-    if (valid) {
+    if (valid && str_role) {
         h.store(p.state, p.n, i);
         uint32_t *gw = p.state + kHeaderWords * p.n;
         const uint32_t k = e.x >> 11;
@@ -507,12 +528,27 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
     }
 }
 
+template <class ObsT, int SPLIT, int BLOCK>
+static cudaError_t launch_limit_fsm_split(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
+    constexpr int RING = 8, kGroups = BLOCK / 32 / SPLIT, kSlots = SPLIT == 2 ? 2 * RING : RING;
+    const size_t smem = (size_t)kGroups * 32 * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + (size_t)kGroups * kSlots * 32 * sizeof(uint2);
+    const size_t per_block = (size_t)kGroups * 32;
+    k_rollout_limit_fsm<ObsT, BLOCK, RING, SPLIT><<<(unsigned)((p.n + per_block - 1) / per_block), BLOCK, smem, s>>>(p, tab, nstates);
+    return cudaGetLastError();
+}
 template <class ObsT>
 static cudaError_t launch_limit_fsm(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
-    constexpr int BLOCK = 64, RING = 8;
-    const size_t smem = (size_t)BLOCK * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + (size_t)(BLOCK / 32) * RING * 32 * sizeof(uint2);
-    k_rollout_limit_fsm<ObsT, BLOCK, RING><<<(unsigned)((p.n + BLOCK - 1) / BLOCK), BLOCK, smem, s>>>(p, tab, nstates);
-    return cudaGetLastError();
+    const char *sp = getenv("RLC_LIMIT_FSM");                  // "1": one warp per group; default: the two-warp split
+    const char *bs = getenv("RLC_LIMIT_BLOCK");
+    const int block = bs ? atoi(bs) : 128;              // measured 64 / 128 / 256: 0.1032 / 0.1007 / 0.0996 ms at 16 384 envs (256 leaves 20 SMs empty)
+    if (sp && sp[0] == '1') {
+        if (block == 32) return launch_limit_fsm_split<ObsT, 1, 32>(p, tab, nstates, s);
+        if (block == 128) return launch_limit_fsm_split<ObsT, 1, 128>(p, tab, nstates, s);
+        return launch_limit_fsm_split<ObsT, 1, 64>(p, tab, nstates, s);
+    }
+    if (block == 128) return launch_limit_fsm_split<ObsT, 2, 128>(p, tab, nstates, s);
+    if (block == 256) return launch_limit_fsm_split<ObsT, 2, 256>(p, tab, nstates, s);
+    return launch_limit_fsm_split<ObsT, 2, 64>(p, tab, nstates, s);
 }
 
 template <class ObsT>
