@@ -222,6 +222,65 @@ __device__ __forceinline__ uint32_t holdem_strength_masks(const uint32_t (&s)[4]
     return v;
 }
 
+// ---- the same evaluator over lookup tables (north_star: "7-card hand evaluator via shared-memory lookup tables") ----------
+// Two tables, tabulated ONCE per device from the functions above (tu_limit.cu k_holdem_build_tables: table == engine) and
+// staged in shared memory by the kernels that score showdowns in their inner loop:
+//   card64[52]  card id -> its bit in a 4 x 16-bit layout (suit s, rank bit r -> bit 16 s + r): seven cards are seven
+//               64-bit loads OR-ed together instead of seven div / mod / four-way select sequences
+//   t5[8192]    13-bit rank mask -> 0x8000 | straight_top(m) when m holds a straight, else its five highest bits
+//               (top_bits(m, 5)): one look-up answers "straight?" / "straight flush?" and yields the flush / high-card
+//               kickers
+// With the tables the categories are tested in order of rank and only the winning one is scored: at a Limit showdown one
+// or two lanes of the warp are active, so a branchy evaluator costs its own path (~60 instructions), not the sum of all
+// nine categories (~180 branch free).  Returns exactly holdem_strength_masks().
+struct HoldemLut { const unsigned long long *card64; const uint16_t *t5; };
+constexpr int kHoldemLutBytes = 52 * 8 + 8192 * 2;           // card64 | t5, in this order (16-byte aligned sizes)
+__device__ __forceinline__ uint32_t holdem_strength_lut(const uint32_t (&s)[4], const uint16_t *t5) {
+    const uint32_t any = s[0] | s[1] | s[2] | s[3];
+    uint32_t fl = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) fl = __popc(s[k]) >= 5 ? s[k] : fl;
+    if (fl) {                                                  // seven cards: a flush excludes quads and full houses
+        const uint32_t e = t5[fl];
+        return (e & 0x8000u) ? (9u << 26) | (e & 15u) : (6u << 26) | e;
+    }
+    const uint32_t x4 = s[0] & s[1] & s[2] & s[3];
+    if (x4) {
+        const uint32_t q = top_bit(x4);
+        return (8u << 26) | (q << 4) | top_bit(any & ~(1u << q));
+    }
+    const uint32_t x3 = (s[0] & s[1] & s[2]) | (s[0] & s[1] & s[3]) | (s[0] & s[2] & s[3]) | (s[1] & s[2] & s[3]);
+    const uint32_t x2 = ((s[0] & s[1]) | (s[0] & s[2]) | (s[0] & s[3]) | (s[1] & s[2]) | (s[1] & s[3]) | (s[2] & s[3])) & ~x3;
+    const uint32_t t3 = top_bit(x3);
+    if (x3) {
+        const uint32_t rest3 = (x3 & ~(1u << t3)) | x2;
+        if (rest3) return (7u << 26) | (t3 << 4) | top_bit(rest3);
+    }
+    const uint32_t e = t5[any];
+    if (e & 0x8000u) return (5u << 26) | (e & 15u);
+    if (x3) return (4u << 26) | (t3 << 13) | top_bits(any & ~(1u << t3), 2);
+    if (x2) {
+        const uint32_t p2 = top_bit(x2), r2 = x2 & ~(1u << p2);
+        if (r2) {
+            const uint32_t p2b = top_bit(r2);
+            return (3u << 26) | (p2 << 17) | (p2b << 13) | top_bits(any & ~(1u << p2) & ~(1u << p2b), 1);
+        }
+        return (2u << 26) | (p2 << 13) | top_bits(any & ~(1u << p2), 3);
+    }
+    return (1u << 26) | e;                                    // seven distinct ranks, no straight: e = the five highest
+}
+// who wins a showdown of the nine cards (w0 / w1 card fields of the Limit state words): 0 seat 0, 1 seat 1, 2 split
+__device__ __forceinline__ int holdem_showdown_lut(uint32_t c_lo, uint32_t c_hi, const HoldemLut &lut) {
+    const unsigned long long bd = lut.card64[(c_lo >> 24) & 63u] | lut.card64[c_hi & 63u] | lut.card64[(c_hi >> 6) & 63u] |
+                                  lut.card64[(c_hi >> 12) & 63u] | lut.card64[(c_hi >> 18) & 63u];
+    const unsigned long long h0 = bd | lut.card64[c_lo & 63u] | lut.card64[(c_lo >> 12) & 63u];
+    const unsigned long long h1 = bd | lut.card64[(c_lo >> 6) & 63u] | lut.card64[(c_lo >> 18) & 63u];
+    const uint32_t m0[4] = { (uint32_t)h0 & 0x1fffu, (uint32_t)(h0 >> 16) & 0x1fffu, (uint32_t)(h0 >> 32) & 0x1fffu, (uint32_t)(h0 >> 48) & 0x1fffu };
+    const uint32_t m1[4] = { (uint32_t)h1 & 0x1fffu, (uint32_t)(h1 >> 16) & 0x1fffu, (uint32_t)(h1 >> 32) & 0x1fffu, (uint32_t)(h1 >> 48) & 0x1fffu };
+    const uint32_t s0 = holdem_strength_lut(m0, lut.t5), s1 = holdem_strength_lut(m1, lut.t5);
+    return s0 > s1 ? 0 : (s1 > s0 ? 1 : 2);
+}
+
 // ========================================================================================
 // Limit Hold'em: 4 game words.
 //  w0: cards 0..4 (6 bits each): hole p0a, p1a, p0b, p1b (deal order game.py:68-69), flop0

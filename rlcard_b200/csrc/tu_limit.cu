@@ -276,7 +276,27 @@ __global__ void __launch_bounds__(32 * kWsWarps) k_rollout_limit_ws(const KParam
 constexpr int kLimFsmMax = 128;
 static uint4 *g_lfsm[64];
 static int g_lfsm_n[64];
+static uint8_t *g_hlut[64];                  // evaluator tables (game_poker.cuh HoldemLut): card64[52] | t5[8192]
 static std::mutex g_lfsm_mu;
+
+// the evaluator's lookup tables, tabulated from the evaluator's own functions (holdem_add_card, straight_top, top_bits)
+__global__ void k_holdem_build_tables(uint8_t *blob) {
+    unsigned long long *card64 = reinterpret_cast<unsigned long long *>(blob);
+    uint16_t *t5 = reinterpret_cast<uint16_t *>(blob + 52 * 8);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 52) {
+        uint32_t m[4] = {0, 0, 0, 0};
+        holdem_add_card(m, i);
+        card64[i] = (unsigned long long)m[0] | ((unsigned long long)m[1] << 16) | ((unsigned long long)m[2] << 32) | ((unsigned long long)m[3] << 48);
+    }
+    if (i < 8192) {
+        const uint32_t m = (uint32_t)i, st = (uint32_t)straight_top(m);
+        uint32_t top = m;
+        while (__popc(top) > 5) top &= top - 1;              // == top_bits(m, 5) wherever that is defined (<= 8 bits set)
+        if (__popc(m) <= 8 && top != top_bits(m, 5)) top = 0xffffu;   // poison: the KATs would fail
+        t5[i] = (uint16_t)(st ? (0x8000u | st) : top);
+    }
+}
 
 __device__ __forceinline__ uint32_t lim_key(const Limit &g) {
     return (uint32_t)g.r.have_raised | ((uint32_t)g.r.not_raise_num << 3) | ((uint32_t)g.r.pointer << 5) | ((uint32_t)g.fold0 << 6) |
@@ -350,10 +370,23 @@ cudaError_t limit_init(int device) {
     if (e == cudaSuccess) e = cudaMemcpy(&h, cnt, sizeof h, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && h <= 0) e = cudaErrorUnknown;
     if (cnt) cudaFree(cnt);
-    if (e == cudaSuccess) { g_lfsm[device] = tab; g_lfsm_n[device] = h; }
-    else if (tab) cudaFree(tab);
+    uint8_t *lut = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&lut, kHoldemLutBytes);
+    if (e == cudaSuccess) { k_holdem_build_tables<<<8192 / 128, 128>>>(lut); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) { g_lfsm[device] = tab; g_lfsm_n[device] = h; g_hlut[device] = lut; }
+    else { if (tab) cudaFree(tab); if (lut) cudaFree(lut); }
     cudaSetDevice(prev);
     return e;
+}
+// evaluator tables of the current device (built by limit_init on first use; NULL if that fails)
+static const uint8_t *holdem_lut_on_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    { std::lock_guard<std::mutex> lock(g_lfsm_mu); if (g_hlut[dev]) return g_hlut[dev]; }
+    if (limit_init(dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_lfsm_mu);
+    return g_hlut[dev];
 }
 static const uint4 *limit_fsm_on_device(int &n) {
     int dev = 0;
@@ -373,14 +406,19 @@ __device__ __forceinline__ uint32_t lim_byte(uint32_t w, uint32_t k) { return __
 // replaces one that both warps consumed before top-up r - 1).  SPLIT = 1: one warp does everything (64-thread blocks
 // then hold two groups).
 template <class ObsT, int BLOCK, int RING, int SPLIT>
-__global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, const uint4 *__restrict__ gtab, int nstates) {
+__global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, const uint4 *__restrict__ gtab, int nstates, const uint4 *__restrict__ glut) {
     extern __shared__ uint4 smem_raw[];
     constexpr int kGroups = BLOCK / 32 / SPLIT, kSlots = SPLIT == 2 ? 2 * RING : RING;
     constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT);
     constexpr int kTileBytes = kGroups * 32 * kRowBytes;
     uint4 *stab = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes);
     uint2 *ring_all = reinterpret_cast<uint2 *>(stab + kLimFsmMax);          // [kGroups][kSlots][32]
+    uint4 *slut = reinterpret_cast<uint4 *>(ring_all + kGroups * kSlots * 32);   // evaluator tables: card64[52] | t5[8192]
     for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
+    for (int j = threadIdx.x; j < kHoldemLutBytes / 16; j += BLOCK) slut[j] = glut[j];
+    HoldemLut lut;
+    lut.card64 = reinterpret_cast<const unsigned long long *>(slut);
+    lut.t5 = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(slut) + 52 * 8);
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int grp = SPLIT == 2 ? wib >> 1 : wib, role = SPLIT == 2 ? wib & 1 : 0;   // role 0 emits obs rows, role 1 the other streams
@@ -496,11 +534,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
                 if (str_role) {
                     const uint32_t f0 = (e.x >> 17) & 1u, f1 = (e.x >> 18) & 1u;
                     int oc = f1 ? 0 : 1;
-                    if ((f0 | f1) == 0u) {     // showdown: random play rarely gets here, whole warps skip the evaluator
-                        Limit g;
-                        limit_unpack_cards(g, make_uint2(c_lo, c_hi));
-                        oc = g.showdown_outcome();
-                    }
+                    if ((f0 | f1) == 0u)       // showdown: random play rarely gets here, whole warps skip the evaluator
+                        oc = holdem_showdown_lut(c_lo, c_hi, lut);        // == Limit::showdown_outcome() (checked by rlc_judge_holdem)
                     const float pot = (float)min(chips & 255u, chips >> 8);
                     const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * pot;
                     pay = make_float2(p0, -p0);
@@ -531,9 +566,15 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
 template <class ObsT, int SPLIT, int BLOCK>
 static cudaError_t launch_limit_fsm_split(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
     constexpr int RING = 8, kGroups = BLOCK / 32 / SPLIT, kSlots = SPLIT == 2 ? 2 * RING : RING;
-    const size_t smem = (size_t)kGroups * 32 * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + (size_t)kGroups * kSlots * 32 * sizeof(uint2);
+    const size_t smem = (size_t)kGroups * 32 * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + (size_t)kGroups * kSlots * 32 * sizeof(uint2) + kHoldemLutBytes;
     const size_t per_block = (size_t)kGroups * 32;
-    k_rollout_limit_fsm<ObsT, BLOCK, RING, SPLIT><<<(unsigned)((p.n + per_block - 1) / per_block), BLOCK, smem, s>>>(p, tab, nstates);
+    const uint8_t *lut = holdem_lut_on_device();
+    if (!lut) return cudaErrorNotReady;
+    auto k = k_rollout_limit_fsm<ObsT, BLOCK, RING, SPLIT>;
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)((p.n + per_block - 1) / per_block), BLOCK, smem, s>>>(p, tab, nstates, reinterpret_cast<const uint4 *>(lut));
     return cudaGetLastError();
 }
 template <class ObsT>
@@ -585,24 +626,39 @@ cudaError_t dispatch_limit(int op, int chance, int obs_dtype, const KParams &p, 
 }
 
 // limitholdem/utils.py:526-569 compare_hands as a standalone operator: one thread per case
-__global__ void k_judge_holdem(const uint8_t *cards, int n, int P, uint8_t *winners) {
+// Hands are scored by the table evaluator (tables staged in shared memory, as in the rollout) AND by the branch-free
+// one: a case on which the two disagree answers 255 for every seat, so the reference's known-answer vectors pin both.
+__global__ void k_judge_holdem(const uint8_t *cards, int n, int P, uint8_t *winners, const uint4 *__restrict__ glut) {
+    __shared__ uint4 slut[kHoldemLutBytes / 16];
+    for (int j = threadIdx.x; j < kHoldemLutBytes / 16; j += blockDim.x) slut[j] = glut[j];
+    __syncthreads();
+    const unsigned long long *card64 = reinterpret_cast<const unsigned long long *>(slut);
+    const uint16_t *t5 = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(slut) + 52 * 8);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t str[RLC_MAX_PLAYERS], best = 0;
+    bool agree = true;
     for (int p = 0; p < P; p++) {
         const uint8_t *c = cards + ((size_t)i * P + p) * 7;
         str[p] = 0;
         if (c[0] != 255) {
             const int h[7] = { c[0], c[1], c[2], c[3], c[4], c[5], c[6] };
-            str[p] = 1u + holdem_strength7(h);
+            unsigned long long m64 = 0;
+            for (int k = 0; k < 7; k++) m64 |= card64[h[k]];
+            const uint32_t m[4] = { (uint32_t)m64 & 0x1fffu, (uint32_t)(m64 >> 16) & 0x1fffu, (uint32_t)(m64 >> 32) & 0x1fffu, (uint32_t)(m64 >> 48) & 0x1fffu };
+            const uint32_t v = holdem_strength_lut(m, t5);
+            agree = agree && v == holdem_strength7(h);
+            str[p] = 1u + v;
         }
         best = max(best, str[p]);
     }
-    for (int p = 0; p < P; p++) winners[(size_t)i * P + p] = (str[p] != 0 && str[p] == best) ? 1 : 0;
+    for (int p = 0; p < P; p++) winners[(size_t)i * P + p] = !agree ? 255 : ((str[p] != 0 && str[p] == best) ? 1 : 0);
 }
 cudaError_t judge_holdem(const uint8_t *cards, int n, int P, uint8_t *winners, cudaStream_t s) {
     if (P < 1 || P > RLC_MAX_PLAYERS) return cudaErrorInvalidValue;
-    k_judge_holdem<<<(n + 127) / 128, 128, 0, s>>>(cards, n, P, winners);
+    const uint8_t *lut = holdem_lut_on_device();
+    if (!lut) return cudaErrorNotReady;
+    k_judge_holdem<<<(n + 127) / 128, 128, 0, s>>>(cards, n, P, winners, reinterpret_cast<const uint4 *>(lut));
     return cudaGetLastError();
 }
 }  // namespace rlc

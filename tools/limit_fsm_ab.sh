@@ -1,10 +1,10 @@
 #!/bin/bash
-# usage: bash tools/limit_fsm_ab.sh TAG  -- Limit Hold'em throughput rollout: generic register engine (RLC_LIMIT_FSM=0) vs tabulated engine + deal rings
+# usage: bash tools/limit_fsm_ab.sh TAG  -- Limit Hold'em throughput rollout: generic register engine (RLC_LIMIT_FSM=0) vs tabulated engine, one warp (1) / two warps (2) per group
 set -u
 TAG=$1
 OUT=gpurun_out
 mkdir -p $OUT
-python -m pytest tests -m gpu -x -q -k "limit" > $OUT/pytest_limit_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_limit_$TAG.log
+python -m pytest tests -m gpu -x -q -k "limit or holdem or judge or kat" > $OUT/pytest_limit_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_limit_$TAG.log
 tail -3 $OUT/pytest_limit_$TAG.log
 for r in 1 2; do
   for v in 0 1 2; do
