@@ -33,21 +33,25 @@ __device__ __forceinline__ int nib(uint64_t x, int k) { return (int)((x >> (4 * 
 // may run in one half only: it has no collective, only barriers on the group's own mask.
 template <int LPE>
 struct ScoutT {
-    static_assert(LPE == 32 || LPE == 16, "a warp or a half-warp per env");
+    static_assert(LPE == 32 || LPE == 16 || LPE == 8, "a warp, a half-warp or a quarter-warp per env");
+    static constexpr int kPasses = LPE >= 16 ? 1 : 16 / LPE;      // the 16 hand / table slots (and starts) a lane covers
     static constexpr int kLanes = LPE;
     template <int L> using WithLanes = ScoutT<L>;
-    static constexpr int kRolloutLanes = 16;      // lanes per env of the fused throughput rollout (RLC_WROLLOUT_LPE=32: a warp per env)
+    static constexpr int kRolloutLanes = 8;       // lanes per env of the fused throughput rollout (RLC_WROLLOUT_LPE=32 / 16 force a warp / half-warp per env)
     uint32_t gm; int gsh;                         // LPE == 16: lane mask of this env's half-warp and its first lane
     __device__ __forceinline__ void bind_group(uint32_t mask, int shift) { gm = mask; gsh = shift; }
     __device__ __forceinline__ uint32_t ballot(bool pred) const {
         if constexpr (LPE == 32) return __ballot_sync(kFull, pred);
-        else return (__ballot_sync(kFull, pred) >> gsh) & 0xffffu;
+        else return (__ballot_sync(kFull, pred) >> gsh) & ((1u << LPE) - 1u);
     }
     __device__ __forceinline__ uint32_t red_or(uint32_t v) const {
         if constexpr (LPE == 32) return __reduce_or_sync(kFull, v);
-        else {
+        else if constexpr (LPE == 16) {
             const uint32_t lo = __reduce_or_sync(kFull, gsh ? 0u : v), hi = __reduce_or_sync(kFull, gsh ? v : 0u);
             return gsh ? hi : lo;
+        } else {                                                       // butterfly inside the group's eight lanes
+            v |= __shfl_xor_sync(kFull, v, 1); v |= __shfl_xor_sync(kFull, v, 2); v |= __shfl_xor_sync(kFull, v, 4);
+            return v;
         }
     }
     __device__ __forceinline__ void wsync() const { __syncwarp(); }                          // all 32 lanes are here
@@ -129,32 +133,44 @@ struct ScoutT {
         const int n = hl_of(cur);
         int ttype = 0, trank = 0;
         if (tl > 0) segment(tt, 0, tl, ttype, trank);
-        const int a = nib(T, lane & 15), b = nib(T, (lane + 1) & 15);
-        const bool adj = lane < 15 && lane + 1 < n;
-        const uint32_t eqm = ballot(adj && b == a);
-        const uint32_t upm = ballot(adj && b == a + 1);
-        const uint32_t dnm = ballot(adj && b == a - 1);
-        int lo_id = 1, hi_id = 0;                                          // empty
-        if (lane < n && lane < 16) {
-            const int s = lane;
-            const int req = __ffs((int)~(eqm >> s)) - 1, rup = __ffs((int)~(upm >> s)) - 1, rdn = __ffs((int)~(dnm >> s)) - 1;
-            const int hi_len = min(max(req, max(rup, rdn)) + 1, n - s);
-            int lo_len = 1;
-            if (tl > 0) {                                                  // a set of exactly tl cards: stronger than the table?
-                const bool group = tl - 1 <= req, asc = tl - 1 <= rup;
-                const int type = tl == 1 ? 0 : (group ? 2 : 1);
-                const int rank = (tl > 1 && !group) ? (asc ? a + tl - 1 : a) : a;          // run: max(first, last)
-                lo_len = (type > ttype || (type == ttype && rank > trank)) ? tl : tl + 1;   // validity of length tl: tl <= hi_len
+        // adjacency of hand positions (s, s + 1), s = 0 .. 14, as three 16-bit sets; a lane covers the positions lane + q LPE
+        uint32_t eqm = 0, upm = 0, dnm = 0;
+#pragma unroll
+        for (int q = 0; q < kPasses; q++) {
+            const int s = (lane & 15) + q * LPE;
+            const int a = nib(T, s & 15), b = nib(T, (s + 1) & 15);
+            const bool adj = lane < 16 && s < 15 && s + 1 < n;
+            eqm |= ballot(adj && b == a) << (q * LPE);
+            upm |= ballot(adj && b == a + 1) << (q * LPE);
+            dnm |= ballot(adj && b == a - 1) << (q * LPE);
+        }
+        uint32_t acc[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int q = 0; q < kPasses; q++) {
+            const int s = lane + q * LPE;
+            int lo_id = 1, hi_id = 0;                                      // empty
+            if (s < n && s < 16) {
+                const int a = nib(T, s);
+                const int req = __ffs((int)~(eqm >> s)) - 1, rup = __ffs((int)~(upm >> s)) - 1, rdn = __ffs((int)~(dnm >> s)) - 1;
+                const int hi_len = min(max(req, max(rup, rdn)) + 1, n - s);
+                int lo_len = 1;
+                if (tl > 0) {                                              // a set of exactly tl cards: stronger than the table?
+                    const bool group = tl - 1 <= req, asc = tl - 1 <= rup;
+                    const int type = tl == 1 ? 0 : (group ? 2 : 1);
+                    const int rank = (tl > 1 && !group) ? (asc ? a + tl - 1 : a) : a;      // run: max(first, last)
+                    lo_len = (type > ttype || (type == ttype && rank > trank)) ? tl : tl + 1;   // validity of length tl: tl <= hi_len
+                }
+                const int base = 16 * s - ((s * (s - 1)) >> 1);
+                lo_id = base + lo_len - 1; hi_id = base + hi_len - 1;
             }
-            const int base = 16 * s - ((s * (s - 1)) >> 1);
-            lo_id = base + lo_len - 1; hi_id = base + hi_len - 1;
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
+                acc[r] |= x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
+            }
         }
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
-            const uint32_t bits = x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
-            m[r] = red_or(bits);
-        }
+        for (int r = 0; r < 5; r++) m[r] = red_or(acc[r]);
         forced = (m[0] | m[1] | m[2] | m[3] | m[4]) == 0;
         m[5] = m[6] = 0;
         if (tl > 0 && n < 16) {                                            // scout: insert position <= n; back variants need tl > 1
@@ -281,36 +297,46 @@ struct ScoutT {
     // envs/scout.py:171-235 (row pre-zeroed).  Scalars are float32(python float64 expression).
     template <class T> __device__ void encode_obs(int seat, bool, T *row, uint8_t *, int lane) const {
         if (lane < 16) {
-            const int s = lane;
-            if (s < hl_of(seat)) {
-                row[s * 10 + nib(top_of(seat), s) - 1] = (T)1;
-                row[160 + s * 10 + nib(bot_of(seat), s) - 1] = (T)1;
-                row[640 + s] = (T)1;
+#pragma unroll
+            for (int q = 0; q < kPasses; q++) {
+                const int s = lane + q * LPE;
+                if (s < hl_of(seat)) {
+                    row[s * 10 + nib(top_of(seat), s) - 1] = (T)1;
+                    row[160 + s * 10 + nib(bot_of(seat), s) - 1] = (T)1;
+                    row[640 + s] = (T)1;
+                }
             }
         }
-        if (LPE == 16 || lane >= 16) {                                      // half-warp: the same 16 lanes write the table slots
-            const int j = lane & 15;
-            if (j < tl) {
-                row[320 + j * 10 + nib(tt, j) - 1] = (T)1;
-                row[480 + j * 10 + nib(tb, j) - 1] = (T)1;
-                row[656 + j] = (T)1;
+        if (LPE <= 16 || lane >= 16) {                                      // fewer than 32 lanes: the same lanes write the table slots
+#pragma unroll
+            for (int q = 0; q < kPasses; q++) {
+                const int j = (lane & 15) + q * LPE;
+                if (j < tl) {
+                    row[320 + j * 10 + nib(tt, j) - 1] = (T)1;
+                    row[480 + j * 10 + nib(tb, j) - 1] = (T)1;
+                    row[656 + j] = (T)1;
+                }
             }
         }
         if (lane < 16) {
-            float v = 0.f;
-            if (lane < 5) v = owner == lane ? 1.f : 0.f;
-            else if (lane == 5) v = consec == 0 ? 0.f : (consec == 1 ? (float)(1.0 / 3.0) : (consec == 2 ? (float)(2.0 / 3.0) : 1.f));
-            else if (lane < 10) v = (float)hl_of(lane - 6) * 0.0625f;
-            else if (lane == 10) v = (float)score_of(seat) * 0.0625f;
-            else if (lane == 11) v = (float)tl * 0.0625f;
-            else if (lane == 13) v = forced ? 1.f : 0.f;
-            else if (lane >= 14) {
-                const int r = tl == 0 ? 0 : (lane == 14 ? nib(tt, 0) : nib(tt, tl - 1));
-                const float tenth[11] = { 0.f, (float)(1 / 10.0), (float)(2 / 10.0), (float)(3 / 10.0), (float)(4 / 10.0), (float)(5 / 10.0),
-                                          (float)(6 / 10.0), (float)(7 / 10.0), (float)(8 / 10.0), (float)(9 / 10.0), 1.f };
-                v = tenth[r];
+#pragma unroll
+            for (int q = 0; q < kPasses; q++) {
+                const int i = lane + q * LPE;                               // scalar i of envs/scout.py:171-235
+                float v = 0.f;
+                if (i < 5) v = owner == i ? 1.f : 0.f;
+                else if (i == 5) v = consec == 0 ? 0.f : (consec == 1 ? (float)(1.0 / 3.0) : (consec == 2 ? (float)(2.0 / 3.0) : 1.f));
+                else if (i < 10) v = (float)hl_of(i - 6) * 0.0625f;
+                else if (i == 10) v = (float)score_of(seat) * 0.0625f;
+                else if (i == 11) v = (float)tl * 0.0625f;
+                else if (i == 13) v = forced ? 1.f : 0.f;
+                else if (i >= 14) {
+                    const int r = tl == 0 ? 0 : (i == 14 ? nib(tt, 0) : nib(tt, tl - 1));
+                    const float tenth[11] = { 0.f, (float)(1 / 10.0), (float)(2 / 10.0), (float)(3 / 10.0), (float)(4 / 10.0), (float)(5 / 10.0),
+                                              (float)(6 / 10.0), (float)(7 / 10.0), (float)(8 / 10.0), (float)(9 / 10.0), 1.f };
+                    v = tenth[r];
+                }
+                row[672 + i] = (T)v;
             }
-            row[672 + lane] = (T)v;
         }
     }
 };

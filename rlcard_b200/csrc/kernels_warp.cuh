@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout(const KParams
 // (play vs scout, an episode ending), so every barrier and collective names the group's own lane mask.  Philox mode, every
 // trajectory stream optional, no ABI-2 extensions (those run on k_wrollout).
 template <class G, class Ch, class ObsT, int BLOCK, int LPE>
-__global__ void __launch_bounds__(BLOCK, G::kMinBlocks) k_wrollout_multi(const KParams p) {
-    static_assert(LPE == 16 && G::kLanes == LPE, "half-warp groups");
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 128 ? G::kMinBlocks : 8) k_wrollout_multi(const KParams p) {
+    static_assert((LPE == 16 || LPE == 8) && G::kLanes == LPE, "half- or quarter-warp groups");
     extern __shared__ uint4 smem_raw[];
     constexpr int kGroups = 32 / LPE;
     const int lane_abs = threadIdx.x & 31, sub = lane_abs / LPE, lane = lane_abs % LPE;
@@ -435,15 +435,18 @@ cudaError_t launch_wop(int op, const KParams &p, cudaStream_t stream) {
         if (p.t_forced || p.tm_row) RLC_WLAUNCH((k_wrollout<G, Ch, ObsT, BLOCK, true>));
         else {
             if constexpr (Ch::kKind == 0 && RolloutLanes<G>::value < 32) {          // several envs per warp (throughput mode)
-                constexpr int LPE = RolloutLanes<G>::value;
                 const char *lv = getenv("RLC_WROLLOUT_LPE");
-                if (!lv || atoi(lv) != 32) {
-                    using GL = typename G::template WithLanes<LPE>;
-                    const unsigned mgrid = (unsigned)((p.n + BLOCK / LPE - 1) / (BLOCK / LPE));
-                    const size_t msmem = smem * (32 / LPE);
-                    auto kk = k_wrollout_multi<GL, Ch, ObsT, BLOCK, LPE>;
-                    if (msmem > 48 * 1024) e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-                    if (e == cudaSuccess) { kk<<<mgrid, BLOCK, msmem, stream>>>(p); e = cudaGetLastError(); }
+                const int lpe = lv ? atoi(lv) : RolloutLanes<G>::value;
+                if (lpe == 16 || lpe == 8) {
+                    auto go = [&](auto kk, int block, int lanes) {
+                        const unsigned mgrid = (unsigned)((p.n + block / lanes - 1) / (block / lanes));
+                        const size_t msmem = (smem / (BLOCK / 32)) * (size_t)(block / lanes);
+                        if (msmem > 48 * 1024) e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+                        if (e == cudaSuccess) { kk<<<mgrid, block, msmem, stream>>>(p); e = cudaGetLastError(); }
+                    };
+                    // a quarter-warp per env: 64-thread blocks (8 envs, 23 KB of shared memory for Scout) keep the SMs evenly filled
+                    if (lpe == 8) go(k_wrollout_multi<typename G::template WithLanes<8>, Ch, ObsT, 64, 8>, 64, 8);
+                    else go(k_wrollout_multi<typename G::template WithLanes<16>, Ch, ObsT, BLOCK, 16>, BLOCK, 16);
                     break;
                 }
             }
