@@ -60,7 +60,7 @@ struct ScoutT {
     static constexpr bool kMaskBitpacked = false;
     static constexpr int kMinBlocks = 7;          // resident 128-thread blocks per SM the rollout kernel is compiled for (71 registers, no spills;
                                                   // measured 5 / 6 / 7 / 8 blocks: 1.175 / 1.139 / 1.050 / 1.043 ms, 8 spills)
-    static constexpr int kScratchBytes = 48 + 64;   // reset: 45-card deck | the four hands (tops, bottoms)
+    static constexpr int kScratchBytes = 48 + 64 + 32;   // reset: 45-card deck | the four hands (tops, bottoms) | legal-set accumulator (5 words)
     static constexpr bool kRowFlushFull = true;   // 2752-byte rows: batched compile-time flush (1.235 -> 1.212 ms)
     static constexpr bool kMaskBulk = false;      // 204-byte mask rows are not whole 16-byte units
     uint64_t *hands;       // shared memory of the warp: [0..3] hand tops p0..p3, [4..7] hand bottoms.  Every lane writes the
@@ -81,7 +81,11 @@ struct ScoutT {
         sc01 += (p & 2) ? 0u : d; sc23 += (p & 2) ? d : 0u;
     }
 
-    __device__ __forceinline__ void bind(const KParams &, uint8_t *scratch) { hands = reinterpret_cast<uint64_t *>(scratch + 48); }
+    uint32_t *acc_sm;      // LPE < 32: the lanes OR their id ranges into five shared words (two ATOMS per start) instead of 5 x 2 REDUX / 15 shuffles
+    __device__ __forceinline__ void bind(const KParams &, uint8_t *scratch) {
+        hands = reinterpret_cast<uint64_t *>(scratch + 48);
+        acc_sm = reinterpret_cast<uint32_t *>(scratch + 48 + 64);
+    }
     __device__ void load(const uint32_t *w, int lane) {
 #pragma unroll
         for (int p = 0; p < 4; p++) {
@@ -145,6 +149,7 @@ struct ScoutT {
             dnm |= ballot(adj && b == a - 1) << (q * LPE);
         }
         uint32_t acc[5] = {0u, 0u, 0u, 0u, 0u};
+        if constexpr (LPE < 32) { if (lane < 5) acc_sm[lane] = 0u; wsync(); }
 #pragma unroll
         for (int q = 0; q < kPasses; q++) {
             const int s = lane + q * LPE;
@@ -163,14 +168,28 @@ struct ScoutT {
                 const int base = 16 * s - ((s * (s - 1)) >> 1);
                 lo_id = base + lo_len - 1; hi_id = base + hi_len - 1;
             }
+            if constexpr (LPE < 32) {
+                if (lo_id <= hi_id) {                                      // at most 16 ids: one or two words
+                    const uint64_t bits = ((2ull << (hi_id - lo_id)) - 1ull) << (lo_id & 31);
+                    atomicOr(acc_sm + (lo_id >> 5), (uint32_t)bits);
+                    if ((uint32_t)(bits >> 32)) atomicOr(acc_sm + (lo_id >> 5) + 1, (uint32_t)(bits >> 32));
+                }
+            } else {
 #pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
-                acc[r] |= x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
+                for (int r = 0; r < 5; r++) {
+                    const int x = max(lo_id - 32 * r, 0), y = min(hi_id - 32 * r, 31);
+                    acc[r] |= x <= y ? ((2u << y) - 1u) & ~((1u << x) - 1u) : 0u;
+                }
             }
         }
+        if constexpr (LPE < 32) {
+            wsync();
 #pragma unroll
-        for (int r = 0; r < 5; r++) m[r] = red_or(acc[r]);
+            for (int r = 0; r < 5; r++) m[r] = acc_sm[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 5; r++) m[r] = red_or(acc[r]);
+        }
         forced = (m[0] | m[1] | m[2] | m[3] | m[4]) == 0;
         m[5] = m[6] = 0;
         if (tl > 0 && n < 16) {                                            // scout: insert position <= n; back variants need tl > 1

@@ -68,7 +68,7 @@ __device__ __forceinline__ void warp_write_mask(void *gmask, size_t row, const u
 #pragma unroll
         for (int q = lane; q < G::A / 4; q += LANES) {
             const uint32_t b = (sm[q >> 3] >> ((q & 7) * 4)) & 15u;
-            st_stream(dst + q, (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21));
+            st_stream(dst + q, (b * 0x00204081u) & 0x01010101u);       // bit a -> byte a
         }
     }
 }
