@@ -457,6 +457,29 @@ struct UnoT {
         out[0] = winner == 0 ? 1.f : (winner == 1 ? -1.f : 0.f);
         out[1] = winner == 1 ? 1.f : (winner == 0 ? -1.f : 0.f);
     }
+    // encode_obs() of the acting seat by lane PAIRS: with 16 envs per warp (kernels.cuh) lanes 16..31 carry no env, so lane
+    // L + 16 fetches env L's hand words by shuffle and writes the planes of colours 2, 3 while lane L writes colours 0, 1
+    // and the target -- half the one-hot byte stores per lane.  Called by all 32 lanes; `row` is env (lane & 15)'s row.
+    static constexpr bool kPairEmit = BAG;
+    template <class T> __device__ void encode_obs_pair(bool valid, int lane, T *row) const {
+        const int src = lane & 15, seat = cur;
+        const uint32_t w0 = __shfl_sync(0xffffffffu, hcp(seat, 0), src), w1 = __shfl_sync(0xffffffffu, hcp(seat, 1), src);
+        const uint32_t w2 = __shfl_sync(0xffffffffu, hcp(seat, 2), src), w3 = __shfl_sync(0xffffffffu, hcp(seat, 3), src);
+        const uint32_t hwv = __shfl_sync(0xffffffffu, hwp(seat), src);
+        const int tc = __shfl_sync(0xffffffffu, tcode, src);
+        if (!__shfl_sync(0xffffffffu, (int)valid, src)) return;
+        const bool upper = lane >= 16;
+        const uint32_t wa = upper ? w2 : w0, wb = upper ? w3 : w1;
+        T *ra = row + (upper ? 30 : 0), *rb = ra + 15;
+#pragma unroll
+        for (int t = 0; t < 13; t++) {
+            ra[60 * ((wa >> (2 * t)) & 3) + t] = (T)1;                     // count 0 keeps plane 0 set
+            rb[60 * ((wb >> (2 * t)) & 3) + t] = (T)1;
+        }
+        const int kw = (hwv & 7u) ? 60 : 0, k4 = ((hwv >> 11) & 7u) ? 60 : 0;
+        ra[kw + 13] = (T)1; ra[k4 + 14] = (T)1; rb[kw + 13] = (T)1; rb[k4 + 14] = (T)1;
+        if (!upper) row[180 + tc] = (T)1;
+    }
     // envs/uno.py:24-33, utils.py:69-127 (row pre-zeroed): planes 0..2 hand copies, plane 3 target
     template <class T> __device__ void encode_obs(int seat, bool, T *row) const {
 #pragma unroll

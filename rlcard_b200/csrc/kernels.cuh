@@ -240,6 +240,30 @@ __device__ __forceinline__ void stage_mask_row(uint8_t *mtile, int lane, const u
     }
 }
 
+// the same by lane pairs (16 envs per warp): lane L stages the first eight words of env L's row, lane L + 16 the rest
+template <class G>
+__device__ __forceinline__ void stage_mask_row_pair(uint8_t *mtile, int lane, bool valid, const uint32_t (&m)[G::MASK_WORDS]) {
+    static_assert(G::MASK_WORDS == 2 && G::A <= 61 && (16 * G::A) % 4 == 0, "61-id rows on the word grid");
+    const int src = lane & 15;
+    const uint32_t m0 = __shfl_sync(0xffffffffu, m[0], src), m1 = __shfl_sync(0xffffffffu, m[1], src);
+    if (!__shfl_sync(0xffffffffu, (int)valid, src)) return;
+    const int o = (src * G::A) & 3;
+    const uint64_t mm = ((uint64_t)m0 | ((uint64_t)m1 << 32)) << o;
+    const bool upper = lane >= 16;
+    const uint32_t half = upper ? (uint32_t)(mm >> 32) : (uint32_t)mm;
+    uint32_t *w = reinterpret_cast<uint32_t *>(mtile + src * G::A - o) + (upper ? 8 : 0);
+    constexpr int kW = (G::A + 3 + 3) / 4;                    // 16 words
+    static_assert(kW == 16, "two lanes, eight words each");
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t v = (((half >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;     // bit a -> byte a
+        if (j == 0 || j == 7) atomicOr(w + j, v);             // words 0 / 15 of the row are shared with its neighbours; 7 / 8 are not
+        else w[j] = v;                                        // (an OR there is harmless: the tile is zero between steps)
+    }
+}
+template <class G, class = void> struct HasPairEmit { static constexpr bool value = false; };
+template <class G> struct HasPairEmit<G, std::void_t<decltype(G::kPairEmit)>> { static constexpr bool value = G::kPairEmit; };
+
 // Fused random rollout: T env-steps per env, state in registers for the whole launch; per step the
 // warp emits one coalesced obs tile plus mask/action/player/done/payoff rows of the trajectory.
 // ALL = every trajectory pointer is present and the obs rows of a full warp are 16-byte aligned (the
@@ -278,6 +302,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     uint8_t *mtile = reinterpret_cast<uint8_t *>(smem_raw) + kTileBytes + ((G::kSharedBytes + 15) & ~15) + wib * kMaskTile;
     if constexpr (kStageMask) { warp_tile_zero(mtile, kMaskTile, lane); __syncwarp(); }   // rows OR their edge words into the tile
     constexpr bool kWarpDeal = G::kWarpDeal && Ch::kKind == 0;   // episodes are dealt by the whole warp (UNO, throughput mode)
+    constexpr bool kPairEmit = HasPairEmit<G>::value && ALL && EPW == 16 && Ch::kKind == 0 && G::MASK_WORDS == 2;
     bool starts = false;                                         // this lane's env begins an episode at this point
     if (valid) {
         h.load(p.state, p.n, i);
@@ -298,7 +323,12 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const KParams p) {
     for (int t = 0; t < p.T; t++, rowi += p.n, o_obs += obs_step) {
         uint32_t m[G::MASK_WORDS];
         starts = false;
-        if (valid) {
+        if constexpr (kPairEmit) {                                // lanes 16..31 build half of every row (see encode_obs_pair)
+            m[0] = m[1] = 0u;
+            if (valid) g.legal(m);
+            g.encode_obs_pair(valid, lane, row);
+            stage_mask_row_pair<G>(mtile, lane, valid, m);
+        } else if (valid) {
             if (ALL || p.t_obs) g.encode_obs(g.player(), h.t == 0, row);
             g.legal(m);
             if constexpr (kStageMask) {
