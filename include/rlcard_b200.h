@@ -146,7 +146,9 @@ const char *rlc_last_error(void);
 int rlc_game_info(int game_id, rlc_info *out);
 
 /* constant rule tables (DouDizhu action table = games/doudizhu/jsondata.zip, utils.py:14-38),
- * uploaded once per device; blob format in DESIGN.md */
+ * uploaded once per device; blob format in DESIGN.md.  RLC_LEDUC / RLC_LIMIT take no blob (NULL, 0): the call tabulates
+ * the betting automaton (and for RLC_LIMIT the 7-card evaluator's lookup tables, games/limitholdem/utils.py:37-84,526-614)
+ * on the device from the engine itself; without it rlc_rollout_random runs the generic engine (same results). */
 int rlc_upload_tables(int game_id, int device, const void *blob, size_t nbytes);
 
 /* Env.reset (env.py:52-63) for envs with reset_mask[i] != 0 (NULL = all): deal, first state,

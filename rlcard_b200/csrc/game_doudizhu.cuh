@@ -116,19 +116,32 @@ struct Doudizhu {
     }
     // game.py:23-51, round.py:25-39, dealer.py:12-76: rank-sorted deck, one shuffle, 17/17/17 + 3 to seat 0
     template <class WCh> __device__ void reset(WCh &ch, uint8_t *deck, int lane) {
-        if (lane == 0) {
+        if (lane == 0) {                                   // lane 0 owns the chance source: it shuffles alone, nothing is broadcast
             for (int i = 0; i < 52; i++) deck[i] = (uint8_t)(i >> 2);
             deck[52] = 13; deck[53] = 14;
+            for (int i = 53; i >= 1; i--) {
+                const uint32_t j = ch.ch.below((uint32_t)i + 1u);
+                const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t;
+            }
         }
         __syncwarp();
-        for (int i = 53; i >= 1; i--) {
-            const uint32_t j = ch.below((uint32_t)i + 1u);
-            if (lane == 0) { const uint8_t t = deck[i]; deck[i] = deck[j]; deck[j] = t; }
-        }
-        __syncwarp();
-        uint64_t nh[3] = {0, 0, 0};
+        // rank counts of the three hands: lane l adds cards l and l + 32 into the owner's nibble (17 / 17 / 17, the last three
+        // to the landlord); a count never exceeds 4, so the six 32-bit halves are plain warp sums
+        uint32_t inc[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
 #pragma unroll
-        for (int k = 0; k < 54; k++) nh[k < 51 ? k / 17 : 0] += 1ull << (4 * deck[k]);
+        for (int q = 0; q < 2; q++) {
+            const int k = lane + 32 * q;
+            if (k < 54) {
+                const int r = deck[k], owner = k < 51 ? k / 17 : 0;
+                const uint32_t bit = 1u << (4 * (r & 7));
+#pragma unroll
+                for (int o = 0; o < 3; o++) { inc[o][0] += (owner == o && r < 8) ? bit : 0u; inc[o][1] += (owner == o && r >= 8) ? bit : 0u; }
+            }
+        }
+        uint64_t nh[3];
+#pragma unroll
+        for (int o = 0; o < 3; o++)
+            nh[o] = (uint64_t)__reduce_add_sync(kFull, inc[o][0]) | ((uint64_t)__reduce_add_sync(kFull, inc[o][1]) << 32);
 #pragma unroll
         for (int q = 0; q < 3; q++) { hand[q] = nh[q]; played[q] = 0; }
         __syncwarp();

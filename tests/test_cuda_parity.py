@@ -507,6 +507,62 @@ def test_doudizhu_bulk_row_variants_equal_oracle(bulk, monkeypatch):
     env.check_errors()
 
 
+@pytest.mark.parametrize('n', [203, 512])
+@pytest.mark.parametrize('lpe', [32, 16, 8])
+def test_scout_lanes_per_env_variants_equal_oracle(lpe, n, monkeypatch):
+    """RLC_WROLLOUT_LPE: the Scout throughput rollout with a warp (32), a half-warp (16) or a quarter-warp (8, default) per
+    env (kernels_warp.cuh k_wrollout_multi) gives the oracle's trajectory and final state -- on a ragged batch (ghost
+    groups in the last warp) and an aligned one, over three launches (episodes of ~146 steps span them)."""
+    monkeypatch.setenv('RLC_WROLLOUT_LPE', str(lpe))
+    T, seed = 64, 909
+    env = rlcard_b200.VecEnv('scout', n, seed=seed)
+    orc = oracle.OracleVec('scout', n, seed)
+    env.reset()
+    for launch in range(3):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (lpe, launch, k)
+    env.check_errors()
+
+
+@pytest.mark.parametrize('block', [64, 128, 256])
+@pytest.mark.parametrize('fsm', ['0', '1', '2'])
+def test_limit_tabulated_rollout_variants_equal_oracle(fsm, block, monkeypatch):
+    """RLC_LIMIT_FSM: the generic register engine (0), the tabulated automaton with deal rings on one warp per group (1)
+    and split over two warps per group (2, default) give the oracle's trajectory, on a ragged batch, over three launches
+    (state words carried across launches, deals keyed by the episode ordinal), for every block size of the sweep."""
+    monkeypatch.setenv('RLC_LIMIT_FSM', fsm)
+    monkeypatch.setenv('RLC_LIMIT_BLOCK', str(block))
+    n, T, seed = 1000, 40, 616
+    env = rlcard_b200.VecEnv('limit-holdem', n, seed=seed)
+    orc = oracle.OracleVec('limit-holdem', n, seed)
+    env.reset()
+    for launch in range(3):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (fsm, block, launch, k)
+    env.check_errors()
+
+
+def test_limit_tabulated_rollout_continues_step_api_state():
+    """The tabulated Limit rollout maps the packed state words onto its automaton and back: envs advanced by rlc_step
+    (mid-episode, and finished episodes left without auto reset) continue exactly like the oracle."""
+    n, seed = 777, 626
+    env = rlcard_b200.VecEnv('limit-holdem', n, seed=seed)
+    orc = oracle.OracleVec('limit-holdem', n, seed)
+    env.reset()
+    tr = env.rollout_random(7)
+    ref = orc.rollout(7, nthreads=8)
+    assert np.array_equal(to_np(tr['action']), ref['action'])
+    tr = env.rollout_random(33)
+    ref = orc.rollout(33, nthreads=8)
+    for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+        assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), k
+    env.check_errors()
+
+
 THREAD_GAMES = [g for g in GAMES if g not in ('doudizhu', 'scout')]
 
 

@@ -1,6 +1,8 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, smoke, per-game bench lines, reference arm, ncu launch lists + full captures.
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh [tag] [games to profile ...]
+# gpurun merges back at most 64 MiB per call and a full capture is 6-17 MB: profile at most three games here and the rest
+# with tools/prof_games.sh in a second call.
 set -u
 TAG=${1:-r01}
 shift || true
