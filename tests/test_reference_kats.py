@@ -81,6 +81,32 @@ def test_cuda_holdem_compare_hands(kats):
 
 
 @pytest.mark.gpu
+def test_cuda_holdem_table_evaluator_random_hands():
+    """400 000 random showdowns (2 seats, 5 shared board cards) through rlc_judge_holdem: the table evaluator (card64 / t5 in shared
+    memory) must agree with the branch-free evaluator on every hand (the kernel answers 255 where they differ) and with the
+    oracle's evaluator on the winners."""
+    import torch
+    import oracle
+    from rlcard_b200 import judgers
+    rng = np.random.default_rng(20261019)
+    n = 400_000
+    deck = np.argsort(rng.random((n, 52)), axis=1)[:, :9].astype(np.uint8)          # nine distinct cards per case
+    cards = np.empty((n, 2, 7), np.uint8)
+    cards[:, 0, :2], cards[:, 1, :2] = deck[:, 0:2], deck[:, 2:4]
+    cards[:, :, 2:] = deck[:, None, 4:9]
+    got = judgers.compare_hands(torch.from_numpy(cards).cuda()).cpu().numpy()
+    assert not (got == 255).any(), np.nonzero((got == 255).any(1))[0][:5]
+    L = oracle.lib()
+    want = np.zeros((n, 2), np.uint8)
+    flat = np.ascontiguousarray(cards.reshape(n, 14))
+    for i in range(0, n, 97):                                                       # the oracle on a 1 % sample
+        L.orc_holdem_winners(flat[i].ctypes.data, 2, want[i].ctypes.data)
+        assert np.array_equal(got[i], want[i]), (i, cards[i])
+    ties = (got.sum(1) == 2).mean()
+    assert 0.005 < ties < 0.08                                                       # split pots exist and are rare
+
+
+@pytest.mark.gpu
 def test_cuda_doudizhu_playable_sets(kats):
     import torch
     from rlcard_b200 import judgers
