@@ -351,7 +351,7 @@ def bench_game(game, args, ctx, envs=None, steps=None, e2e_steps=None, headline=
                        'clock, max over ranks' % args.e2e_chunk}
         env2.check_errors()
         assert h_traj['done'].numpy().any(), 'e2e trajectory did not reach the host'
-        # ---- the same leg with the compact wire format (Leduc 4 B, Limit 12 B per env-step instead of 57 / 93): the chunk
+        # ---- the same leg with the compact wire format (Leduc 4 B, Limit 12 B, UNO 28 B, DouDizhu 132 B, Scout 80 B per env-step): the chunk
         # is re-encoded on the device, only the records cross PCIe; the consumer expands rows on demand (compact.expand)
         if env2.compact_words():
             h_pack = env2.alloc_host_compact(T)

@@ -263,9 +263,11 @@ int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T
 int rlc_seed_mt19937(const uint32_t *key_words, const int32_t *key_len, int n, uint32_t *mt, void *stream);
 
 /* Compact host wire format of a dense trajectory window (csrc/tu_compact.cu has the record layouts): [T][n] cells of
- * obs + mask + action + player + done + payoffs -> out uint32 [T][n][words], words = rlc_compact_words(game) (Leduc 1,
- * Limit Hold'em 3; 0 = the game has no compact format and rlc_compact_trajectory returns RLC_ENOTIMPL).  A host consumer
- * behind PCIe fetches 4 / 12 bytes per env-step instead of 57 / 93 and expands rows on demand (rlcard_b200/compact.py). */
+ * obs + mask + action + player + done + payoffs -> out uint32 [T][n][words], words = rlc_compact_words(game): Leduc 1,
+ * Limit Hold'em 3, UNO 7, DouDizhu 33, Scout 20 (float32 obs only); 0 = the game has no compact format and
+ * rlc_compact_trajectory returns RLC_ENOTIMPL.  A host consumer behind PCIe fetches 4 / 12 / 28 / 132 / 80 bytes per env-step
+ * instead of 57 / 93 / 319 / 4374 / 2983 and expands rows on demand (rlcard_b200/compact.py; DouDizhu's legal mask is not sent
+ * but recomputed on the host from the row and the action table). */
 int rlc_compact_words(int game_id);
 int rlc_compact_trajectory(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, uint32_t *out, void *stream);
 

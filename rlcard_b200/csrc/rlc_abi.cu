@@ -300,7 +300,16 @@ int rlc_reorganize(int game_id, const rlc_trajectory *traj, int obs_dtype, int T
 #endif
 }
 
-int rlc_compact_words(int game_id) { return game_id == RLC_LEDUC ? 1 : (game_id == RLC_LIMIT ? 3 : 0); }
+int rlc_compact_words(int game_id) {
+    switch (game_id) {
+    case RLC_LEDUC: return 1;
+    case RLC_LIMIT: return 3;
+    case RLC_UNO: return 7;
+    case RLC_DOUDIZHU: return 33;
+    case RLC_SCOUT: return 20;
+    default: return 0;
+    }
+}
 
 int rlc_compact_trajectory(int game_id, const rlc_trajectory *traj, int obs_dtype, int T, int n, uint32_t *out, void *stream) {
     if (game_id < 0 || game_id >= RLC_NUM_GAMES) return fail(RLC_EINVAL, "bad game id %d", game_id);

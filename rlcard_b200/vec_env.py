@@ -333,8 +333,8 @@ class VecEnv:
         copied device->host into the pinned ``host_out`` tensors on a second stream.  If ``host_state`` (a pinned
         int32 tensor shaped like ``self.state``) is given, the packed env state is uploaded from it before the
         first chunk and written back after the last one, i.e. the caller owns the state in host memory.
-        ``compact=True`` (Leduc, Limit Hold'em): ``host_out`` is the tensor of alloc_host_compact; every chunk is
-        re-encoded on the device by rlc_compact_trajectory and only the 4 / 12-byte records cross PCIe
+        ``compact=True`` (Leduc, Limit Hold'em, UNO, DouDizhu, Scout): ``host_out`` is the tensor of alloc_host_compact; every
+        chunk is re-encoded on the device by rlc_compact_trajectory and only the 4 / 12 / 28 / 132 / 80-byte records cross PCIe
         (rlcard_b200.compact.expand rebuilds the dense rows on the host, bit-exact).
         Returns after everything has landed in host memory."""
         dev = self.device

@@ -46,6 +46,18 @@ def test_oracle_doudizhu_playable_sets(kats):
     assert int(kats['ddz_n_test_hands']) >= 6 and len(kats['ddz_assert']) >= 170
 
 
+def test_host_doudizhu_legal_mask_matches_reference(kats):
+    """rlcard_b200.compact.doudizhu_legal_mask (the host side of DouDizhu's compact wire format recomputes the legal set from
+    the hand and the action to beat) on the reference's 1 607 playable-set vectors."""
+    from rlcard_b200 import compact, doudizhu_table as T
+    tab = T.load()
+    hands, tg, legal = kats['ddz_hand'], kats['ddz_target'], kats['ddz_legal']
+    for i in range(len(hands)):
+        target = [0] * 15 if tg[i] < 0 else T.unpack_counts(tab['counts'][tg[i]])
+        got = compact.doudizhu_legal_mask(hands[i], target).view(np.uint8)[:legal.shape[1]]
+        assert np.array_equal(got, legal[i]), (i, hands[i], tg[i])
+
+
 def test_oracle_leduc_judger(kats):
     L = oracle.lib()
     out = np.zeros(2, np.float64)
