@@ -30,6 +30,8 @@ struct DdzTables {
     const uint8_t *type;       // [27472]
     const uint8_t *weight;     // [27472]
     const uint32_t *tw_start;  // [39][17] first id of type t with weight >= w; [t][16] = end of type t
+    const uint16_t *therm;     // [27472][27] the 54-byte obs block of every action (envs/doudizhu.py:153-167: 4 x 13 thermometer + two joker
+                               //         bytes), built on the device from `rows` at upload: the twelve action blocks of a byte obs row are COPIED
 };
 constexpr int kDdzPass = 27471, kDdzRocket = 27470, kDdzBomb0 = 27457, kDdzTypeBomb = 35, kDdzTypeRocket = 36;
 constexpr uint64_t kNibHi = 0x8888888888888888ull;
@@ -87,7 +89,7 @@ struct Doudizhu {
         hand = reinterpret_cast<uint64_t *>(scratch + kObsScratch + 128); played = hand + 3;
         tab.rows = reinterpret_cast<const uint64_t *>(p.tab[0]); tab.need = reinterpret_cast<const ulonglong2 *>(p.tab[1]);
         tab.type = reinterpret_cast<const uint8_t *>(p.tab[2]); tab.weight = reinterpret_cast<const uint8_t *>(p.tab[3]);
-        tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]);
+        tab.tw_start = reinterpret_cast<const uint32_t *>(p.tab[4]); tab.therm = reinterpret_cast<const uint16_t *>(p.tab[5]);
         n_legal = 0; n_live = 0; has_pass = false;           // legal() relies on these describing the (zeroed) smask; writing the
                                                              // mask row as zero words + listed words on top measured 14 % slower
     }
@@ -299,42 +301,47 @@ struct Doudizhu {
     template <class T> __device__ void encode_obs(int seat, bool, T *row, uint8_t *scratch, int lane) const {
         const int up = seat == 2 ? 0 : seat + 1, down = seat == 0 ? 2 : seat - 1, mate = 3 - seat;
         if constexpr (sizeof(T) == 1) {
-            // byte rows: the 14 (landlord) / 16 (peasant) 54-d blocks are built together.  Lane b computes the rank
-            // counts of block b (action blocks fetch their table row, all in flight at once) and parks them in
-            // shared memory; then lane (r, parity) writes the 4-byte thermometer of rank r (r = 13: the two joker
-            // bytes) of every second block -- 8 rounds of one LDS and two 16-bit STS (blocks are 2-byte aligned).
-            uint64_t *cw = reinterpret_cast<uint64_t *>(scratch + kObsScratch);
-            if (lane < 16) {
-                const int b = lane;
+            // byte rows.  The twelve ACTION blocks (last action, the nine-action trace, and for peasants the landlord's and the
+            // team-mate's last action) are 54-byte rows of the per-action table: lane l < 27 copies 16-bit unit l of each (ids are
+            // warp-uniform and the trace index is a compile-time constant here, so there is no select chain and no arithmetic
+            // per block).  The four COUNT blocks (own hand, the others' hands, two played piles) are expanded from their rank
+            // counts: lane (r, parity) writes the 4-byte thermometer of rank r (r = 13: the two joker bytes) of two of them.
+            uint8_t *rowb = reinterpret_cast<uint8_t *>(row);
+            if (lane < 27) {
                 const uint32_t newest = trace_at(8), prev = trace_at(7);
-                uint32_t id = (uint32_t)kDdzPass;                               // table row of 'pass' = no cards
-                if (b == 2) id = newest != (uint32_t)kDdzPass ? newest : prev;
-                else if (b >= 3 && b <= 11) id = trace_at(b - 3);
-                else if (b == 14) id = last_by[0];
-                else if (b == 15) id = mate == 1 ? last_by[1] : last_by[2];
-                uint64_t v = action_counts(id);
-                if (b == 0) v = sel3(hand, seat);
-                else if (b == 1) v = sel3(hand, up) + sel3(hand, down);
-                else if (b == 12) v = seat == 0 ? played[2] : played[0];
-                else if (b == 13) v = seat == 0 ? played[1] : sel3(played, mate);
-                cw[b] = v;
+                const uint16_t *th = tab.therm + lane;
+                uint16_t *d16 = reinterpret_cast<uint16_t *>(rowb) + lane;
+                d16[27 * 2] = __ldg(th + 27u * (newest != (uint32_t)kDdzPass ? newest : prev));
+#pragma unroll
+                for (int k = 0; k < 9; k++) d16[27 * (3 + k)] = __ldg(th + 27u * trace_at(k));
+                if (seat != 0) {
+                    d16[27 * 14] = __ldg(th + 27u * last_by[0]);
+                    d16[27 * 15] = __ldg(th + 27u * (mate == 1 ? last_by[1] : last_by[2]));
+                }
+            }
+            uint64_t *cw = reinterpret_cast<uint64_t *>(scratch + kObsScratch);
+            if (lane < 4) {                                                     // count blocks 0, 1, 12, 13 -> cw[0..3]
+                uint64_t v = sel3(hand, seat);
+                if (lane == 1) v = sel3(hand, up) + sel3(hand, down);
+                else if (lane == 2) v = seat == 0 ? played[2] : played[0];
+                else if (lane == 3) v = seat == 0 ? played[1] : sel3(played, mate);
+                cw[lane] = v;
             }
             __syncwarp();
-            const int r = lane & 15, nb = seat == 0 ? 14 : 16;
+            const int r = lane & 15;
             if (r < 14) {
-                uint8_t *dst = reinterpret_cast<uint8_t *>(row) + 54 * (lane >> 4) + 4 * r;
-                const uint32_t *half = reinterpret_cast<const uint32_t *>(cw) + 2 * (lane >> 4) + (r >> 3);   // the word holding rank r
+                const int par = lane >> 4;                                      // parity 0: blocks 0, 12 ; parity 1: blocks 1, 13
                 const int sh = 4 * (r & 7);
                 const uint32_t joker_bit = r == 13 ? 0x100u : 0u;      // r = 13 writes the two joker bytes (B in the low byte, R above)
 #pragma unroll
-                for (int b = lane >> 4; b < 16; b += 2, dst += 108, half += 4) {
-                    if (b < nb) {                                       // branch free inside: every lane of the half-warp stores
-                        const uint32_t w = *half, k = (w >> sh) & 15u;                                 // 0..4 copies of rank r
-                        uint32_t v = __funnelshift_lc(0x01010101u, 0u, 8u * k);                         // k thermometer bytes
-                        v |= (w >> 16) & joker_bit;                                                     // red joker: nibble 14 -> byte 1
-                        *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
-                        if (r < 13) *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(v >> 16);
-                    }
+                for (int q = 0; q < 2; q++) {
+                    const int b = q == 0 ? par : 12 + par;
+                    uint8_t *dst = rowb + 54 * b + 4 * r;
+                    const uint32_t w = reinterpret_cast<const uint32_t *>(cw)[2 * (2 * q + par) + (r >> 3)], k = (w >> sh) & 15u;   // 0..4 copies of rank r
+                    uint32_t v = __funnelshift_lc(0x01010101u, 0u, 8u * k);                             // k thermometer bytes
+                    v |= (w >> 16) & joker_bit;                                                         // red joker: nibble 14 -> byte 1
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+                    if (r < 13) *reinterpret_cast<uint16_t *>(dst + 2) = (uint16_t)(v >> 16);
                 }
             }
         } else {

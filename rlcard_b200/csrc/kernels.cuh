@@ -22,7 +22,7 @@ struct KParams {
     // pool of per-seat terminal states (env.py:161-164) with the row index per trajectory cell
     const int32_t *t_forced; void *tm_obs; void *tm_mask; int32_t *tm_row; int32_t *tm_count; int tm_cap;
     int32_t *order; int order_stride;            // legal ids in the reference's insertion order (rlc_buffers.legal_order)
-    const void *tables; const void *tab[5];      // per-game constant tables (device pointers), see Game::bind
+    const void *tables; const void *tab[6];      // per-game constant tables (device pointers), see Game::bind
 };
 
 enum { kModeReset = 0, kModeStep = 1, kModeObserve = 2 };

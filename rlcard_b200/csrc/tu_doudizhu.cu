@@ -10,6 +10,23 @@ struct DdzBlobHeader {
 };
 static DdzTables g_tab[64];
 static void *g_dev_blob[64];
+static uint16_t *g_therm[64];                 // per-action 54-byte obs blocks, built on the device from the rows at upload
+static_assert(sizeof(DdzTables) == 6 * sizeof(void *), "DdzTables is copied into KParams::tab[6]");
+
+// envs/doudizhu.py:153-167 _cards2array for every action id: byte 4 r + k = (count of rank r > k), bytes 52 / 53 = the jokers
+__global__ void k_ddz_build_therm(const uint64_t *rows, int n_actions, uint16_t *therm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_actions * 27) return;
+    const int id = i / 27, u = i - 27 * id;
+    const uint64_t c = rows[id];
+    uint32_t v = 0;
+    for (int h = 0; h < 2; h++) {
+        const int j = 2 * u + h;
+        const uint32_t on = j < 52 ? (uint32_t)(((c >> (4 * (j >> 2))) & 15ull) > (uint64_t)(j & 3)) : (uint32_t)(((c >> (4 * (j - 39))) & 15ull) != 0ull);
+        v |= on << (8 * h);
+    }
+    therm[i] = (uint16_t)v;
+}
 
 const uint64_t *doudizhu_rows_on_device(int device) {
     return (device >= 0 && device < 64 && g_dev_blob[device]) ? g_tab[device].rows : nullptr;
@@ -28,15 +45,26 @@ cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
     if (g_dev_blob[device]) { cudaFree(g_dev_blob[device]); g_dev_blob[device] = nullptr; memset(&g_tab[device], 0, sizeof g_tab[device]); }
+    if (g_therm[device]) { cudaFree(g_therm[device]); g_therm[device] = nullptr; }
     void *dev_blob = nullptr;
+    uint16_t *therm = nullptr;
     e = cudaMalloc(&dev_blob, nbytes);
     if (e == cudaSuccess) e = cudaMemcpy(dev_blob, blob, nbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&therm, (size_t)h.n_actions * 27 * sizeof(uint16_t));
+    if (e == cudaSuccess) {
+        const int units = (int)h.n_actions * 27;
+        k_ddz_build_therm<<<(units + 255) / 256, 256>>>(reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(dev_blob) + h.off_rows), (int)h.n_actions, therm);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
     if (e != cudaSuccess) {                                   // nothing half-installed: later calls keep answering NotReady
         if (dev_blob) cudaFree(dev_blob);
+        if (therm) cudaFree(therm);
         cudaSetDevice(prev);
         return e;
     }
     g_dev_blob[device] = dev_blob;
+    g_therm[device] = therm;
     {
         const char *b = reinterpret_cast<const char *>(g_dev_blob[device]);
         g_tab[device].rows = reinterpret_cast<const uint64_t *>(b + h.off_rows);
@@ -44,6 +72,7 @@ cudaError_t doudizhu_upload(int device, const void *blob, size_t nbytes) {
         g_tab[device].type = reinterpret_cast<const uint8_t *>(b + h.off_type);
         g_tab[device].weight = reinterpret_cast<const uint8_t *>(b + h.off_weight);
         g_tab[device].tw_start = reinterpret_cast<const uint32_t *>(b + h.off_tw);
+        g_tab[device].therm = therm;
     }
     cudaSetDevice(prev);
     return e;
