@@ -582,8 +582,17 @@ static cudaError_t launch_limit_fsm_split(const KParams &p, const uint4 *tab, in
 template <class ObsT>
 static cudaError_t launch_limit_fsm(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
     const char *sp = getenv("RLC_LIMIT_FSM");                  // "1": one warp per group; default: the two-warp split
+    // groups of 32 envs per block (two warps each): 4 once the batch gives every SM more than a block's worth, else fewer so that
+    // small batches still spread (16 384 envs, blocks of 64 / 128 / 256 threads: 0.0937 / 0.0934 / 0.0918 ms); RLC_LIMIT_BLOCK overrides
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms = v > 0 ? v : 148;
+    }
+    const size_t groups = (p.n + 31) / 32;
     const char *bs = getenv("RLC_LIMIT_BLOCK");
-    const int block = bs ? atoi(bs) : 128;              // measured 64 / 128 / 256: 0.1032 / 0.1007 / 0.0996 ms at 16 384 envs (256 leaves 20 SMs empty)
+    const int block = bs ? atoi(bs) : (groups >= (size_t)(3 * sms / 2) ? 256 : (groups >= (size_t)(sms / 2) ? 128 : 64));
     if (sp && sp[0] == '1') {
         if (block == 32) return launch_limit_fsm_split<ObsT, 1, 32>(p, tab, nstates, s);
         if (block == 128) return launch_limit_fsm_split<ObsT, 1, 128>(p, tab, nstates, s);
