@@ -570,6 +570,39 @@ def test_limit_tabulated_rollout_continues_step_api_state():
     env.check_errors()
 
 
+@pytest.mark.parametrize('block', [64, 128, 512, 1024])
+def test_leduc_block_size_variants_equal_oracle(block, monkeypatch):
+    """RLC_LEDUC_BLOCK: the tabulated Leduc rollout is launched with one SMSP-balanced block per SM at large batches (512 threads
+    at 65 536 envs) and with 64-thread blocks at small ones; every block size gives the oracle's trajectory on a ragged batch."""
+    monkeypatch.setenv('RLC_LEDUC_BLOCK', str(block))
+    n, T, seed = 5003, 40, 717
+    env = rlcard_b200.VecEnv('leduc-holdem', n, seed=seed)
+    orc = oracle.OracleVec('leduc-holdem', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (block, launch, k)
+    env.check_errors()
+
+
+@pytest.mark.parametrize('block', [64, 128, 256, 448, 512])
+def test_scout_block_size_variants_equal_oracle(block, monkeypatch):
+    """RLC_WROLLOUT_BLOCK: block sizes of the four-envs-per-warp Scout rollout (448 = one 14-warp block per SM at 8 192 envs)."""
+    monkeypatch.setenv('RLC_WROLLOUT_BLOCK', str(block))
+    n, T, seed = 333, 48, 727
+    env = rlcard_b200.VecEnv('scout', n, seed=seed)
+    orc = oracle.OracleVec('scout', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (block, launch, k)
+    env.check_errors()
+
+
 THREAD_GAMES = [g for g in GAMES if g not in ('doudizhu', 'scout')]
 
 
