@@ -563,6 +563,266 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
     }
 }
 
+// ==========================================================================================
+// k_rollout_limit_pipe: the tabulated rollout as a PIPELINE of role warps per group of 32 envs (one block = one group).
+//   ENV   (1 warp)   runs only the betting automaton + policy words and appends one 16-byte record per env-step to a
+//                    double-buffered record chunk (kPipeChunk steps); nothing it does waits on the emission
+//   DEAL  (ND warps) prepare the episode-keyed deals (Limit::reset, deal words) ahead of the ENV warp into per-lane rings;
+//                    a ring slot carries the episode tag in its spare byte, so ENV validates a deal with the ONE 64-bit
+//                    shared-memory load it needs anyway (no flag, no fence on its chain)
+//   EMIT  (NE warps) turn records into trajectory rows; the steps of a chunk are dealt round-robin over the EMIT warps, so the
+//                    ~120-instruction emission of one step has NE step-times to finish
+// Chunks are handed over with named barriers (bar.arrive / bar.sync, ids 1..4: full[2], free[2]) -- one hand-shake per 16
+// steps instead of one per step (k_rollout_limit_ws polled a ring every step and lost what it gained).  Same state words,
+// Philox words, deals and trajectory as k_rollout_limit_fsm / k_rollout<Limit>: only the mapping of work to warps differs.
+// ==========================================================================================
+constexpr int kPipeChunk = 16;     // env-steps per record buffer
+constexpr int kPipeRing = 32;      // deal slots per lane; >= kPipeChunk + 1 (a lane opens at most one episode per step + the first)
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ uint2 lds_volatile_u2(const uint2 *q) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(q)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *q) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(q)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t *q, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(smem_u32(q)), "r"(v) : "memory");
+}
+
+template <class ObsT, int NE, int ND>
+__global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const KParams p, const uint4 *__restrict__ gtab, int nstates,
+                                                                            const uint4 *__restrict__ glut) {
+    constexpr int BLOCK = 32 * (1 + ND + NE), K = kPipeChunk, RING = kPipeRing;
+    constexpr int kRowBytes = Limit::OBS * (int)sizeof(ObsT), kTileBytes = 32 * kRowBytes;
+    constexpr int kBarCount = 32 * (1 + NE);
+    static_assert(RING >= K + 1 && ND >= 1 && ND <= 2, "see the flow-control argument below");
+    extern __shared__ uint4 smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>(smem_raw);
+    uint4 *stab = reinterpret_cast<uint4 *>(sm + NE * kTileBytes);
+    uint4 *recs = stab + kLimFsmMax;                                         // [2][K][32]
+    uint2 *ring_all = reinterpret_cast<uint2 *>(recs + 2 * K * 32);          // [RING][32]
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(ring_all + RING * 32);      // [0..32) episodes consumed per lane | 32: steps done | 33: finished
+    uint4 *slut = reinterpret_cast<uint4 *>(ctl + 48);
+    for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
+    for (int j = threadIdx.x; j < kHoldemLutBytes / 16; j += BLOCK) slut[j] = glut[j];
+    for (int j = threadIdx.x; j < RING * 32; j += BLOCK) ring_all[j] = make_uint2(0u, 0u);      // tag 0 = no deal
+    for (int j = threadIdx.x; j < 48; j += BLOCK) ctl[j] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t warp_env0 = (size_t)blockIdx.x * 32;
+    if (warp_env0 >= p.n) return;
+    const size_t i = warp_env0 + lane;
+    const bool valid = i < p.n;
+    const int nvalid = (int)min((size_t)32, p.n - warp_env0);
+    const int nchunks = (p.T + K - 1) / K;
+    uint2 *ring = ring_all + lane;                                           // deal of episode E: ring[(E % RING) * 32]
+
+    EnvHeader h; h.episode = 0; h.t = 0; h.k = 0;
+    uint32_t c_lo = 0, c_hi = 0, sid = 0, chips = 0, rn = 0, rn_shown = 0;
+    bool fresh = false;
+    if (wib == 0) {                                                          // ENV: the state words (as in k_rollout_limit_fsm)
+        if (valid) {
+            h.load(p.state, p.n, i);
+            const uint32_t *gw = p.state + kHeaderWords * p.n;
+            const uint32_t w0 = gw[i], w1 = gw[p.n + i], w2 = gw[2 * p.n + i], w3 = gw[3 * p.n + i];
+            c_lo = w0 & 0x3fffffffu; c_hi = w1 & 0xffffffu;
+            chips = bf_get(w2, 0, 6) | (bf_get(w2, 6, 6) << 8);
+            rn = w3 & 0xfffu; rn_shown = (w3 >> 12) & 0xfffu;
+            const uint32_t key = bf_get(w1, 24, 3) | (bf_get(w1, 27, 2) << 3) | (bf_get(w1, 29, 1) << 5) | (bf_get(w1, 30, 1) << 6) |
+                                 (bf_get(w1, 31, 1) << 7) | (bf_get(w2, 12, 5) << 8) | (bf_get(w2, 17, 5) << 13) | (bf_get(w2, 22, 3) << 18);
+            int found = -1;
+            for (int j = 0; j < nstates; j++) if ((stab[j].x >> 11) == key) { found = j; break; }
+            fresh = h.episode == 0 || found < 0 || ((stab[found].x >> 4) & 1u);
+            sid = found < 0 ? 0u : (uint32_t)found;
+        }
+        ctl[lane] = h.episode;
+    }
+    __syncthreads();                                                         // the DEAL warps start from the published episode ordinals
+
+    if (wib == 0) {
+        // ---------------------------------------------------------------- ENV
+        ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
+        auto open_episode = [&]() {                // game.py:46-103 once the deal is known
+            h.episode++; h.t = 0;
+            const uint32_t tag = 0x80u | (h.episode & 0x7fu);
+            const uint2 *slot = ring + (h.episode % RING) * 32;
+            uint2 d;
+            do { d = lds_volatile_u2(slot); } while ((d.y >> 24) != tag);   // normally there: the DEAL warps run ahead
+            c_lo = d.x & 0x3fffffffu; c_hi = d.y & 0xffffffu;
+            sid = d.x >> 30;                                       // states 0 / 1: seat 0 / 1 is the small blind
+            chips = sid ? (2u | (1u << 8)) : (1u | (2u << 8));
+            rn_shown = rn; rn = 0;                                 // Q-LH1
+        };
+        if (fresh) open_episode();
+        uint4 e = stab[sid];
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1, t0 = c * K, steps = min(K, p.T - t0);
+            if (c >= 2) named_sync(3 + b, kBarCount);              // the EMIT warps are done with this buffer
+            if (c > 0) {                                           // flow control for the DEAL warps, once per chunk
+                __threadfence_block();
+                sts_volatile_u32(ctl + lane, h.episode);
+                if (lane == 0) sts_volatile_u32(ctl + 32, (uint32_t)t0);
+            }
+            uint4 *rec = recs + (size_t)b * K * 32 + lane;
+            for (int s = 0; s < steps; s++, rec += 32) {
+                if (valid) {
+                    const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
+                    const uint32_t word = ch.begin_step(h.k);
+                    const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
+                    const uint32_t a = lim_byte(e.z, kth);
+                    const uint32_t shown = h.t == 0 ? rn_shown : rn;
+                    uint4 r;
+                    r.x = c_lo | (ptr << 30); r.y = c_hi | (sid << 24);
+                    chips += lim_byte(e.w, kth) << (8u * ptr);
+                    rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
+                    sid = lim_byte(e.y, kth);
+                    r.z = shown | (a << 12) | (sid << 16); r.w = chips;
+                    *rec = r;
+                    e = stab[sid];
+                    h.t++; h.k++;
+                    if ((e.x >> 4) & 1u) { open_episode(); e = stab[sid]; }
+                }
+            }
+            __threadfence_block();
+            named_arrive(1 + b, kBarCount);
+        }
+        __syncwarp();
+        if (lane == 0) sts_volatile_u32(ctl + 33, 1u);             // the DEAL warps may leave
+        if (valid) {
+            h.store(p.state, p.n, i);
+            uint32_t *gw = p.state + kHeaderWords * p.n;
+            const uint32_t k = e.x >> 11;
+            gw[i] = c_lo;
+            gw[p.n + i] = c_hi | (bf_get(k, 0, 3) << 24) | (bf_get(k, 3, 2) << 27) | (bf_get(k, 5, 1) << 29) | (bf_get(k, 6, 1) << 30) | (bf_get(k, 7, 1) << 31);
+            gw[2 * p.n + i] = (chips & 63u) | (((chips >> 8) & 63u) << 6) | (bf_get(k, 8, 5) << 12) | (bf_get(k, 13, 5) << 17) | (bf_get(k, 18, 3) << 22);
+            gw[3 * p.n + i] = rn | (rn_shown << 12);
+        }
+    } else if (wib <= ND) {
+        // ---------------------------------------------------------------- DEAL
+        // Warp d deals the episodes with ordinal = d (mod ND).  A lane is topped up to `cap` deals beyond the ordinal ENV published
+        // at its last chunk boundary; within a chunk a lane opens at most kPipeChunk (+ 1 at launch) episodes and cap >= that,
+        // so ENV can always be served; a slot (E mod RING) is rewritten only for E - RING <= published ordinal, i.e. consumed.
+        const uint32_t d = (uint32_t)(wib - 1);
+        ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
+        uint32_t next = lds_volatile_u32(ctl + lane) + 1u;
+        if (ND == 2 && (next & 1u) != d) next++;
+        for (;;) {
+            const uint32_t fin = lds_volatile_u32(ctl + 33);
+            const uint32_t cons = lds_volatile_u32(ctl + lane), tp = lds_volatile_u32(ctl + 32);
+            const uint32_t cap = min((uint32_t)RING, (uint32_t)p.T - tp + 1u);
+            const bool need = valid && next <= cons + cap;
+            if (!__any_sync(0xffffffffu, need)) {
+                if (fin) break;
+                __nanosleep(128);
+                continue;
+            }
+            if (need) {
+                Limit g; g.rn = 0;
+                ChancePhilox dc = ch;
+                dc.begin_episode(next);
+                g.reset(dc);                                       // deal words (episode-keyed) -> nine cards + small blind
+                const uint2 cd = limit_pack_cards(g);
+                ring[(next % RING) * 32] = make_uint2(cd.x | ((uint32_t)g.r.pointer << 30), cd.y | ((0x80u | (next & 0x7fu)) << 24));
+                next += ND;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- EMIT
+        const int j = wib - 1 - ND;
+        HoldemLut lut;
+        lut.card64 = reinterpret_cast<const unsigned long long *>(slut);
+        lut.t5 = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(slut) + 52 * 8);
+        ObsT *tile = reinterpret_cast<ObsT *>(sm + (size_t)j * kTileBytes);
+        ObsT *row = tile + lane * Limit::OBS;
+        warp_tile_zero(reinterpret_cast<uint8_t *>(tile), kTileBytes, lane);
+        __syncwarp();
+        uint8_t *o_obs0 = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
+        const size_t obs_step = p.n * (size_t)kRowBytes;
+        auto run = [&](auto full_c) {
+        constexpr bool kFullWarp = decltype(full_c)::value;
+        const bool live = kFullWarp || valid;
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1, t0 = c * K, steps = min(K, p.T - t0);
+            named_sync(1 + b, kBarCount);                          // the chunk's records are written
+            for (int s = (j + NE - t0 % NE) % NE; s < steps; s += NE) {
+                const int t = t0 + s;
+                const size_t rowi = (size_t)t * p.n + i;
+                uint4 r = make_uint4(0u, 0u, 0u, 0u), epre = r;
+                if (live) { r = recs[((size_t)b * K + s) * 32 + lane]; epre = stab[r.y >> 24]; }
+                const uint32_t c_lo_ = r.x & 0x3fffffffu, ptr = r.x >> 30, c_hi_ = r.y & 0xffffffu;
+                if (live) {                        // envs/limitholdem.py:40-71 (Limit::encode_obs)
+                    const uint32_t sh = 6u * ptr;
+                    row[(c_lo_ >> sh) & 63u] = (ObsT)1; row[(c_lo_ >> (sh + 12u)) & 63u] = (ObsT)1;
+                    const uint32_t np_ = (epre.x >> 5) & 7u;
+                    if (np_ >= 3u) { row[(c_lo_ >> 24) & 63u] = (ObsT)1; row[c_hi_ & 63u] = (ObsT)1; row[(c_hi_ >> 6) & 63u] = (ObsT)1; }
+                    if (np_ >= 4u) row[(c_hi_ >> 12) & 63u] = (ObsT)1;
+                    if (np_ >= 5u) row[(c_hi_ >> 18) & 63u] = (ObsT)1;
+                    const uint32_t shown = r.z & 0xfffu;
+                    row[52 + (shown & 7u)] = (ObsT)1; row[57 + ((shown >> 3) & 7u)] = (ObsT)1;
+                    row[62 + ((shown >> 6) & 7u)] = (ObsT)1; row[67 + ((shown >> 9) & 7u)] = (ObsT)1;
+                }
+                __syncwarp();
+                uint8_t *o_obs = o_obs0 + (size_t)t * obs_step;
+                if constexpr (kFullWarp) warp_tile_flush_full<kTileBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+                else warp_tile_flush(o_obs, reinterpret_cast<uint8_t *>(tile), nvalid * kRowBytes, lane);
+                if (live) {
+                    const uint32_t legal = epre.x & 15u;
+                    st_stream(reinterpret_cast<uint32_t *>(p.t_mask) + rowi, (legal * 0x00204081u) & 0x01010101u);   // bit a -> byte a
+                    st_stream(p.t_player + rowi, (int)ptr);
+                    st_stream(p.t_action + rowi, (int)((r.z >> 12) & 3u));
+                    const uint32_t ex = stab[(r.z >> 16) & 255u].x;
+                    const bool over = (ex >> 4) & 1u;
+                    float2 pay = make_float2(0.f, 0.f);
+                    if (over) {                    // game.py:233-243, judger.py:11-108 for two players
+                        const uint32_t f0 = (ex >> 17) & 1u, f1 = (ex >> 18) & 1u;
+                        int oc = f1 ? 0 : 1;
+                        if ((f0 | f1) == 0u) oc = holdem_showdown_lut(c_lo_, c_hi_, lut);
+                        const float pot = (float)min(r.w & 255u, r.w >> 8);
+                        const float p0 = oc == 2 ? 0.f : (oc == 0 ? 0.5f : -0.5f) * pot;
+                        pay = make_float2(p0, -p0);
+                    }
+                    p.t_done[rowi] = over ? 1 : 0;
+                    st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, pay);
+                }
+                __syncwarp();
+            }
+            if (c + 2 < nchunks) { __threadfence_block(); named_arrive(3 + b, kBarCount); }
+        }
+        };
+        if (nvalid == 32) run(std::true_type{}); else run(std::false_type{});
+    }
+}
+
+template <class ObsT, int NE, int ND>
+static cudaError_t launch_limit_pipe_as(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
+    const size_t smem = (size_t)NE * 32 * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + sizeof(uint4) * 2 * kPipeChunk * 32 +
+                        sizeof(uint2) * kPipeRing * 32 + 48 * sizeof(uint32_t) + kHoldemLutBytes;
+    const uint8_t *lut = holdem_lut_on_device();
+    if (!lut) return cudaErrorNotReady;
+    auto k = k_rollout_limit_pipe<ObsT, NE, ND>;
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)((p.n + 31) / 32), 32 * (1 + ND + NE), smem, s>>>(p, tab, nstates, reinterpret_cast<const uint4 *>(lut));
+    return cudaGetLastError();
+}
+template <class ObsT>
+static cudaError_t launch_limit_pipe(const KParams &p, const uint4 *tab, int nstates, int ne, int nd, cudaStream_t s) {
+    if (nd == 1) {
+        if (ne == 2) return launch_limit_pipe_as<ObsT, 2, 1>(p, tab, nstates, s);
+        if (ne == 4) return launch_limit_pipe_as<ObsT, 4, 1>(p, tab, nstates, s);
+        return launch_limit_pipe_as<ObsT, 3, 1>(p, tab, nstates, s);
+    }
+    if (ne == 2) return launch_limit_pipe_as<ObsT, 2, 2>(p, tab, nstates, s);
+    if (ne == 4) return launch_limit_pipe_as<ObsT, 4, 2>(p, tab, nstates, s);
+    return launch_limit_pipe_as<ObsT, 3, 2>(p, tab, nstates, s);
+}
+
 template <class ObsT, int SPLIT, int BLOCK>
 static cudaError_t launch_limit_fsm_split(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
     // deals prepared ahead per lane: measured 8 / 16 / 32 / 48 / 64: 0.0999 / 0.0957 / 0.0932 / 0.0953 / 0.0939 ms (an env needs ~40 deals per 128 steps;
@@ -628,6 +888,12 @@ cudaError_t dispatch_limit(int op, int chance, int obs_dtype, const KParams &p, 
     const uint4 *tab = nullptr;
     if (!(fsm && fsm[0] == '0') && op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & kFlagNoFsm) && p.T > 0 && p.t_obs &&
         p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs && (tab = limit_fsm_on_device(nstates)) != nullptr) {
+        const char *pipe = getenv("RLC_LIMIT_PIPE");          // "<EMIT warps><DEAL warps>", e.g. "32"; "0" = off
+        const int ne = pipe && pipe[0] >= '2' && pipe[0] <= '4' ? pipe[0] - '0' : 0, nd = pipe && pipe[0] && pipe[1] == '1' ? 1 : 2;
+        if (ne && obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS)) & 15u) == 0)
+            return launch_limit_pipe<uint8_t>(p, tab, nstates, ne, nd, s);
+        if (ne && obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS * 4)) & 15u) == 0)
+            return launch_limit_pipe<float>(p, tab, nstates, ne, nd, s);
         if (obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS)) & 15u) == 0)
             return launch_limit_fsm<uint8_t>(p, tab, nstates, s);
         if (obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS * 4)) & 15u) == 0)

@@ -553,6 +553,25 @@ def test_limit_tabulated_rollout_variants_equal_oracle(fsm, block, monkeypatch):
     env.check_errors()
 
 
+@pytest.mark.parametrize('T', [40, 7, 129])
+@pytest.mark.parametrize('pipe', ['32', '22', '42', '31'])
+def test_limit_pipelined_rollout_equals_oracle(pipe, T, monkeypatch):
+    """RLC_LIMIT_PIPE=<EMIT warps><DEAL warps>: the tabulated Limit rollout as a pipeline of role warps per group (ENV automaton ->
+    16-step record chunks -> EMIT warps; DEAL warps fill tagged deal rings ahead) gives the oracle's trajectory on a ragged batch,
+    over three launches (state carried), for window lengths below, at and beyond one chunk."""
+    monkeypatch.setenv('RLC_LIMIT_PIPE', pipe)
+    n, seed = 1000, 636
+    env = rlcard_b200.VecEnv('limit-holdem', n, seed=seed)
+    orc = oracle.OracleVec('limit-holdem', n, seed)
+    env.reset()
+    for launch in range(3):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (pipe, launch, k)
+    env.check_errors()
+
+
 def test_limit_tabulated_rollout_continues_step_api_state():
     """The tabulated Limit rollout maps the packed state words onto its automaton and back: envs advanced by rlc_step
     (mid-episode, and finished episodes left without auto reset) continue exactly like the oracle."""
