@@ -646,20 +646,72 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
 
     if (wib == 0) {
         // ---------------------------------------------------------------- ENV
+        // The step is branch-free on its main path: the deal of the NEXT episode is fetched (volatile, tag-checked) while the
+        // current step runs, an episode end is a handful of selects (the two opening table entries live in registers), the
+        // policy words of four steps come from one Philox block computed ahead of them, and every shared-memory access
+        // goes through a 32-bit shared address held in a register.
         ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
-        auto open_episode = [&]() {                // game.py:46-103 once the deal is known
-            h.episode++; h.t = 0;
-            const uint32_t tag = 0x80u | (h.episode & 0x7fu);
-            const uint2 *slot = ring + (h.episode % RING) * 32;
-            uint2 d;
-            do { d = lds_volatile_u2(slot); } while ((d.y >> 24) != tag);   // normally there: the DEAL warps run ahead
+        uint32_t sbase;
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem_raw)));        // opaque: never rematerialised
+        const uint32_t stab_s = sbase + (uint32_t)(NE * kTileBytes);
+        const uint32_t recs_s = stab_s + (uint32_t)sizeof(uint4) * kLimFsmMax + 16u * (uint32_t)lane;
+        const uint32_t ring_s = stab_s + (uint32_t)sizeof(uint4) * (kLimFsmMax + 2 * K * 32) + 8u * (uint32_t)lane;
+        auto lds_tab = [&](uint32_t id) {
+            uint4 v;
+            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stab_s + 16u * id));
+            return v;
+        };
+        auto lds_deal = [&](uint32_t ep) {         // ring slot of episode ep (volatile: the DEAL warps write it)
+            uint2 v;
+            asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(ring_s + 256u * (ep % (uint32_t)RING)) : "memory");
+            return v;
+        };
+        const uint4 e_open0 = stab[0], e_open1 = stab[1];                  // states 0 / 1: seat 0 / 1 is the small blind
+        uint32_t first = h.t == 0 ? 1u : 0u;
+        auto take_deal = [&](uint2 d) {            // game.py:46-103 once the deal is known
+            h.episode++; first = 1u; h.t = 0;
             c_lo = d.x & 0x3fffffffu; c_hi = d.y & 0xffffffu;
-            sid = d.x >> 30;                                       // states 0 / 1: seat 0 / 1 is the small blind
+            sid = d.x >> 30;
             chips = sid ? (2u | (1u << 8)) : (1u | (2u << 8));
             rn_shown = rn; rn = 0;                                 // Q-LH1
         };
-        if (fresh) open_episode();
-        uint4 e = stab[sid];
+        auto deal_ready = [&](uint2 d, uint32_t ep) { return (d.y >> 24) == (0x80u | (ep & 0x7fu)); };
+        if (fresh) {
+            uint2 d;
+            do { d = lds_deal(h.episode + 1u); } while (!deal_ready(d, h.episode + 1u));
+            take_deal(d);
+        }
+        uint4 e = lds_tab(sid);
+        uint32_t rec_s = 0;
+        auto step = [&](uint32_t word) {
+            const uint2 nd = lds_deal(h.episode + 1u);             // next episode's deal: normally there long before it is needed
+            const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
+            const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
+            const uint32_t a = lim_byte(e.z, kth);
+            const uint32_t shown = first ? rn_shown : rn;
+            const uint32_t sid2 = lim_byte(e.y, kth);
+            chips += lim_byte(e.w, kth) << (8u * ptr);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(rec_s), "r"(c_lo | (ptr << 30)), "r"(c_hi | (sid << 24)),
+                         "r"(shown | (a << 12) | (sid2 << 16)), "r"(chips) : "memory");
+            rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
+            const uint4 e2 = lds_tab(sid2);
+            h.k++; rec_s += 512u;
+            const bool over = (e2.x >> 4) & 1u;
+            uint2 d = nd;
+            while (over && !deal_ready(d, h.episode + 1u)) d = lds_deal(h.episode + 1u);   // rare: the DEAL warps fell behind
+            const uint32_t nsid = d.x >> 30;
+            // episode end = selects (h.t is only needed as "first step of the episode"; it is rebuilt for the state store)
+            h.t = over ? 0u : h.t + 1u;
+            first = over ? 1u : 0u;
+            h.episode += over ? 1u : 0u;
+            c_lo = over ? (d.x & 0x3fffffffu) : c_lo; c_hi = over ? (d.y & 0xffffffu) : c_hi;
+            sid = over ? nsid : sid2;
+            chips = over ? (nsid ? (2u | (1u << 8)) : (1u | (2u << 8))) : chips;
+            rn_shown = over ? rn : rn_shown; rn = over ? 0u : rn;
+            e.x = over ? (nsid ? e_open1.x : e_open0.x) : e2.x; e.y = over ? (nsid ? e_open1.y : e_open0.y) : e2.y;
+            e.z = over ? (nsid ? e_open1.z : e_open0.z) : e2.z; e.w = over ? (nsid ? e_open1.w : e_open0.w) : e2.w;
+        };
+        const bool full_warp = nvalid == 32;
         for (int c = 0; c < nchunks; c++) {
             const int b = c & 1, t0 = c * K, steps = min(K, p.T - t0);
             if (c >= 2) named_sync(3 + b, kBarCount);              // the EMIT warps are done with this buffer
@@ -668,24 +720,16 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
                 sts_volatile_u32(ctl + lane, h.episode);
                 if (lane == 0) sts_volatile_u32(ctl + 32, (uint32_t)t0);
             }
-            uint4 *rec = recs + (size_t)b * K * 32 + lane;
-            for (int s = 0; s < steps; s++, rec += 32) {
-                if (valid) {
-                    const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
-                    const uint32_t word = ch.begin_step(h.k);
-                    const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
-                    const uint32_t a = lim_byte(e.z, kth);
-                    const uint32_t shown = h.t == 0 ? rn_shown : rn;
-                    uint4 r;
-                    r.x = c_lo | (ptr << 30); r.y = c_hi | (sid << 24);
-                    chips += lim_byte(e.w, kth) << (8u * ptr);
-                    rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
-                    sid = lim_byte(e.y, kth);
-                    r.z = shown | (a << 12) | (sid << 16); r.w = chips;
-                    *rec = r;
-                    e = stab[sid];
-                    h.t++; h.k++;
-                    if ((e.x >> 4) & 1u) { open_episode(); e = stab[sid]; }
+            rec_s = recs_s + (uint32_t)b * (uint32_t)(K * 512);
+            if (full_warp && (steps & 3) == 0 && __all_sync(0xffffffffu, (h.k & 3u) == 0u)) {
+                for (int s = 0; s < steps; s += 4) {               // one Philox block = the policy words of four steps
+                    uint32_t w0, w1, w2, w3;
+                    philox4x32_10(h.k >> 2, 0u, ch.env, (uint32_t)kDomBase, ch.k0, ch.k1, w0, w1, w2, w3);
+                    step(w0); step(w1); step(w2); step(w3);
+                }
+            } else {
+                for (int s = 0; s < steps; s++) {
+                    if (valid) step(ch.begin_step(h.k)); else rec_s += 512u;
                 }
             }
             __threadfence_block();
