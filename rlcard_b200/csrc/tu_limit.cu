@@ -576,8 +576,18 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
 // steps instead of one per step (k_rollout_limit_ws polled a ring every step and lost what it gained).  Same state words,
 // Philox words, deals and trajectory as k_rollout_limit_fsm / k_rollout<Limit>: only the mapping of work to warps differs.
 // ==========================================================================================
-constexpr int kPipeChunk = 16;     // env-steps per record buffer
-constexpr int kPipeRing = 32;      // deal slots per lane; >= kPipeChunk + 1 (a lane opens at most one episode per step + the first)
+#ifndef RLC_PIPE_CHUNK
+#define RLC_PIPE_CHUNK 16
+#endif
+#ifndef RLC_PIPE_RING
+#define RLC_PIPE_RING 32
+#endif
+#ifndef RLC_PIPE_POLICY
+#define RLC_PIPE_POLICY 0
+#endif
+constexpr int kPipeChunk = RLC_PIPE_CHUNK;     // env-steps per record buffer
+constexpr int kPipeRing = RLC_PIPE_RING;       // deal slots per lane; >= kPipeChunk + 1 (a lane opens at most one episode per step + the first)
+constexpr bool kPipePolicyByDeal = RLC_PIPE_POLICY != 0;   // policy words prepared by DEAL warp 0 (measured slower than four words per Philox block in ENV)
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ uint2 lds_volatile_u2(const uint2 *q) {
@@ -606,14 +616,20 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
     uint4 *stab = reinterpret_cast<uint4 *>(sm + NE * kTileBytes);
     uint4 *recs = stab + kLimFsmMax;                                         // [2][K][32]
     uint2 *ring_all = reinterpret_cast<uint2 *>(recs + 2 * K * 32);          // [RING][32]
-    uint32_t *ctl = reinterpret_cast<uint32_t *>(ring_all + RING * 32);      // [0..32) episodes consumed per lane | 32: steps done | 33: finished
-    uint4 *slut = reinterpret_cast<uint4 *>(ctl + 48);
-    for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
-    for (int j = threadIdx.x; j < kHoldemLutBytes / 16; j += BLOCK) slut[j] = glut[j];
-    for (int j = threadIdx.x; j < RING * 32; j += BLOCK) ring_all[j] = make_uint2(0u, 0u);      // tag 0 = no deal
-    for (int j = threadIdx.x; j < 48; j += BLOCK) ctl[j] = 0u;
-    __syncthreads();
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(ring_all + RING * 32);      // [0..32) episodes consumed per lane | 32: steps done | 33: finished | [64..96) h.k at launch
+    uint32_t *pol = ctl + 96;                                                // [2][K][32] policy words W_k of a chunk (DEAL warp 0 -> ENV)
+    uint4 *slut = reinterpret_cast<uint4 *>(pol + 2 * K * 32);               // evaluator tables, staged by the EMIT warps (only they judge showdowns)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
+    for (int j = threadIdx.x; j < RING * 32; j += BLOCK) ring_all[j] = make_uint2(0u, 0u);      // tag 0 = no deal
+    for (int j = threadIdx.x; j < 64; j += BLOCK) ctl[j] = 0u;
+    if (wib == 0) {                                                          // what the DEAL warps start from: episode ordinal and step index per env
+        const size_t i0 = (size_t)blockIdx.x * 32 + lane;
+        const bool v0 = i0 < p.n;
+        ctl[lane] = v0 ? p.state[i0] : 0u;
+        ctl[64 + lane] = v0 ? p.state[2 * p.n + i0] : 0u;
+    }
+    __syncthreads();                                                         // the only block-wide barrier: the roles part here
     const size_t warp_env0 = (size_t)blockIdx.x * 32;
     if (warp_env0 >= p.n) return;
     const size_t i = warp_env0 + lane;
@@ -636,13 +652,12 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
             const uint32_t key = bf_get(w1, 24, 3) | (bf_get(w1, 27, 2) << 3) | (bf_get(w1, 29, 1) << 5) | (bf_get(w1, 30, 1) << 6) |
                                  (bf_get(w1, 31, 1) << 7) | (bf_get(w2, 12, 5) << 8) | (bf_get(w2, 17, 5) << 13) | (bf_get(w2, 22, 3) << 18);
             int found = -1;
-            for (int j = 0; j < nstates; j++) if ((stab[j].x >> 11) == key) { found = j; break; }
-            fresh = h.episode == 0 || found < 0 || ((stab[found].x >> 4) & 1u);
+#pragma unroll 7
+            for (int j = nstates - 1; j >= 0; j--) found = (stab[j].x >> 11) == key ? j : found;   // no early exit: the loads pipeline
+            fresh = h.episode == 0 || found < 0 || ((stab[found < 0 ? 0 : found].x >> 4) & 1u);
             sid = found < 0 ? 0u : (uint32_t)found;
         }
-        ctl[lane] = h.episode;
     }
-    __syncthreads();                                                         // the DEAL warps start from the published episode ordinals
 
     if (wib == 0) {
         // ---------------------------------------------------------------- ENV
@@ -656,6 +671,7 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
         const uint32_t stab_s = sbase + (uint32_t)(NE * kTileBytes);
         const uint32_t recs_s = stab_s + (uint32_t)sizeof(uint4) * kLimFsmMax + 16u * (uint32_t)lane;
         const uint32_t ring_s = stab_s + (uint32_t)sizeof(uint4) * (kLimFsmMax + 2 * K * 32) + 8u * (uint32_t)lane;
+        const uint32_t pol_s = ring_s - 8u * (uint32_t)lane + (uint32_t)sizeof(uint2) * RING * 32 + 4u * (96u + (uint32_t)lane);
         auto lds_tab = [&](uint32_t id) {
             uint4 v;
             asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stab_s + 16u * id));
@@ -682,8 +698,10 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
             take_deal(d);
         }
         uint4 e = lds_tab(sid);
-        uint32_t rec_s = 0;
+        uint32_t rec_s = 0, word_s = 0;
         auto step = [&](uint32_t word) {
+            if constexpr (kPipePolicyByDeal)                       // W_k, prepared by DEAL warp 0 (same Philox block as ch.begin_step)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(word_s) : "memory");
             const uint2 nd = lds_deal(h.episode + 1u);             // next episode's deal: normally there long before it is needed
             const uint32_t legal = e.x & 15u, ptr = (e.x >> 16) & 1u;
             const uint32_t kth = __umulhi(word, (uint32_t)__popc(legal));     // uniform over the legal ids, ascending
@@ -695,7 +713,7 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
                          "r"(shown | (a << 12) | (sid2 << 16)), "r"(chips) : "memory");
             rn += (a == (uint32_t)kRaise ? 1u : 0u) << (3u * (e.x >> 29));
             const uint4 e2 = lds_tab(sid2);
-            h.k++; rec_s += 512u;
+            h.k++; rec_s += 512u; word_s += 128u;
             const bool over = (e2.x >> 4) & 1u;
             uint2 d = nd;
             while (over && !deal_ready(d, h.episode + 1u)) d = lds_deal(h.episode + 1u);   // rare: the DEAL warps fell behind
@@ -721,7 +739,18 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
                 if (lane == 0) sts_volatile_u32(ctl + 32, (uint32_t)t0);
             }
             rec_s = recs_s + (uint32_t)b * (uint32_t)(K * 512);
-            if (full_warp && (steps & 3) == 0 && __all_sync(0xffffffffu, (h.k & 3u) == 0u)) {
+            word_s = pol_s + (uint32_t)b * (uint32_t)(K * 128);
+            if constexpr (kPipePolicyByDeal) {
+                named_sync(5 + b, 64);                             // the chunk's policy words are there
+                if (full_warp) {
+#pragma unroll 4
+                    for (int s = 0; s < steps; s++) step(0u);
+                } else {
+                    for (int s = 0; s < steps; s++) {
+                        if (valid) step(0u); else { rec_s += 512u; word_s += 128u; }
+                    }
+                }
+            } else if (full_warp && (steps & 3) == 0 && __all_sync(0xffffffffu, (h.k & 3u) == 0u)) {
                 for (int s = 0; s < steps; s += 4) {               // one Philox block = the policy words of four steps
                     uint32_t w0, w1, w2, w3;
                     philox4x32_10(h.k >> 2, 0u, ch.env, (uint32_t)kDomBase, ch.k0, ch.k1, w0, w1, w2, w3);
@@ -755,9 +784,20 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
         ChancePhilox ch; ch.init(p.seed, p.env_id_base + (uint32_t)i);
         uint32_t next = lds_volatile_u32(ctl + lane) + 1u;
         if (ND == 2 && (next & 1u) != d) next++;
+        const uint32_t k_launch = ctl[64 + lane];
+        int pol_next = 0;                                          // warp 0 also prepares the policy words, one chunk ahead of ENV
         for (;;) {
             const uint32_t fin = lds_volatile_u32(ctl + 33);
             const uint32_t cons = lds_volatile_u32(ctl + lane), tp = lds_volatile_u32(ctl + 32);
+            if (kPipePolicyByDeal && d == 0u && pol_next < nchunks && (uint32_t)pol_next <= tp / (uint32_t)K + 1u) {
+                const int b = pol_next & 1, t0 = pol_next * K, steps = min(K, p.T - t0);
+                if (valid)
+                    for (int s = 0; s < steps; s++) pol[(b * K + s) * 32 + lane] = ch.begin_step(k_launch + (uint32_t)(t0 + s));
+                __threadfence_block();
+                named_arrive(5 + b, 64);
+                pol_next++;
+                continue;
+            }
             const uint32_t cap = min((uint32_t)RING, (uint32_t)p.T - tp + 1u);
             const bool need = valid && next <= cons + cap;
             if (!__any_sync(0xffffffffu, need)) {
@@ -784,7 +824,8 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
         ObsT *tile = reinterpret_cast<ObsT *>(sm + (size_t)j * kTileBytes);
         ObsT *row = tile + lane * Limit::OBS;
         warp_tile_zero(reinterpret_cast<uint8_t *>(tile), kTileBytes, lane);
-        __syncwarp();
+        for (int q = j * 32 + lane; q < kHoldemLutBytes / 16; q += NE * 32) slut[q] = glut[q];
+        named_sync(7, 32 * NE);                                    // among the EMIT warps, while ENV plays its first chunk
         uint8_t *o_obs0 = reinterpret_cast<uint8_t *>(p.t_obs) + warp_env0 * (size_t)kRowBytes;
         const size_t obs_step = p.n * (size_t)kRowBytes;
         auto run = [&](auto full_c) {
@@ -845,7 +886,7 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
 template <class ObsT, int NE, int ND>
 static cudaError_t launch_limit_pipe_as(const KParams &p, const uint4 *tab, int nstates, cudaStream_t s) {
     const size_t smem = (size_t)NE * 32 * Limit::OBS * sizeof(ObsT) + sizeof(uint4) * kLimFsmMax + sizeof(uint4) * 2 * kPipeChunk * 32 +
-                        sizeof(uint2) * kPipeRing * 32 + 48 * sizeof(uint32_t) + kHoldemLutBytes;
+                        sizeof(uint2) * kPipeRing * 32 + (96 + 2 * kPipeChunk * 32) * sizeof(uint32_t) + kHoldemLutBytes;
     const uint8_t *lut = holdem_lut_on_device();
     if (!lut) return cudaErrorNotReady;
     auto k = k_rollout_limit_pipe<ObsT, NE, ND>;
@@ -932,8 +973,11 @@ cudaError_t dispatch_limit(int op, int chance, int obs_dtype, const KParams &p, 
     const uint4 *tab = nullptr;
     if (!(fsm && fsm[0] == '0') && op == kOpRollout && chance == RLC_CHANCE_PHILOX && !(p.flags & kFlagNoFsm) && p.T > 0 && p.t_obs &&
         p.t_mask && p.t_action && p.t_player && p.t_done && p.t_payoffs && (tab = limit_fsm_on_device(nstates)) != nullptr) {
-        const char *pipe = getenv("RLC_LIMIT_PIPE");          // "<EMIT warps><DEAL warps>", e.g. "32"; "0" = off
-        const int ne = pipe && pipe[0] >= '2' && pipe[0] <= '4' ? pipe[0] - '0' : 0, nd = pipe && pipe[0] && pipe[1] == '1' ? 1 : 2;
+        // default: the role-warp pipeline with three EMIT warps and one DEAL warp (0.0915 -> 0.060 ms at 16 384 envs, profiles/r02_limit_pipe.md);
+        // RLC_LIMIT_PIPE="<EMIT warps><DEAL warps>" picks another shape, "0" the two-warp kernel below
+        const char *pipe = getenv("RLC_LIMIT_PIPE");
+        const bool fsm_named = fsm && (fsm[0] == '1' || fsm[0] == '2');   // RLC_LIMIT_FSM=1|2 names the one- / two-warp kernel explicitly
+        const int ne = !pipe ? (fsm_named ? 0 : 3) : (pipe[0] >= '2' && pipe[0] <= '4' ? pipe[0] - '0' : 0), nd = !pipe ? 1 : (pipe[0] && pipe[1] == '2' ? 2 : 1);
         if (ne && obs_dtype == RLC_U8 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS)) & 15u) == 0)
             return launch_limit_pipe<uint8_t>(p, tab, nstates, ne, nd, s);
         if (ne && obs_dtype == RLC_F32 && ((reinterpret_cast<uintptr_t>(p.t_obs) | (p.n * Limit::OBS * 4)) & 15u) == 0)
