@@ -460,7 +460,7 @@ def bench_game(game, args, ctx, envs=None, steps=None, e2e_steps=None, headline=
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get('%s:%s:%d:%d' % (game, obs_dtype, E, T))
-    kernel = ('k_rollout_leduc_fsm' if game == 'leduc-holdem' else
+    kernel = ('k_rollout_leduc_fsm' if game == 'leduc-holdem' else 'k_rollout_limit_pipe' if game == 'limit-holdem' else
               ('k_wrollout<%s>' if info.threads_per_env == 32 else 'k_rollout<%s>') % game)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,

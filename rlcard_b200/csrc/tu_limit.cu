@@ -619,10 +619,15 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
     uint32_t *ctl = reinterpret_cast<uint32_t *>(ring_all + RING * 32);      // [0..32) episodes consumed per lane | 32: steps done | 33: finished | [64..96) h.k at launch
     uint32_t *pol = ctl + 96;                                                // [2][K][32] policy words W_k of a chunk (DEAL warp 0 -> ENV)
     uint4 *slut = reinterpret_cast<uint4 *>(pol + 2 * K * 32);               // evaluator tables, staged by the EMIT warps (only they judge showdowns)
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#ifndef RLC_PIPE_ENV_LAST
+#define RLC_PIPE_ENV_LAST 0
+#endif
+    // role index: 0 ENV, 1..ND DEAL, then EMIT.  Measured: putting the pace-setting ENV role on the LAST warp of the block (the scheduler
+    // arbitrates highest warp id first) changes nothing (0.0598 vs 0.0594 ms), so roles follow the warp index
+    const int lane = threadIdx.x & 31, wib = RLC_PIPE_ENV_LAST ? (int)((threadIdx.x >> 5) + 1) % (1 + ND + NE) : (int)(threadIdx.x >> 5);
     for (int j = threadIdx.x; j < kLimFsmMax; j += BLOCK) stab[j] = j < nstates ? gtab[j] : make_uint4(16u, 0u, 0u, 0u);
     for (int j = threadIdx.x; j < RING * 32; j += BLOCK) ring_all[j] = make_uint2(0u, 0u);      // tag 0 = no deal
-    for (int j = threadIdx.x; j < 64; j += BLOCK) ctl[j] = 0u;
+    for (int j = 32 + threadIdx.x; j < 64; j += BLOCK) ctl[j] = 0u;           // [0..32) and [64..96) are written by the ENV warp just below
     if (wib == 0) {                                                          // what the DEAL warps start from: episode ordinal and step index per env
         const size_t i0 = (size_t)blockIdx.x * 32 + lane;
         const bool v0 = i0 < p.n;

@@ -4,7 +4,7 @@ set -u
 TAG=$1
 OUT=gpurun_out
 P=profiles
-declare -A KREG=( [leduc-holdem]='k_rollout_leduc_fsmIhLi512E' [limit-holdem]='k_rollout_limit_fsmIhLi256ELi32ELi2' [uno]='k_rollout.*UnoT.*Philox.*EhLi64ELb1ELi16'
+declare -A KREG=( [leduc-holdem]='k_rollout_leduc_fsmIhLi512E' [limit-holdem]='k_rollout_limit_pipeIhLi3ELi1' [uno]='k_rollout.*UnoT.*Philox.*EhLi64ELb1ELi16'
                   [doudizhu]='k_wrollout.*Doudizhu.*Philox.*EhLi128ELb0ELi3' [scout]='k_wrollout_multi.*ScoutTILi8EEENS_12ChancePhiloxEfLi448ELi8' [blackjack]='k_rollout.*Blackjack.*Philox.*EhLi64ELb1ELi32'
                   [no-limit-holdem]='k_rollout.*NoLimit.*Philox.*EhLi64ELb1ELi32' )
 declare -A OBJ=( [leduc-holdem]=tu_leduc [limit-holdem]=tu_limit [uno]=tu_uno [doudizhu]=tu_doudizhu [scout]=tu_scout [blackjack]=tu_blackjack [no-limit-holdem]=tu_nolimit )
