@@ -587,6 +587,12 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
 #endif
 constexpr int kPipeChunk = RLC_PIPE_CHUNK;     // env-steps per record buffer
 constexpr int kPipeRing = RLC_PIPE_RING;       // deal slots per lane; >= kPipeChunk + 1 (a lane opens at most one episode per step + the first)
+#ifndef RLC_PIPE_SHORT_TAIL
+#define RLC_PIPE_SHORT_TAIL 0
+#endif
+// The launch ends with the emission of the LAST chunk, which no ENV work overlaps.  RLC_PIPE_SHORT_TAIL=1 cuts the last chunk so
+// that its final NE steps (one per EMIT warp) form a chunk of their own: measured SLOWER (0.0610 vs 0.0600 ms, pass p10), off.
+constexpr bool kPipeShortTail = RLC_PIPE_SHORT_TAIL != 0 && RLC_PIPE_POLICY == 0;
 constexpr bool kPipePolicyByDeal = RLC_PIPE_POLICY != 0;   // policy words prepared by DEAL warp 0 (measured slower than four words per Philox block in ENV)
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
@@ -640,7 +646,14 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
     const size_t i = warp_env0 + lane;
     const bool valid = i < p.n;
     const int nvalid = (int)min((size_t)32, p.n - warp_env0);
-    const int nchunks = (p.T + K - 1) / K;
+    const int n0 = (p.T + K - 1) / K, last_len = p.T - (n0 - 1) * K;         // chunks of K steps; the last one holds last_len <= K
+    const bool split_tail = kPipeShortTail && last_len > NE;
+    const int nchunks = n0 + (split_tail ? 1 : 0);
+    auto chunk_bounds = [&](int c, int &t0, int &steps) {
+        if (c < n0 - 1) { t0 = c * K; steps = K; }
+        else if (c == n0 - 1) { t0 = c * K; steps = split_tail ? last_len - NE : last_len; }
+        else { t0 = p.T - NE; steps = NE; }
+    };
     uint2 *ring = ring_all + lane;                                           // deal of episode E: ring[(E % RING) * 32]
 
     EnvHeader h; h.episode = 0; h.t = 0; h.k = 0;
@@ -736,7 +749,9 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
         };
         const bool full_warp = nvalid == 32;
         for (int c = 0; c < nchunks; c++) {
-            const int b = c & 1, t0 = c * K, steps = min(K, p.T - t0);
+            const int b = c & 1;
+            int t0, steps;
+            chunk_bounds(c, t0, steps);
             if (c >= 2) named_sync(3 + b, kBarCount);              // the EMIT warps are done with this buffer
             if (c > 0) {                                           // flow control for the DEAL warps, once per chunk
                 __threadfence_block();
@@ -837,7 +852,9 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
         constexpr bool kFullWarp = decltype(full_c)::value;
         const bool live = kFullWarp || valid;
         for (int c = 0; c < nchunks; c++) {
-            const int b = c & 1, t0 = c * K, steps = min(K, p.T - t0);
+            const int b = c & 1;
+            int t0, steps;
+            chunk_bounds(c, t0, steps);
             named_sync(1 + b, kBarCount);                          // the chunk's records are written
             for (int s = (j + NE - t0 % NE) % NE; s < steps; s += NE) {
                 const int t = t0 + s;
