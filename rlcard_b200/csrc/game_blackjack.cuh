@@ -52,7 +52,12 @@ struct Blackjack {
     }
     // judger.py:54-73: A=11, T/J/Q/K=10; card id = 13*suit + rank (A=0, 2..9, T, J, Q, K)
     __device__ static __forceinline__ int card_score(int c) { const int r = c % 13; return r == 0 ? 11 : (r >= 9 ? 10 : r + 1); }
-    __device__ static __forceinline__ int soft(int sum, int aces) { while (sum > 21 && aces > 0) { aces--; sum -= 10; } return sum; }
+    // judger.py:66-72 `while score > 21 and count_a > 0: count_a -= 1; score -= 10` in closed form (no data-dependent loop under
+    // divergence): the loop runs min(aces, ceil((sum - 21) / 10)) times
+    __device__ static __forceinline__ int soft(int sum, int aces) {
+        const int need = sum > 21 ? (sum - 12) / 10 : 0;
+        return sum - 10 * min(aces, need);
+    }
     template <class Ch> __device__ int deal(Ch &ch) {            // dealer.py:26-37
         const int idx = (int)ch.below((uint32_t)deck_len);
         deck_len--;
