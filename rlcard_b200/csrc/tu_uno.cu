@@ -128,9 +128,139 @@ static cudaError_t launch_uno_ee(const KParams &p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ==========================================================================================
+// k_rollout_uno_pipe: the same ENV / EMIT split, handed over in CHUNKS.  The ENV warp appends its 8-word snapshots to a
+// double-buffered chunk of kUnoChunk env-steps and the EMIT warp consumes whole chunks; the two meet at named barriers
+// (bar.arrive / bar.sync, ids 1..4 = full[2], free[2]) once per chunk instead of polling a ring, fencing and publishing a
+// counter in every env-step (what made k_rollout_uno_ee slower than the generic kernel, profiles/r02_uno_ee.md).
+// Same engine functions, same Philox draws, same trajectory.
+// ==========================================================================================
+constexpr int kUnoChunk = 8;
+__device__ __forceinline__ void uno_named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void uno_named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+template <class ObsT, int EPW>
+__global__ void __launch_bounds__(64) k_rollout_uno_pipe(const KParams p) {
+    extern __shared__ uint4 smem_raw[];
+    using G = UnoBag;
+    constexpr int K = kUnoChunk;
+    constexpr int kRowBytes = G::OBS * (int)sizeof(ObsT);
+    constexpr int kTileBytes = EPW * kRowBytes, kMaskTile = (EPW * G::A + 15) & ~15;
+    uint8_t *sm = reinterpret_cast<uint8_t *>(smem_raw);
+    ObsT *tile = reinterpret_cast<ObsT *>(sm);
+    uint8_t *mtile = sm + kTileBytes;
+    uint32_t *snap = reinterpret_cast<uint32_t *>(sm + kTileBytes + kMaskTile);          // [2][K][words][32]
+    const int lane = threadIdx.x & 31;
+    const int role = (int)(((threadIdx.x >> 5) + blockIdx.x) & 1);      // 0 ENV, 1 EMIT
+    const size_t env0 = (size_t)blockIdx.x * EPW;
+    const size_t i = env0 + lane;
+    const bool valid = lane < EPW;                                       // the launcher guarantees n % EPW == 0
+    const int nchunks = (p.T + K - 1) / K;
+
+    if (role == 1) {                                                     // ---- EMIT
+        ObsT *row = tile + (lane & (EPW - 1)) * G::OBS;
+        warp_tile_zero(reinterpret_cast<uint8_t *>(tile), kTileBytes, lane);
+        warp_tile_zero(mtile, kMaskTile, lane);
+        __syncwarp();
+        uint8_t *o_obs = reinterpret_cast<uint8_t *>(p.t_obs) + env0 * (size_t)kRowBytes;
+        uint8_t *o_mask = reinterpret_cast<uint8_t *>(p.t_mask) + env0 * (size_t)G::A;
+        const size_t obs_step = p.n * (size_t)kRowBytes, mask_step = p.n * (size_t)G::A;
+        size_t rowi = i;
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1, steps = min(K, p.T - c * K);
+            uno_named_sync(1 + b, 64);                                   // the chunk's snapshots are written
+            for (int s = 0; s < steps; s++, rowi += p.n, o_obs += obs_step, o_mask += mask_step) {
+                if (valid) {
+                    const uint32_t *sp = snap + ((b * K + s) * kUnoSnapWords) * 32 + lane;
+                    G e;
+                    e.hc[0][0] = sp[0]; e.hc[0][1] = sp[32]; e.hc[0][2] = sp[64]; e.hc[0][3] = sp[96]; e.hw[0] = sp[128];
+                    const uint32_t meta = sp[160];
+                    const uint32_t m[2] = { sp[192], sp[224] };
+                    e.tcode = (int)(meta & 63u);
+                    e.encode_obs(0, false, row);                         // seat's words were published as seat 0
+                    stage_mask_row<G, EPW>(mtile, lane, m);
+                    st_stream(p.t_player + rowi, (int)((meta >> 8) & 1u));
+                }
+                __syncwarp();
+                tile_store_begin<EPW * G::A>(o_mask, mtile, lane);
+                tile_store_begin<kTileBytes>(o_obs, reinterpret_cast<uint8_t *>(tile), lane);
+                tile_store_end<EPW * G::A>(mtile, lane);
+                tile_store_end<kTileBytes>(reinterpret_cast<uint8_t *>(tile), lane);
+                __syncwarp();
+            }
+            if (c + 2 < nchunks) { __threadfence_block(); uno_named_arrive(3 + b, 64); }   // the buffer may be rewritten
+        }
+        return;
+    }
+
+    // ---- ENV
+    G g; EnvHeader h; ChancePhilox ch; int err = 0;
+    bool starts = false;
+    if (valid) {
+        h.load(p.state, p.n, i);
+        g.load(p.state + kHeaderWords * p.n, p.n, i);
+        ch.init(p.seed, p.env_id_base + (uint32_t)i);
+        if (h.episode == 0 || g.over()) { ch.begin_reset(h.k); h.episode++; h.t = 0; starts = true; }
+    }
+    g.warp_deal(ch, starts, lane);
+    size_t rowi = i;
+    for (int c = 0; c < nchunks; c++) {
+        const int b = c & 1, steps = min(K, p.T - c * K);
+        if (c >= 2) uno_named_sync(3 + b, 64);                           // EMIT is done with this buffer
+        for (int s = 0; s < steps; s++, rowi += p.n) {
+            uint32_t m[2] = {0u, 0u};
+            starts = false;
+            if (valid) {
+                g.legal(m);
+                uint32_t *sp = snap + ((b * K + s) * kUnoSnapWords) * 32 + lane;
+                const int seat = g.cur;
+                sp[0] = g.hcp(seat, 0); sp[32] = g.hcp(seat, 1); sp[64] = g.hcp(seat, 2); sp[96] = g.hcp(seat, 3); sp[128] = g.hwp(seat);
+                sp[160] = (uint32_t)g.tcode | ((uint32_t)seat << 8);
+                sp[192] = m[0]; sp[224] = m[1];
+                const uint32_t word = ch.begin_step(h.k);
+                int cnt;
+                const int a = pick_action<G>(m, word, cnt);
+                st_stream(p.t_action + rowi, a);
+                g.apply(a, ch, err);
+                h.t++; h.k++;
+                const bool over = g.over();
+                float pay[2] = {0.f, 0.f};
+                if (over) { g.payoffs(pay); h.episode++; h.t = 0; starts = true; }
+                p.t_done[rowi] = over ? 1 : 0;
+                st_stream(reinterpret_cast<float2 *>(p.t_payoffs) + rowi, make_float2(pay[0], pay[1]));
+            }
+            g.warp_deal(ch, starts, lane);
+        }
+        __threadfence_block();
+        uno_named_arrive(1 + b, 64);
+    }
+    if (valid) {
+        h.store(p.state, p.n, i);
+        g.store(p.state + kHeaderWords * p.n, p.n, i);
+        err |= ch.err;
+        if (err && p.err) p.err[i] |= err;
+    }
+}
+
+template <class ObsT, int EPW>
+static cudaError_t launch_uno_pipe(const KParams &p, cudaStream_t s) {
+    constexpr int kRowBytes = UnoBag::OBS * (int)sizeof(ObsT);
+    const size_t smem = (size_t)EPW * kRowBytes + ((EPW * UnoBag::A + 15) & ~15) + 2 * kUnoChunk * kUnoSnapWords * 32 * 4;
+    k_rollout_uno_pipe<ObsT, EPW><<<(unsigned)(p.n / EPW), 64, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 // throughput mode runs the multiset-pile game (UnoBag), the replay modes the ordered-pile game (Uno)
 cudaError_t dispatch_uno(int op, int chance, int obs_dtype, const KParams &p, cudaStream_t s) {
     if (chance == RLC_CHANCE_PHILOX) {
+        const char *pp = getenv("RLC_UNO_PIPE");                         // 16 / 32 = chunked env/emit kernel with that many envs per group
+        const int ppw = pp ? atoi(pp) : 0;
+        if ((ppw == 16 || ppw == 32) && op == kOpRollout && !(p.flags & kFlagNoFsm) && p.n % ppw == 0 && p.T > 0 && p.t_obs && p.t_mask &&
+            p.t_action && p.t_player && p.t_done && p.t_payoffs && obs_dtype == RLC_U8 &&
+            ((reinterpret_cast<uintptr_t>(p.t_obs) | reinterpret_cast<uintptr_t>(p.t_mask)) & 15u) == 0) {
+            if (ppw == 16) return launch_uno_pipe<uint8_t, 16>(p, s);
+            return launch_uno_pipe<uint8_t, 32>(p, s);
+        }
         const char *ee = getenv("RLC_UNO_EE");                           // 0 = generic kernel, 16 / 32 = env/emit kernel with that many envs per group
         const int epw = ee ? atoi(ee) : 0;
         if ((epw == 16 || epw == 32) && op == kOpRollout && !(p.flags & kFlagNoFsm) && p.n % epw == 0 && p.t_obs && p.t_mask &&

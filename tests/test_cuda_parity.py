@@ -490,6 +490,25 @@ def test_uno_env_emit_rollout_equals_oracle(epw, monkeypatch):
     env.check_errors()
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize('T', [60, 5])
+@pytest.mark.parametrize('epw', [16, 32])
+def test_uno_chunked_env_emit_rollout_equals_oracle(epw, T, monkeypatch):
+    """RLC_UNO_PIPE=16|32: the ENV / EMIT UNO rollout with chunked hand-over (named barriers once per 8 env-steps, tu_uno.cu) gives
+    the oracle's trajectory over two launches, for windows longer and shorter than a chunk."""
+    monkeypatch.setenv('RLC_UNO_PIPE', str(epw))
+    n, seed = 1024, 709
+    env = rlcard_b200.VecEnv('uno', n, seed=seed)
+    orc = oracle.OracleVec('uno', n, seed)
+    env.reset()
+    for launch in range(2):
+        tr = env.rollout_random(T)
+        ref = orc.rollout(T, nthreads=8)
+        for k in ('action', 'player', 'done', 'payoffs', 'mask', 'obs'):
+            assert np.array_equal(to_np(tr[k]).astype(np.float64), ref[k].astype(np.float64)), (launch, k)
+    env.check_errors()
+
+
 @pytest.mark.parametrize('bulk', [0, 1, 3])
 def test_doudizhu_bulk_row_variants_equal_oracle(bulk, monkeypatch):
     """RLC_WROLLOUT_BULK: the DouDizhu rollout with its mask row (1) or mask + obs rows (3) leaving shared memory as
