@@ -831,7 +831,9 @@ __global__ void __launch_bounds__(32 * (1 + ND + NE)) k_rollout_limit_pipe(const
                 dc.begin_episode(next);
                 g.reset(dc);                                       // deal words (episode-keyed) -> nine cards + small blind
                 const uint2 cd = limit_pack_cards(g);
-                ring[(next % RING) * 32] = make_uint2(cd.x | ((uint32_t)g.r.pointer << 30), cd.y | ((0x80u | (next & 0x7fu)) << 24));
+                // ONE 64-bit store (explicitly, not left to the compiler): ENV's 64-bit load sees the cards and their tag together
+                asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" :: "r"(smem_u32(ring + (next % RING) * 32)),
+                             "r"(cd.x | ((uint32_t)g.r.pointer << 30)), "r"(cd.y | ((0x80u | (next & 0x7fu)) << 24)) : "memory");
                 next += ND;
             }
         }
