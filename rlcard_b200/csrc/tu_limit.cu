@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(BLOCK) k_rollout_limit_fsm(const KParams p, co
 //                    a ring slot carries the episode tag in its spare byte, so ENV validates a deal with the ONE 64-bit
 //                    shared-memory load it needs anyway (no flag, no fence on its chain)
 //   EMIT  (NE warps) turn records into trajectory rows; the steps of a chunk are dealt round-robin over the EMIT warps, so the
-//                    ~120-instruction emission of one step has NE step-times to finish
+//                    ~200-instruction emission of one step has NE step-times to finish; they also stage the evaluator's
+//                    lookup tables into shared memory while ENV plays its first chunk
 // Chunks are handed over with named barriers (bar.arrive / bar.sync, ids 1..4: full[2], free[2]) -- one hand-shake per 16
 // steps instead of one per step (k_rollout_limit_ws polled a ring every step and lost what it gained).  Same state words,
 // Philox words, deals and trajectory as k_rollout_limit_fsm / k_rollout<Limit>: only the mapping of work to warps differs.
@@ -596,11 +597,6 @@ constexpr bool kPipeShortTail = RLC_PIPE_SHORT_TAIL != 0 && RLC_PIPE_POLICY == 0
 constexpr bool kPipePolicyByDeal = RLC_PIPE_POLICY != 0;   // policy words prepared by DEAL warp 0 (measured slower than four words per Philox block in ENV)
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ uint2 lds_volatile_u2(const uint2 *q) {
-    uint2 v;
-    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(q)) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *q) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(q)) : "memory");
